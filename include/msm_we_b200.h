@@ -1,0 +1,168 @@
+/*
+ * msm_we_b200 -- C ABI of the B200-native discretization + flux hot path of jdrusso/msm_we.
+ *
+ * The reference is pure Python; its "FFI" for this path is the call into scikit-learn's Cython
+ * kernels and scipy.sparse.  Each entry point below names the reference call site it replaces
+ * (paths relative to the reference root, or sklearn/ for the third-party kernels).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / Python types.
+ *   - every data pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *     unless stated; calls are re-entrant per stream (workspaces are caller-owned);
+ *   - return value: 0 on success, negative MWE_E_* otherwise; mwe_last_error() gives the text
+ *     (thread-local);
+ *   - data-dependent errors the reference raises as Python exceptions (coordinate outside the bin
+ *     space, label out of range, WE bin without centres) cannot be raised from inside a kernel:
+ *     they are counted into a caller-supplied device int32 `err_count[MWE_ERR_SLOTS]` which the
+ *     host layer reads at its next synchronisation point and converts into the reference's
+ *     exception type.
+ */
+#ifndef MSM_WE_B200_H
+#define MSM_WE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MWE_ABI_VERSION 1
+#define MWE_API __attribute__((visibility("default")))
+
+#define MWE_OK 0
+#define MWE_E_INVALID (-1)   /* bad argument                                   */
+#define MWE_E_CUDA (-2)      /* CUDA runtime error, see mwe_last_error()        */
+#define MWE_E_WORKSPACE (-3) /* workspace too small                             */
+#define MWE_E_UNSUPPORTED (-4)
+
+/* slots of the device error counter array */
+#define MWE_ERR_SLOTS 4
+#define MWE_ERR_OUT_OF_BINSPACE 0 /* westpa ValueError("coordinate outside of bin space")          */
+#define MWE_ERR_NO_CENTERS 1      /* AssertionError, msm_we/stratified_clustering.py:187-189      */
+#define MWE_ERR_LABEL_RANGE 2     /* ValueError from coo_matrix, msm_we/_hamsm/_fluxmatrix.py:147 */
+#define MWE_ERR_INTERNAL 3
+
+/* flag bits written by mwe_bin_flags_f64 */
+#define MWE_FLAG_BASIS 1u
+#define MWE_FLAG_TARGET 2u
+
+/* mapper kinds */
+#define MWE_MAPPER_RECTILINEAR 0
+#define MWE_MAPPER_VORONOI 1
+#define MWE_MAPPER_PRECOMPUTED 2
+
+/* precision paths of the assignment kernel */
+#define MWE_ASSIGN_FP64 0      /* fp64 tensor (DMMA) distances, the parity path                    */
+#define MWE_ASSIGN_TF32X3 1    /* tcgen05 split-TF32 candidate pass + fp64 re-check of near-ties   */
+
+MWE_API int mwe_abi_version(void);
+MWE_API const char* mwe_last_error(void);
+/* number of SMs of the current device (grid sizing is done inside the library) */
+MWE_API int mwe_device_sm_count(void);
+
+/* ---- K0: WE-bin lookup + basis/target flags -------------------------------------------------
+ * Replaces bin_mapper.assign(pcoords) + we_remap (msm_we/stratified_clustering.py:134-135,
+ * msm_we/_hamsm/_clustering.py:877) and modelWE.is_WE_basis / is_WE_target
+ * (msm_we/msm_we.py:462-527; call sites stratified_clustering.py:137-138, _fluxmatrix.py:33-53).
+ *   pcoord      [N, P] f64 row-major
+ *   mapper_kind MWE_MAPPER_RECTILINEAR: mapper_data = all boundaries concatenated (float32, as
+ *               westpa stores them), mapper_lens_host[P] (HOST) = boundary count per dimension;
+ *               MWE_MAPPER_VORONOI: mapper_data = centres [nbins, P] float32 (Euclidean dfunc);
+ *               MWE_MAPPER_PRECOMPUTED: bin_out already holds the raw bin of every point (a host
+ *               mapper produced it); only we_remap and the flags are applied.
+ *   basis_lohi_host / target_lohi_host [P, 2] f64 (HOST, passed to the kernel by value), strict
+ *               lo < p < hi on every dimension.
+ *   we_remap    [nbins] int32 (nullable = identity)
+ *   bin_out     [N] int32 remapped WE bin; flag_out [N] uint8 (MWE_FLAG_* bits)
+ *   bin_count   nullable [nbins] int32, += number of points with flag == 0 in each bin
+ */
+MWE_API int mwe_bin_flags_f64(const double* pcoord, int64_t N, int P, int mapper_kind, const float* mapper_data,
+                      const int32_t* mapper_lens_host, int32_t nbins, const double* basis_lohi_host,
+                      const double* target_lohi_host, const int32_t* we_remap, int32_t* bin_out, uint8_t* flag_out,
+                      int32_t* bin_count, int32_t* err_count, void* stream);
+
+/* ---- K1: stratified nearest-centre assignment -----------------------------------------------
+ * Replaces the per-segment MiniBatchKMeans.predict([coord]) loop of StratifiedClusters.predict
+ * (msm_we/stratified_clustering.py:152-203) and the E step of partial_fit / KMeans.fit
+ * (sklearn/cluster/_k_means_lloyd.pyx:168-218: ||c||^2 - 2 x.c, strict-< argmin, lowest index).
+ *   X [N, D] f64, row stride ldx (elements); bin/flag from K0 (flag nullable = all free);
+ *   centers [sumK, D] f64 all bins concatenated; csq [sumK] = row squared norms
+ *   (mwe_centers_sqnorm_f64); bin_offset [nbins+1] int64 prefix of per-bin centre counts.
+ *   label_out [N] int64: target -> T+1, basis -> T (target tested first), else
+ *   bin_offset[bin] + argmin, T = bin_offset[nbins]   (stratified_clustering.py:143-196).
+ *   local_out  nullable [N] int32: argmin local to the bin (what partial_fit's E step needs).
+ */
+MWE_API size_t mwe_assign_workspace_bytes(int64_t N, int32_t nbins);
+MWE_API int mwe_centers_sqnorm_f64(const double* centers, int64_t sumK, int D, double* csq, void* stream);
+MWE_API int mwe_assign_stratified_f64(const double* X, int64_t N, int D, int64_t ldx, const int32_t* bin,
+                              const uint8_t* flag, const double* centers, const double* csq,
+                              const int64_t* bin_offset, int32_t nbins, int32_t max_k, int precision_path,
+                              int64_t* label_out, int32_t* local_out, void* workspace, size_t workspace_bytes,
+                              int32_t* err_count, void* stream);
+
+/* ---- K2: centroid accumulation / update -----------------------------------------------------
+ * Replaces update_center_dense (sklearn/cluster/_k_means_minibatch.pyx:59-111, reached from
+ * msm_we/_hamsm/_clustering.py:909) and the M step of lloyd_iter_chunked_dense
+ * (sklearn/cluster/_k_means_lloyd.pyx:23-165, reached from _clustering.py:289,491).
+ * Deterministic: points are grouped by label with a stable sort and every cluster's rows are
+ * summed in original index order (the order the single-threaded reference uses).
+ *   label [N] int64 global cluster index in [0, sumK); entries outside are skipped
+ *   (basis/target points).  w nullable (= 1).
+ *   mwe_centroid_accumulate_f64: sum_wx [sumK, D], sum_w [sumK] are OVERWRITTEN with the sums
+ *   (these are the buffers a multi-GPU run all-reduces).
+ *   mwe_minibatch_update_f64: centers/counts updated in place with the running-mean rule,
+ *   starting each sum from centers*counts exactly as the reference does.
+ *   mwe_lloyd_finalize_f64 / mwe_minibatch_finalize_f64: apply the rule to reduced partial sums.
+ */
+MWE_API size_t mwe_centroid_workspace_bytes(int64_t N, int64_t sumK);
+MWE_API int mwe_centroid_accumulate_f64(const double* X, int64_t N, int D, int64_t ldx, const double* w,
+                                const int64_t* label, int64_t sumK, double* sum_wx, double* sum_w,
+                                void* workspace, size_t workspace_bytes, void* stream);
+MWE_API int mwe_minibatch_update_f64(const double* X, int64_t N, int D, int64_t ldx, const double* w,
+                             const int64_t* label, int64_t sumK, double* centers, double* counts,
+                             void* workspace, size_t workspace_bytes, void* stream);
+MWE_API int mwe_lloyd_finalize_f64(const double* sum_wx, const double* sum_w, int64_t sumK, int D, double* centers,
+                           void* stream);
+MWE_API int mwe_minibatch_finalize_f64(const double* sum_wx, const double* sum_w, int64_t sumK, int D, double* centers,
+                               double* counts, void* stream);
+
+/* ---- K3: weighted transition scatter into the flux matrix -----------------------------------
+ * Replaces FluxMatrixMixin.build_flux_matrix + .todense() + the per-iteration accumulation of
+ * get_fluxMatrix (msm_we/_hamsm/_fluxmatrix.py:97-164, 61-72, 232-260, 311-342) and the coloured
+ * count scatter of NonMarkovModel.fit (msm_we/nmm.py:132-158).
+ *   start/end [N] int64 cluster labels of parent and child; flag0/flag1 [N] uint8 from K0 on
+ *   pcoord0 / pcoord1 (nullable): end[target]=n+1, start[basis]=n, end[basis]=n in that order
+ *   (_fluxmatrix.py:135-137).  col0/col1 nullable uint8 history colours (C=2):
+ *   row = C*start+col0, col = C*end+col1 (nmm.py:147-154).  w nullable (= 1.0).
+ *   Matrix side: CM = C*(n_clusters+2).  Labels outside [0, n_clusters+2) count an
+ *   MWE_ERR_LABEL_RANGE error and are dropped.
+ *   The transitions are stably sorted by (row, col); every cell is summed in input order --
+ *   per iteration first and then across iterations when iter_offsets [n_iters+1] is given,
+ *   which is the association of the reference's serial path -- so the result does not depend on
+ *   thread scheduling.
+ *   dense_inout nullable [CM, CM] f64: cell += sum.  coo_* nullable: sorted unique (row, col, sum),
+ *   *nnz_out (device int64) = count; coo capacity must be >= N.
+ */
+MWE_API size_t mwe_flux_workspace_bytes(int64_t N);
+MWE_API int mwe_flux_accumulate_f64(const int64_t* start, const int64_t* end, const uint8_t* flag0, const uint8_t* flag1,
+                            const uint8_t* col0, const uint8_t* col1, const double* w, int64_t N,
+                            int64_t n_clusters, int C, const int64_t* iter_offsets, int64_t n_iters,
+                            double* dense_inout, int64_t* coo_row, int64_t* coo_col, double* coo_val,
+                            int64_t* nnz_out, void* workspace, size_t workspace_bytes, int32_t* err_count,
+                            void* stream);
+/* buf[i] = buf[i] / divisor      (fluxMatrix / nI, _fluxmatrix.py:342) */
+MWE_API int mwe_divide_f64(double* buf, int64_t count, double divisor, void* stream);
+
+/* ---- shared primitive, exported for tests ---------------------------------------------------
+ * Stable LSD radix sort of (key, value) pairs on the low `key_bits` bits of the key.
+ * keys/vals are sorted in place (a ping-pong copy lives in the workspace). */
+MWE_API size_t mwe_sort_workspace_bytes(int64_t N);
+MWE_API int mwe_sort_pairs_u64_u32(uint64_t* keys, uint32_t* vals, int64_t N, int key_bits, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSM_WE_B200_H */

@@ -1,0 +1,496 @@
+// K1: stratified nearest-centre assignment, fp64 parity path (DMMA tensor pipe).
+//
+// reference: StratifiedClusters.predict (msm_we/stratified_clustering.py:101-212) whose inner
+// call is MiniBatchKMeans.predict([coord]) -> sklearn/cluster/_k_means_lloyd.pyx:168-218:
+//     score[j] = ||c_j||^2 - 2 x.c_j ;  label = first j with the smallest score (strict <).
+//
+// Design.  Points of one WE bin only ever meet that bin's K_b centres, so the points are first
+// bucketed by bin (count -> scan -> scatter of indices, order inside a bucket is irrelevant
+// because every point's label is computed independently).  A tile is 64 points of ONE bin; the
+// x.c products of a tile are a [64 x K_b x D] GEMM run on the fp64 tensor pipe
+// (mma.sync.m8n8k4.f64 -> SASS DMMA): warp w owns points [16w, 16w+16) x all centres of the block,
+// accumulators stay in registers, the argmin epilogue is fused (quad shuffles), and no distance
+// matrix ever reaches HBM.  One producer warp streams k-chunks of the gathered point rows and of
+// the bin's centre rows into a 3-stage shared-memory ring with cp.async (zero-filling tails) and
+// signals mbarriers; four consumer warps issue the DMMAs.  The grid is persistent
+// (multiple of the SM count) and the ring runs across tile boundaries, so short-D tiles
+// (D=64 is two chunks) do not drain the pipeline.
+//
+// Algorithmic traffic per point: D*8 bytes of features (+4 B bucket index, +8 B label); centres
+// are re-read from L2.  FLOPs per point: 2*K_b*D.
+#include "common.cuh"
+#include "sort.cuh"
+
+namespace mwe {
+
+static constexpr int AS_TP = 64;                // points per tile
+static constexpr int AS_CWARPS = 4;             // consumer warps, 16 points each
+static constexpr int AS_THREADS = (AS_CWARPS + 1) * 32;
+static constexpr int AS_DC = 32;                // doubles per k-chunk
+static constexpr int AS_LD = AS_DC + 4;         // padded row: 72 words == 8 (mod 32): conflict-free LDS.64 fragments
+static constexpr int AS_STAGES = 3;
+static constexpr int AS_SPIN_LIMIT = 1 << 26;
+
+// ---- bucketing -----------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+    assign_count_kernel(const int32_t* __restrict__ bin, const uint8_t* __restrict__ flag, int64_t N, int32_t nbins,
+                        const int64_t* __restrict__ bin_offset, int64_t* __restrict__ label_out,
+                        int32_t* __restrict__ local_out, int32_t* __restrict__ bin_count) {
+    const int64_t T = bin_offset[nbins];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        const uint8_t f = flag ? flag[i] : (uint8_t)0;
+        const int32_t b = bin[i];
+        if (f) {
+            // target is tested before basis (stratified_clustering.py:159-169)
+            label_out[i] = (f & MWE_FLAG_TARGET) ? T + 1 : T;
+            if (local_out) local_out[i] = -1;
+        } else if (b < 0 || b >= nbins) {
+            label_out[i] = -1;
+            if (local_out) local_out[i] = -1;
+        } else {
+            // warp-aggregated count
+            const uint32_t peers = __match_any_sync(__activemask(), b);
+            if ((peers & ((1u << lane_id()) - 1u)) == 0) atomicAdd(&bin_count[b], __popc(peers));
+        }
+    }
+}
+
+// one CTA: bucket starts, per-bin tile prefix, cursors; flags bins that hold points but no centres
+__global__ void __launch_bounds__(256)
+    assign_scan_kernel(const int32_t* __restrict__ bin_count, const int64_t* __restrict__ bin_offset, int32_t nbins,
+                       int32_t* __restrict__ bin_start, int32_t* __restrict__ bin_cursor,
+                       int32_t* __restrict__ tile_prefix, int32_t* __restrict__ err_count) {
+    __shared__ int scratch[9];
+    __shared__ int s_carry[2];
+    if (threadIdx.x == 0) { s_carry[0] = 0; s_carry[1] = 0; }
+    __syncthreads();
+    for (int base = 0; base < nbins; base += 256) {
+        const int b = base + threadIdx.x;
+        int cnt = 0, tiles = 0;
+        if (b < nbins) {
+            cnt = bin_count[b];
+            const int64_t kb = bin_offset[b + 1] - bin_offset[b];
+            if (cnt > 0 && kb <= 0) {
+                atomicAdd(&err_count[MWE_ERR_NO_CENTERS], cnt);
+                tiles = 0;
+            } else {
+                tiles = (cnt + AS_TP - 1) / AS_TP;
+            }
+        }
+        int tot_c, tot_t;
+        const int ex_c = block_excl_scan_256(cnt, scratch, &tot_c);
+        const int ex_t = block_excl_scan_256(tiles, scratch, &tot_t);
+        const int c0 = s_carry[0], c1 = s_carry[1];
+        if (b < nbins) {
+            bin_start[b] = c0 + ex_c;
+            bin_cursor[b] = c0 + ex_c;
+            tile_prefix[b] = c1 + ex_t;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { s_carry[0] = c0 + tot_c; s_carry[1] = c1 + tot_t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        bin_start[nbins] = s_carry[0];
+        tile_prefix[nbins] = s_carry[1];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    assign_scatter_kernel(const int32_t* __restrict__ bin, const uint8_t* __restrict__ flag, int64_t N, int32_t nbins,
+                          int32_t* __restrict__ bin_cursor, int32_t* __restrict__ perm) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        const uint8_t f = flag ? flag[i] : (uint8_t)0;
+        const int32_t b = bin[i];
+        if (!f && b >= 0 && b < nbins) {
+            const uint32_t peers = __match_any_sync(__activemask(), b);
+            const uint32_t lt = peers & ((1u << lane_id()) - 1u);
+            const int leader = __ffs(peers) - 1;
+            int base = 0;
+            if (lt == 0) base = atomicAdd(&bin_cursor[b], __popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            perm[base + __popc(lt)] = (int32_t)i;
+        }
+    }
+}
+
+// ---- PTX helpers -----------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    int spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (++spins > AS_SPIN_LIMIT) __trap();  // never hang the GPU on a protocol bug
+    }
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int VEC>
+__device__ __forceinline__ void cp_async_zfill(void* dst, const void* src, int src_bytes) {
+    if (VEC == 2) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+    } else {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+    }
+}
+__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+struct AssignParams {
+    const double* X;
+    int64_t ldx;
+    int D;
+    const double* centers;
+    const double* csq;
+    const int64_t* bin_offset;
+    int32_t nbins;
+    const int32_t* perm;
+    const int32_t* bin_start;
+    const int32_t* tile_prefix;
+    int64_t* label_out;
+    int32_t* local_out;
+    int ncb;  // centre blocks of NT*8 per tile
+    int nch;  // k-chunks of AS_DC per centre block
+};
+
+// tile -> bin lookup; tiles handled by one CTA are increasing, so scan forward from the last bin
+struct TileCursor {
+    int32_t bin;
+    __device__ __forceinline__ void seek(const int32_t* __restrict__ tile_prefix, int32_t nbins, int32_t tile) {
+        while (bin + 1 < nbins && tile >= tile_prefix[bin + 1]) ++bin;
+    }
+};
+
+template <int NT, int VEC>
+__global__ void __launch_bounds__(AS_THREADS) assign_dmma_kernel(const AssignParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int CROWS = NT * 8;
+    constexpr int STAGE_DOUBLES = (AS_TP + CROWS) * AS_LD;
+    double* stage_base = reinterpret_cast<double*>(smem_raw);
+    __shared__ uint64_t full_bar[AS_STAGES];
+    __shared__ uint64_t empty_bar[AS_STAGES];
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < AS_STAGES; ++s) {
+            mbar_init(&full_bar[s], 32);         // every producer lane arrives (cp.async ... noinc)
+            mbar_init(&empty_bar[s], AS_CWARPS); // one elected lane per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int32_t n_tiles = p.tile_prefix[p.nbins];
+    const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int spt = p.ncb * p.nch;  // pipeline steps per tile
+    const int64_t total_steps = (int64_t)my_tiles * spt;
+
+    if (warp == AS_CWARPS) {
+        // ===================== producer warp =====================
+        constexpr int SEGS = AS_DC / VEC;       // copies per row chunk
+        constexpr int RPI = 32 / SEGS;          // rows covered by one warp-wide copy instruction
+        const int seg = lane % SEGS;
+        const int rsub = lane / SEGS;
+        TileCursor cur{0};
+        int32_t perm_lo = 0, perm_hi = 0;
+        int32_t pcount = 0;
+        int64_t coff = 0;
+        int32_t kb = 0;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int64_t step = 0; step < total_steps; ++step) {
+            const int ti = (int)(step / spt);
+            const int rem = (int)(step - (int64_t)ti * spt);
+            const int cb = rem / p.nch;
+            const int kc = rem - cb * p.nch;
+            if (rem == 0) {
+                const int32_t tile = (int32_t)blockIdx.x + ti * (int32_t)gridDim.x;
+                cur.seek(p.tile_prefix, p.nbins, tile);
+                const int32_t b = cur.bin;
+                const int32_t in_bin = (tile - p.tile_prefix[b]) * AS_TP;
+                const int32_t pstart = p.bin_start[b] + in_bin;
+                const int32_t bcount = p.bin_start[b + 1] - p.bin_start[b];
+                pcount = min(AS_TP, bcount - in_bin);
+                coff = p.bin_offset[b];
+                kb = (int32_t)(p.bin_offset[b + 1] - coff);
+                perm_lo = (lane < pcount) ? p.perm[pstart + lane] : -1;
+                perm_hi = (lane + 32 < pcount) ? p.perm[pstart + lane + 32] : -1;
+            }
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            double* sX = stage_base + (size_t)stage * STAGE_DOUBLES;
+            double* sC = sX + AS_TP * AS_LD;
+            const int k0 = kc * AS_DC;
+            const int kcol = k0 + seg * VEC;
+            int vbytes = (p.D - kcol) * 8;
+            vbytes = vbytes < 0 ? 0 : (vbytes > VEC * 8 ? VEC * 8 : vbytes);
+            // point rows
+#pragma unroll 4
+            for (int r0 = 0; r0 < AS_TP; r0 += RPI) {
+                const int r = r0 + rsub;
+                const int32_t idx = __shfl_sync(0xffffffffu, (r < 32) ? perm_lo : perm_hi, r & 31);
+                const bool ok = idx >= 0;
+                const double* src = ok ? (p.X + (int64_t)idx * p.ldx + kcol) : p.X;
+                cp_async_zfill<VEC>(sX + r * AS_LD + seg * VEC, src, ok ? vbytes : 0);
+            }
+            // centre rows of this block
+#pragma unroll 4
+            for (int r0 = 0; r0 < CROWS; r0 += RPI) {
+                const int r = r0 + rsub;
+                const int c = cb * CROWS + r;
+                const bool ok = c < kb;
+                const double* src = ok ? (p.centers + (coff + c) * p.D + kcol) : p.centers;
+                cp_async_zfill<VEC>(sC + r * AS_LD + seg * VEC, src, ok ? vbytes : 0);
+            }
+            cp_async_arrive_noinc(&full_bar[stage]);
+            if (++stage == AS_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        // drain outstanding copies before the CTA may exit
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    } else {
+        // ===================== consumer warps =====================
+        const int g = lane >> 2;  // fragment row / column group
+        const int t = lane & 3;   // position inside the k4 step
+        TileCursor cur{0};
+        int stage = 0;
+        uint32_t phase = 0;
+        double acc[2][NT][2];
+        double best[2] = {0.0, 0.0};
+        int32_t besti[2] = {0, 0};
+        int32_t pstart = 0, pcount = 0, kb = 0;
+        int64_t coff = 0;
+        for (int64_t step = 0; step < total_steps; ++step) {
+            const int ti = (int)(step / spt);
+            const int rem = (int)(step - (int64_t)ti * spt);
+            const int cb = rem / p.nch;
+            const int kc = rem - cb * p.nch;
+            if (rem == 0) {
+                const int32_t tile = (int32_t)blockIdx.x + ti * (int32_t)gridDim.x;
+                cur.seek(p.tile_prefix, p.nbins, tile);
+                const int32_t b = cur.bin;
+                const int32_t in_bin = (tile - p.tile_prefix[b]) * AS_TP;
+                pstart = p.bin_start[b] + in_bin;
+                pcount = min(AS_TP, (p.bin_start[b + 1] - p.bin_start[b]) - in_bin);
+                coff = p.bin_offset[b];
+                kb = (int32_t)(p.bin_offset[b + 1] - coff);
+                best[0] = best[1] = __longlong_as_double(0x7ff0000000000000ll);  // +inf
+                besti[0] = besti[1] = 0;
+            }
+            if (kc == 0) {
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+            }
+            mbar_wait(&full_bar[stage], phase);
+            const double* sX = stage_base + (size_t)stage * STAGE_DOUBLES;
+            const double* sC = sX + AS_TP * AS_LD;
+            const double* xa0 = sX + (warp * 16 + g) * AS_LD + t;
+            const double* xa1 = xa0 + 8 * AS_LD;
+            const double* cb0 = sC + g * AS_LD + t;
+#pragma unroll
+            for (int ks = 0; ks < AS_DC / 4; ++ks) {
+                const double a0 = xa0[ks * 4];
+                const double a1 = xa1[ks * 4];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const double bv = cb0[nt * 8 * AS_LD + ks * 4];
+                    dmma8x8x4(acc[0][nt][0], acc[0][nt][1], a0, bv);
+                    dmma8x8x4(acc[1][nt][0], acc[1][nt][1], a1, bv);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            if (++stage == AS_STAGES) { stage = 0; phase ^= 1u; }
+
+            if (kc == p.nch - 1) {
+                // fold this centre block into the running argmin: score = ||c||^2 - 2 x.c
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int c = cb * CROWS + nt * 8 + 2 * t + j;
+                        if (c < kb) {
+                            const double cs = p.csq[coff + c];
+#pragma unroll
+                            for (int mt = 0; mt < 2; ++mt) {
+                                const double s = fma(-2.0, acc[mt][nt][j], cs);
+                                if (s < best[mt]) { best[mt] = s; besti[mt] = c; }
+                            }
+                        }
+                    }
+                if (cb == p.ncb - 1) {
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        double bs = best[mt];
+                        int32_t bi = besti[mt];
+                        // first column of the block seeds the scan in the reference; emulate its
+                        // "first minimum wins" across the 4 lanes of the quad
+#pragma unroll
+                        for (int o = 1; o <= 2; o <<= 1) {
+                            const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+                            const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                            if (os < bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
+                        }
+                        const int r = warp * 16 + mt * 8 + g;
+                        if (t == 0 && r < pcount) {
+                            const int32_t pt = p.perm[pstart + r];
+                            p.label_out[pt] = coff + bi;
+                            if (p.local_out) p.local_out[pt] = bi;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) centers_sqnorm_kernel(const double* __restrict__ centers, int64_t sumK, int D,
+                                                            double* __restrict__ csq) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (row >= sumK) return;
+    const double* c = centers + row * D;
+    double s = 0.0;
+    for (int k = lane_id(); k < D; k += 32) s = fma(c[k], c[k], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane_id() == 0) csq[row] = s;
+}
+
+struct AssignWs {
+    int32_t* perm;
+    int32_t* bin_count;
+    int32_t* bin_cursor;
+    int32_t* bin_start;
+    int32_t* tile_prefix;
+};
+
+static size_t assign_ws_bytes(int64_t N, int32_t nbins) {
+    size_t b = 0;
+    b += align_up((size_t)(N > 0 ? N : 1) * sizeof(int32_t), 256);
+    b += 4 * align_up((size_t)(nbins + 1) * sizeof(int32_t), 256);
+    return b + 1024;
+}
+
+template <int NT, int VEC>
+static int launch_assign(const AssignParams& p, int64_t max_tiles, cudaStream_t stream) {
+    constexpr size_t smem = (size_t)AS_STAGES * (AS_TP + NT * 8) * AS_LD * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        MWE_CHECK_CUDA(cudaFuncSetAttribute(assign_dmma_kernel<NT, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int occ = 1;
+    MWE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, assign_dmma_kernel<NT, VEC>, AS_THREADS, smem));
+    if (occ < 1) occ = 1;
+    int64_t grid = (int64_t)sm_count() * occ;
+    if (grid > max_tiles) grid = max_tiles;
+    if (grid < 1) grid = 1;
+    assign_dmma_kernel<NT, VEC><<<(unsigned)grid, AS_THREADS, smem, stream>>>(p);
+    MWE_CHECK_LAUNCH();
+    return MWE_OK;
+}
+
+template <int VEC>
+static int dispatch_nt(int nt, const AssignParams& p, int64_t max_tiles, cudaStream_t stream) {
+    switch (nt) {
+        case 2: return launch_assign<2, VEC>(p, max_tiles, stream);
+        case 3: return launch_assign<3, VEC>(p, max_tiles, stream);
+        case 4: return launch_assign<4, VEC>(p, max_tiles, stream);
+        case 7: return launch_assign<7, VEC>(p, max_tiles, stream);
+        case 8: return launch_assign<8, VEC>(p, max_tiles, stream);
+        case 13: return launch_assign<13, VEC>(p, max_tiles, stream);
+        default: return launch_assign<16, VEC>(p, max_tiles, stream);
+    }
+}
+
+}  // namespace mwe
+
+extern "C" size_t mwe_assign_workspace_bytes(int64_t N, int32_t nbins) { return mwe::assign_ws_bytes(N, nbins); }
+
+extern "C" int mwe_centers_sqnorm_f64(const double* centers, int64_t sumK, int D, double* csq, void* stream) {
+    MWE_REQUIRE(sumK >= 0 && D >= 1, "centers_sqnorm: bad shape");
+    if (sumK == 0) return MWE_OK;
+    const int64_t blocks = (sumK + 7) / 8;
+    mwe::centers_sqnorm_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(centers, sumK, D, csq);
+    MWE_CHECK_LAUNCH();
+    return MWE_OK;
+}
+
+extern "C" int mwe_assign_stratified_f64(const double* X, int64_t N, int D, int64_t ldx, const int32_t* bin,
+                                         const uint8_t* flag, const double* centers, const double* csq,
+                                         const int64_t* bin_offset, int32_t nbins, int32_t max_k, int precision_path,
+                                         int64_t* label_out, int32_t* local_out, void* workspace,
+                                         size_t workspace_bytes, int32_t* err_count, void* stream) {
+    using namespace mwe;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    MWE_REQUIRE(N >= 0 && N < ((int64_t)1 << 31), "assign: N must be < 2^31 per call");
+    MWE_REQUIRE(D >= 1 && ldx >= D, "assign: bad D / ldx");
+    MWE_REQUIRE(nbins >= 1 && max_k >= 1, "assign: bad nbins / max_k");
+    MWE_REQUIRE(bin && centers && csq && bin_offset && label_out && err_count, "assign: null pointer");
+    if (precision_path != MWE_ASSIGN_FP64) {
+        set_last_error("assign: precision path %d is not built in this version", precision_path);
+        return MWE_E_UNSUPPORTED;
+    }
+    if (N == 0) return MWE_OK;
+    if (workspace_bytes < assign_ws_bytes(N, nbins)) {
+        set_last_error("assign: workspace too small (%zu < %zu)", workspace_bytes, assign_ws_bytes(N, nbins));
+        return MWE_E_WORKSPACE;
+    }
+    Carver cv(workspace, workspace_bytes);
+    AssignWs ws;
+    ws.perm = cv.take<int32_t>((size_t)N);
+    ws.bin_count = cv.take<int32_t>((size_t)nbins + 1);
+    ws.bin_cursor = cv.take<int32_t>((size_t)nbins + 1);
+    ws.bin_start = cv.take<int32_t>((size_t)nbins + 1);
+    ws.tile_prefix = cv.take<int32_t>((size_t)nbins + 1);
+
+    MWE_CHECK_CUDA(cudaMemsetAsync(ws.bin_count, 0, (size_t)(nbins + 1) * sizeof(int32_t), s));
+    int64_t blocks = (N + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    assign_count_kernel<<<(unsigned)blocks, 256, 0, s>>>(bin, flag, N, nbins, bin_offset, label_out, local_out, ws.bin_count);
+    assign_scan_kernel<<<1, 256, 0, s>>>(ws.bin_count, bin_offset, nbins, ws.bin_start, ws.bin_cursor, ws.tile_prefix, err_count);
+    assign_scatter_kernel<<<(unsigned)blocks, 256, 0, s>>>(bin, flag, N, nbins, ws.bin_cursor, ws.perm);
+    MWE_CHECK_LAUNCH();
+
+    // centre-block width: smallest instantiated NT covering max_k, capped at 16 (128 centres / block)
+    static const int nts[] = {2, 3, 4, 7, 8, 13, 16};
+    int nt = 16;
+    for (int i = 0; i < 7; ++i)
+        if (nts[i] * 8 >= max_k) { nt = nts[i]; break; }
+    AssignParams p;
+    p.X = X; p.ldx = ldx; p.D = D; p.centers = centers; p.csq = csq; p.bin_offset = bin_offset; p.nbins = nbins;
+    p.perm = ws.perm; p.bin_start = ws.bin_start; p.tile_prefix = ws.tile_prefix;
+    p.label_out = label_out; p.local_out = local_out;
+    p.ncb = (max_k + nt * 8 - 1) / (nt * 8);
+    p.nch = (D + AS_DC - 1) / AS_DC;
+    const int64_t max_tiles = (N + AS_TP - 1) / AS_TP + nbins;
+    const bool vec2 = (D % 2 == 0) && (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(centers) & 15) == 0);
+    return vec2 ? dispatch_nt<2>(nt, p, max_tiles, s) : dispatch_nt<1>(nt, p, max_tiles, s);
+}

@@ -1,0 +1,97 @@
+// Shared helpers for the msm_we_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/msm_we_b200.h"
+
+namespace mwe {
+
+void set_last_error(const char* fmt, ...);
+int sm_count();
+
+#define MWE_CHECK_CUDA(expr)                                                                   \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            mwe::set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return MWE_E_CUDA;                                                                 \
+        }                                                                                      \
+    } while (0)
+
+#define MWE_CHECK_LAUNCH()                                                                     \
+    do {                                                                                       \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess) {                                                               \
+            mwe::set_last_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return MWE_E_CUDA;                                                                 \
+        }                                                                                      \
+    } while (0)
+
+#define MWE_REQUIRE(cond, msg)                                                                 \
+    do {                                                                                       \
+        if (!(cond)) {                                                                         \
+            mwe::set_last_error("%s:%d: %s", __FILE__, __LINE__, msg);                         \
+            return MWE_E_INVALID;                                                              \
+        }                                                                                      \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over a caller-owned workspace.
+struct Carver {
+    char* base;
+    size_t off;
+    size_t cap;
+    Carver(void* p, size_t bytes) : base(static_cast<char*>(p)), off(0), cap(bytes) {}
+    template <typename T>
+    T* take(size_t count) {
+        off = align_up(off, 256);
+        T* r = reinterpret_cast<T*>(base + off);
+        off += count * sizeof(T);
+        return r;
+    }
+    bool ok() const { return off <= cap; }
+};
+
+static inline int ceil_log2_u64(uint64_t x) {  // smallest b with 2^b >= x
+    int b = 0;
+    while (b < 64 && ((uint64_t)1 << b) < x) ++b;
+    return b;
+}
+
+// ---- device helpers -----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// exclusive scan of one int per thread across a 256-thread block; returns exclusive prefix and
+// writes the block total to *total (same for all threads). scratch: 9 ints of shared memory.
+__device__ __forceinline__ int block_excl_scan_256(int v, int* scratch, int* total) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += n;
+    }
+    if (lane == 31) scratch[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int s = (lane < 8) ? scratch[lane] : 0;
+        int si = s;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            int n = __shfl_up_sync(0xffffffffu, si, o);
+            if (lane >= (uint32_t)o) si += n;
+        }
+        if (lane < 8) scratch[lane] = si - s;  // exclusive warp base
+        if (lane == 7) scratch[8] = si;
+    }
+    __syncthreads();
+    int r = scratch[warp] + inc - v;
+    *total = scratch[8];
+    __syncthreads();
+    return r;
+}
+
+}  // namespace mwe

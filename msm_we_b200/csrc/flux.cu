@@ -1,0 +1,181 @@
+// K3: weighted transition scatter into the flux matrix, order-deterministic.
+//
+// reference: FluxMatrixMixin.build_flux_matrix (msm_we/_hamsm/_fluxmatrix.py:97-164: relabel
+// end[target]=n+1, start[basis]=n, end[basis]=n, then scipy coo_matrix which sums duplicates in
+// input order), the per-iteration dense accumulation of get_fluxMatrix (:232-260) and the
+// history-coloured count scatter of NonMarkovModel.fit (msm_we/nmm.py:132-158,
+// row = 2*s_prev + colour_prev, col = 2*s_now + colour_now).
+//
+// One launch sequence covers every transition of every iteration of the shard:
+//   keys    : cell = (C*start+c0)*CM + (C*end+c1) after the basis/target overrides; bad labels get
+//             a sentinel cell that sorts last and is dropped
+//   sort    : stable LSD radix sort by cell (radix_sort.cu), value = transition index, so inside a
+//             cell the transitions stay in (iteration, segment) order
+//   segsum  : the thread at the head of each run of equal cells adds the weights in that order --
+//             per iteration first, then across iterations when iteration offsets are given, which
+//             is exactly the association of the reference's serial path -- and performs the single
+//             write of that cell (dense += or one COO triple).  No floating-point atomics anywhere.
+// Integer/HBM-bound: algorithmic bytes per transition = 2*8 (labels) + 8 (weight) [+2 flags +2 colours].
+#include "common.cuh"
+#include "sort.cuh"
+
+namespace mwe {
+
+__global__ void __launch_bounds__(256)
+    flux_keys_kernel(const int64_t* __restrict__ start, const int64_t* __restrict__ end,
+                     const uint8_t* __restrict__ flag0, const uint8_t* __restrict__ flag1,
+                     const uint8_t* __restrict__ col0, const uint8_t* __restrict__ col1, int64_t N, int64_t n_clusters,
+                     int C, uint64_t sentinel, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                     int32_t* __restrict__ err_count) {
+    const int64_t M = n_clusters + 2;
+    const uint64_t CM = (uint64_t)C * (uint64_t)M;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        int64_t s = start[i], e = end[i];
+        const uint8_t f0 = flag0 ? flag0[i] : (uint8_t)0;
+        const uint8_t f1 = flag1 ? flag1[i] : (uint8_t)0;
+        // override order of _fluxmatrix.py:135-137 (a child in both regions ends up in the basis)
+        if (f1 & MWE_FLAG_TARGET) e = n_clusters + 1;
+        if (f0 & MWE_FLAG_BASIS) s = n_clusters;
+        if (f1 & MWE_FLAG_BASIS) e = n_clusters;
+        uint64_t key = sentinel;
+        if (s < 0 || s >= M || e < 0 || e >= M) {
+            atomicAdd(&err_count[MWE_ERR_LABEL_RANGE], 1);
+        } else {
+            const uint64_t c0 = col0 ? (uint64_t)col0[i] : 0ull;
+            const uint64_t c1 = col1 ? (uint64_t)col1[i] : 0ull;
+            if (c0 >= (uint64_t)C || c1 >= (uint64_t)C) atomicAdd(&err_count[MWE_ERR_LABEL_RANGE], 1);
+            else key = ((uint64_t)C * (uint64_t)s + c0) * CM + ((uint64_t)C * (uint64_t)e + c1);
+        }
+        keys[i] = key;
+        vals[i] = (uint32_t)i;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    flux_heads_kernel(const uint64_t* __restrict__ keys, int64_t N, uint64_t sentinel, int32_t* __restrict__ head) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        const uint64_t k = keys[i];
+        head[i] = (k != sentinel && (i == 0 || keys[i - 1] != k)) ? 1 : 0;
+    }
+}
+
+// iteration that owns transition idx: largest it with offsets[it] <= idx
+__device__ __forceinline__ int64_t find_iter(const int64_t* __restrict__ offsets, int64_t n_iters, int64_t idx) {
+    int64_t lo = 0, hi = n_iters;  // answer in [lo, hi)
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= idx) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256)
+    flux_segsum_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t N,
+                       uint64_t sentinel, const double* __restrict__ w, const int64_t* __restrict__ iter_offsets,
+                       int64_t n_iters, uint64_t CM, double* __restrict__ dense, const int32_t* __restrict__ head_pos,
+                       int64_t* __restrict__ coo_row, int64_t* __restrict__ coo_col, double* __restrict__ coo_val) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        const uint64_t k = keys[i];
+        if (k == sentinel) continue;
+        if (i > 0 && keys[i - 1] == k) continue;  // not a run head
+        double total = 0.0;
+        double part = 0.0;
+        int64_t it_end = -1;  // exclusive end (transition index) of the iteration being summed
+        for (int64_t q = i; q < N && keys[q] == k; ++q) {
+            const uint32_t idx = vals[q];
+            const double wv = w ? w[idx] : 1.0;
+            if (iter_offsets && (int64_t)idx >= it_end) {
+                // crossed into a later iteration: close the previous partial (dense add in the reference)
+                total = __dadd_rn(total, part);
+                part = 0.0;
+                it_end = iter_offsets[find_iter(iter_offsets, n_iters, (int64_t)idx) + 1];
+            }
+            part = __dadd_rn(part, wv);
+        }
+        total = __dadd_rn(total, part);
+        const uint64_t r = k / CM, c = k - r * CM;
+        if (dense) dense[k] = __dadd_rn(dense[k], total);
+        if (coo_val) {
+            const int32_t pos = head_pos[i];
+            coo_row[pos] = (int64_t)r;
+            coo_col[pos] = (int64_t)c;
+            coo_val[pos] = total;
+        }
+    }
+}
+
+static size_t flux_ws_bytes(int64_t N) {
+    if (N < 1) N = 1;
+    size_t b = 0;
+    b += align_up((size_t)N * sizeof(uint64_t), 256);  // keys
+    b += align_up((size_t)N * sizeof(uint32_t), 256);  // vals
+    b += align_up((size_t)N * sizeof(int32_t), 256);   // head flags / positions
+    b += sort_workspace_bytes(N);
+    b += scan_workspace_bytes(N);
+    return b + 1024;
+}
+
+}  // namespace mwe
+
+extern "C" size_t mwe_flux_workspace_bytes(int64_t N) { return mwe::flux_ws_bytes(N); }
+
+extern "C" int mwe_flux_accumulate_f64(const int64_t* start, const int64_t* end, const uint8_t* flag0,
+                                       const uint8_t* flag1, const uint8_t* col0, const uint8_t* col1, const double* w,
+                                       int64_t N, int64_t n_clusters, int C, const int64_t* iter_offsets,
+                                       int64_t n_iters, double* dense_inout, int64_t* coo_row, int64_t* coo_col,
+                                       double* coo_val, int64_t* nnz_out, void* workspace, size_t workspace_bytes,
+                                       int32_t* err_count, void* stream) {
+    using namespace mwe;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    MWE_REQUIRE(N >= 0 && N < ((int64_t)1 << 32), "flux: N must be < 2^32 per call");
+    MWE_REQUIRE(n_clusters >= 0 && C >= 1 && C <= 255, "flux: bad n_clusters / C");
+    MWE_REQUIRE(start && end && err_count, "flux: null pointer");
+    MWE_REQUIRE((coo_val == nullptr) == (coo_row == nullptr) && (coo_val == nullptr) == (coo_col == nullptr),
+                "flux: coo_row/coo_col/coo_val must be given together");
+    MWE_REQUIRE(coo_val == nullptr || nnz_out != nullptr, "flux: COO output needs nnz_out");
+    MWE_REQUIRE(iter_offsets == nullptr || n_iters >= 1, "flux: iter_offsets needs n_iters >= 1");
+    const uint64_t CM = (uint64_t)C * (uint64_t)(n_clusters + 2);
+    MWE_REQUIRE(CM < ((uint64_t)1 << 31), "flux: matrix side too large");
+    if (N == 0) {
+        if (nnz_out) MWE_CHECK_CUDA(cudaMemsetAsync(nnz_out, 0, sizeof(int64_t), s));
+        return MWE_OK;
+    }
+    if (workspace_bytes < flux_ws_bytes(N)) {
+        set_last_error("flux: workspace too small (%zu < %zu)", workspace_bytes, flux_ws_bytes(N));
+        return MWE_E_WORKSPACE;
+    }
+    Carver cv(workspace, workspace_bytes);
+    uint64_t* keys = cv.take<uint64_t>((size_t)N);
+    uint32_t* vals = cv.take<uint32_t>((size_t)N);
+    int32_t* head = cv.take<int32_t>((size_t)N);
+    const size_t sort_bytes = sort_workspace_bytes(N);
+    void* sort_ws = cv.take<char>(sort_bytes);
+    const size_t scan_bytes = scan_workspace_bytes(N);
+    void* scan_ws = cv.take<char>(scan_bytes);
+
+    const uint64_t sentinel = CM * CM;  // one past the last cell
+    const int key_bits = ceil_log2_u64(sentinel + 1);
+    int64_t blocks = (N + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    flux_keys_kernel<<<(unsigned)blocks, 256, 0, s>>>(start, end, flag0, flag1, col0, col1, N, n_clusters, C, sentinel,
+                                                     keys, vals, err_count);
+    MWE_CHECK_LAUNCH();
+    uint64_t* ks;
+    uint32_t* vs;
+    int rc = sort_pairs(keys, vals, N, key_bits, sort_ws, sort_bytes, s, &ks, &vs);
+    if (rc != MWE_OK) return rc;
+    if (coo_val) {
+        flux_heads_kernel<<<(unsigned)blocks, 256, 0, s>>>(ks, N, sentinel, head);
+        MWE_CHECK_LAUNCH();
+        rc = exclusive_scan_i32(head, head, N, nnz_out, scan_ws, scan_bytes, s);
+        if (rc != MWE_OK) return rc;
+    }
+    flux_segsum_kernel<<<(unsigned)blocks, 256, 0, s>>>(ks, vs, N, sentinel, w, iter_offsets, n_iters, CM, dense_inout,
+                                                       head, coo_row, coo_col, coo_val);
+    MWE_CHECK_LAUNCH();
+    return MWE_OK;
+}

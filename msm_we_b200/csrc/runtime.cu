@@ -1,0 +1,55 @@
+// Library-level plumbing: last-error text, device queries, small elementwise helpers.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace mwe {
+
+static thread_local char g_last_error[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static thread_local int cached_dev = -1;
+    static thread_local int cached = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        return 148;
+    }
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached = n;
+        else cudaGetLastError();
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+__global__ void divide_kernel(double* __restrict__ buf, int64_t n, double divisor) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) buf[i] = buf[i] / divisor;
+}
+
+}  // namespace mwe
+
+extern "C" int mwe_abi_version(void) { return MWE_ABI_VERSION; }
+extern "C" const char* mwe_last_error(void) { return mwe::g_last_error; }
+extern "C" int mwe_device_sm_count(void) { return mwe::sm_count(); }
+
+extern "C" int mwe_divide_f64(double* buf, int64_t count, double divisor, void* stream) {
+    MWE_REQUIRE(count >= 0, "divide: negative count");
+    if (count == 0) return MWE_OK;
+    int64_t blocks = (count + 255) / 256;
+    int64_t cap = (int64_t)mwe::sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    mwe::divide_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(buf, count, divisor);
+    MWE_CHECK_LAUNCH();
+    return MWE_OK;
+}

@@ -1,0 +1,263 @@
+"""Thin torch-tensor wrappers over the C ABI (include/msm_we_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the CUDA stream; every computation is one of
+the hand-written sm_100a kernels behind ``libmsm_we_b200.so``.  Nothing in this module computes on
+the CPU and nothing falls back to torch ops.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise TypeError(f"{name}: expected a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise TypeError(f"{name}: expected a contiguous tensor")
+
+
+class Workspace:
+    """Grow-only scratch buffer, one per device."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, device, nbytes: int) -> torch.Tensor:
+        key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+        buf = cls._cache.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = None
+            cls._cache.pop(key, None)
+            buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=f"cuda:{key}")
+            cls._cache[key] = buf
+        return buf
+
+    @classmethod
+    def clear(cls):
+        cls._cache.clear()
+
+
+class DeviceErrors:
+    """The device-side error counters of the ABI, turned back into the reference's exceptions."""
+
+    def __init__(self, device):
+        self.counts = torch.zeros(_lib.ERR_SLOTS, dtype=torch.int32, device=device)
+
+    def reset(self):
+        self.counts.zero_()
+
+    def check(self):
+        c = self.counts.cpu().numpy()
+        self.counts.zero_()
+        if c[_lib.ERR_OUT_OF_BINSPACE]:
+            # westpa's rectilinear_assign raises ValueError for a coordinate outside the bin space
+            raise ValueError(f"coordinate outside of bin space ({int(c[_lib.ERR_OUT_OF_BINSPACE])} points)")
+        if c[_lib.ERR_NO_CENTERS]:
+            # msm_we/stratified_clustering.py:187-189
+            raise AssertionError(
+                f"Not initialized: {int(c[_lib.ERR_NO_CENTERS])} segments fall in a WE bin without cluster centers")
+        if c[_lib.ERR_LABEL_RANGE]:
+            # scipy.sparse.coo_matrix raises ValueError for an index outside the shape (_fluxmatrix.py:147-158)
+            raise ValueError(f"row/column index exceeds matrix dimensions ({int(c[_lib.ERR_LABEL_RANGE])} transitions)")
+        if c[_lib.ERR_INTERNAL]:
+            raise RuntimeError("internal device error")
+
+
+class MapperSpec:
+    """Device-resident description of a WE bin mapper for K0."""
+
+    def __init__(self, kind, nbins, data=None, lens=None):
+        self.kind = kind
+        self.nbins = int(nbins)
+        self.data = data                      # float32 CUDA tensor or None
+        self.lens = None if lens is None else np.ascontiguousarray(lens, dtype=np.int32)
+
+    @classmethod
+    def rectilinear(cls, boundaries, device):
+        bs = [np.asarray(b, dtype=np.float32) for b in boundaries]
+        nbins = int(np.prod([len(b) - 1 for b in bs]))
+        data = torch.from_numpy(np.concatenate(bs)).to(device)
+        return cls(_lib.MAPPER_RECTILINEAR, nbins, data, [len(b) for b in bs])
+
+    @classmethod
+    def voronoi(cls, centers, device):
+        c = np.ascontiguousarray(centers, dtype=np.float32)
+        if c.ndim == 1:
+            c = c[:, None]
+        return cls(_lib.MAPPER_VORONOI, c.shape[0], torch.from_numpy(c).to(device))
+
+    @classmethod
+    def precomputed(cls, nbins):
+        return cls(_lib.MAPPER_PRECOMPUTED, nbins)
+
+
+def bin_flags(pcoord, mapper: MapperSpec, basis_bounds, target_bounds, we_remap=None, errors: DeviceErrors = None,
+              bin_out=None, bin_count=None):
+    """K0.  pcoord [N,P] f64 CUDA -> (bin int32 [N], flag uint8 [N])."""
+    _req(pcoord, torch.float64, "pcoord")
+    if pcoord.dim() == 1:
+        pcoord = pcoord[:, None]
+    N, P = pcoord.shape
+    dev = pcoord.device
+    if errors is None:
+        errors = DeviceErrors(dev)
+    if mapper.kind == _lib.MAPPER_PRECOMPUTED:
+        if bin_out is None:
+            raise ValueError("precomputed mapper needs bin_out holding the raw bins")
+        _req(bin_out, torch.int32, "bin_out")
+    elif bin_out is None:
+        bin_out = torch.empty(N, dtype=torch.int32, device=dev)
+    flag = torch.empty(N, dtype=torch.uint8, device=dev)
+    basis = np.ascontiguousarray(basis_bounds, dtype=np.float64).reshape(-1, 2)
+    target = np.ascontiguousarray(target_bounds, dtype=np.float64).reshape(-1, 2)
+    if basis.shape[0] < P or target.shape[0] < P:
+        raise ValueError("basis/target bounds need one (lo, hi) row per pcoord dimension")
+    _req(we_remap, torch.int32, "we_remap")
+    _req(bin_count, torch.int32, "bin_count")
+    lens_p = mapper.lens.ctypes.data if mapper.lens is not None else None
+    check(lib.mwe_bin_flags_f64(_ptr(pcoord), N, P, mapper.kind, _ptr(mapper.data), lens_p, mapper.nbins,
+                                basis.ctypes.data, target.ctypes.data, _ptr(we_remap), _ptr(bin_out), _ptr(flag),
+                                _ptr(bin_count), _ptr(errors.counts), _stream()), "mwe_bin_flags_f64")
+    return bin_out, flag
+
+
+def centers_sqnorm(centers):
+    _req(centers, torch.float64, "centers")
+    sumK, D = centers.shape
+    out = torch.empty(sumK, dtype=torch.float64, device=centers.device)
+    check(lib.mwe_centers_sqnorm_f64(_ptr(centers), sumK, D, _ptr(out), _stream()), "mwe_centers_sqnorm_f64")
+    return out
+
+
+def assign_stratified(X, bin, flag, centers, csq, bin_offset, max_k, path=_lib.ASSIGN_FP64, want_local=False,
+                      errors: DeviceErrors = None, label_out=None):
+    """K1.  X [N,D] f64 (row stride may exceed D) -> labels int64 [N] (and per-bin local argmin)."""
+    if not X.is_cuda or X.dtype != torch.float64 or X.dim() != 2 or X.stride(1) != 1:
+        raise TypeError("X: expected a CUDA float64 [N, D] tensor with unit column stride")
+    _req(bin, torch.int32, "bin"); _req(flag, torch.uint8, "flag")
+    _req(centers, torch.float64, "centers"); _req(csq, torch.float64, "csq"); _req(bin_offset, torch.int64, "bin_offset")
+    N, D = X.shape
+    ldx = X.stride(0) if N > 1 else D
+    dev = X.device
+    nbins = bin_offset.numel() - 1
+    if errors is None:
+        errors = DeviceErrors(dev)
+    if label_out is None:
+        label_out = torch.empty(N, dtype=torch.int64, device=dev)
+    local = torch.empty(N, dtype=torch.int32, device=dev) if want_local else None
+    nbytes = lib.mwe_assign_workspace_bytes(N, nbins)
+    ws = Workspace.get(dev, nbytes)
+    check(lib.mwe_assign_stratified_f64(_ptr(X), N, D, ldx, _ptr(bin), _ptr(flag), _ptr(centers), _ptr(csq),
+                                        _ptr(bin_offset), nbins, int(max_k), int(path), _ptr(label_out), _ptr(local),
+                                        _ptr(ws), ws.numel(), _ptr(errors.counts), _stream()),
+          "mwe_assign_stratified_f64")
+    return (label_out, local) if want_local else label_out
+
+
+def _centroid_common(fn, name, X, w, label, sumK, a, b):
+    if not X.is_cuda or X.dtype != torch.float64 or X.dim() != 2 or X.stride(1) != 1:
+        raise TypeError("X: expected a CUDA float64 [N, D] tensor with unit column stride")
+    _req(w, torch.float64, "w"); _req(label, torch.int64, "label")
+    N, D = X.shape
+    ldx = X.stride(0) if N > 1 else D
+    nbytes = lib.mwe_centroid_workspace_bytes(N, sumK)
+    ws = Workspace.get(X.device, nbytes)
+    check(fn(_ptr(X), N, D, ldx, _ptr(w), _ptr(label), sumK, _ptr(a), _ptr(b), _ptr(ws), ws.numel(), _stream()), name)
+
+
+def centroid_accumulate(X, w, label, sumK):
+    """K2 partial sums: (sum_wx [sumK,D], sum_w [sumK])."""
+    D = X.shape[1]
+    sum_wx = torch.empty(sumK, D, dtype=torch.float64, device=X.device)
+    sum_w = torch.empty(sumK, dtype=torch.float64, device=X.device)
+    _centroid_common(lib.mwe_centroid_accumulate_f64, "mwe_centroid_accumulate_f64", X, w, label, sumK, sum_wx, sum_w)
+    return sum_wx, sum_w
+
+
+def minibatch_update(X, w, label, centers, counts):
+    """K2 fused running-mean update of centers [sumK,D] / counts [sumK], in place."""
+    _req(centers, torch.float64, "centers"); _req(counts, torch.float64, "counts")
+    _centroid_common(lib.mwe_minibatch_update_f64, "mwe_minibatch_update_f64", X, w, label, centers.shape[0], centers, counts)
+
+
+def lloyd_finalize(sum_wx, sum_w, centers):
+    _req(sum_wx, torch.float64, "sum_wx"); _req(sum_w, torch.float64, "sum_w"); _req(centers, torch.float64, "centers")
+    sumK, D = centers.shape
+    check(lib.mwe_lloyd_finalize_f64(_ptr(sum_wx), _ptr(sum_w), sumK, D, _ptr(centers), _stream()), "mwe_lloyd_finalize_f64")
+
+
+def minibatch_finalize(sum_wx, sum_w, centers, counts):
+    _req(sum_wx, torch.float64, "sum_wx"); _req(sum_w, torch.float64, "sum_w")
+    _req(centers, torch.float64, "centers"); _req(counts, torch.float64, "counts")
+    sumK, D = centers.shape
+    check(lib.mwe_minibatch_finalize_f64(_ptr(sum_wx), _ptr(sum_w), sumK, D, _ptr(centers), _ptr(counts), _stream()),
+          "mwe_minibatch_finalize_f64")
+
+
+def flux_accumulate(start, end, w, n_clusters, flag0=None, flag1=None, col0=None, col1=None, C=1, iter_offsets=None,
+                    dense=None, want_coo=False, errors: DeviceErrors = None):
+    """K3.  Adds the transitions into ``dense`` [CM,CM] (created zeroed if None and not want_coo) and/or
+    returns sorted COO triples."""
+    _req(start, torch.int64, "start"); _req(end, torch.int64, "end"); _req(w, torch.float64, "w")
+    for nm, t in (("flag0", flag0), ("flag1", flag1), ("col0", col0), ("col1", col1)):
+        _req(t, torch.uint8, nm)
+    _req(iter_offsets, torch.int64, "iter_offsets")
+    N = start.numel()
+    dev = start.device
+    CM = C * (n_clusters + 2)
+    if errors is None:
+        errors = DeviceErrors(dev)
+    if dense is None and not want_coo:
+        dense = torch.zeros(CM, CM, dtype=torch.float64, device=dev)
+    if dense is not None:
+        _req(dense, torch.float64, "dense")
+        if dense.shape != (CM, CM):
+            raise ValueError(f"dense must be [{CM},{CM}]")
+    coo_r = coo_c = coo_v = nnz = None
+    if want_coo:
+        coo_r = torch.empty(max(N, 1), dtype=torch.int64, device=dev)
+        coo_c = torch.empty(max(N, 1), dtype=torch.int64, device=dev)
+        coo_v = torch.empty(max(N, 1), dtype=torch.float64, device=dev)
+        nnz = torch.zeros(1, dtype=torch.int64, device=dev)
+    n_iters = 0 if iter_offsets is None else iter_offsets.numel() - 1
+    nbytes = lib.mwe_flux_workspace_bytes(N)
+    ws = Workspace.get(dev, nbytes)
+    check(lib.mwe_flux_accumulate_f64(_ptr(start), _ptr(end), _ptr(flag0), _ptr(flag1), _ptr(col0), _ptr(col1), _ptr(w),
+                                      N, int(n_clusters), int(C), _ptr(iter_offsets), n_iters, _ptr(dense), _ptr(coo_r),
+                                      _ptr(coo_c), _ptr(coo_v), _ptr(nnz), _ptr(ws), ws.numel(), _ptr(errors.counts),
+                                      _stream()), "mwe_flux_accumulate_f64")
+    if want_coo:
+        return dense, (coo_r, coo_c, coo_v, nnz)
+    return dense
+
+
+def divide_(buf, divisor: float):
+    _req(buf, torch.float64, "buf")
+    check(lib.mwe_divide_f64(_ptr(buf), buf.numel(), float(divisor), _stream()), "mwe_divide_f64")
+    return buf
+
+
+def sort_pairs_(keys_i64, vals_i32, key_bits: int):
+    """In-place stable radix sort (keys reinterpreted as u64, values as u32). Exported for tests."""
+    _req(keys_i64, torch.int64, "keys"); _req(vals_i32, torch.int32, "vals")
+    N = keys_i64.numel()
+    nbytes = lib.mwe_sort_workspace_bytes(N)
+    ws = Workspace.get(keys_i64.device, nbytes)
+    check(lib.mwe_sort_pairs_u64_u32(_ptr(keys_i64), _ptr(vals_i32), N, int(key_bits), _ptr(ws), ws.numel(), _stream()),
+          "mwe_sort_pairs_u64_u32")
