@@ -1,0 +1,448 @@
+#!/usr/bin/env python
+"""Benchmark of the discretization + flux hot path (BASELINE.json metric: WE frames/s assigned and
+flux-accumulated; 1 frame = 1 WE segment in 1 iteration = 2 feature vectors assigned + 1 weighted
+transition scattered).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl b200|reference]
+
+One step = one pass of the hot path over the whole workload batch held by this rank:
+K0 (bin + basis/target flags of parent and child pcoords) -> K1 (stratified assignment of parent and
+child features) -> K3 (sort + segmented fp64 sum into the dense flux matrix, / nI); with N > 1 ranks
+every rank owns its own iteration range (weak scaling, fixed work per GPU) and the per-rank flux
+matrices are combined with one NCCL all-reduce, the path's only exchange step.
+
+value  : frames/s with the inputs already resident in HBM (CUDA events per step, L2 flushed between
+         steps, max over ranks);
+e2e    : the same metric through the modelWE plugin API (launch_ray_discretization + get_fluxMatrix)
+         with host numpy buffers: H2D of every feature/pcoord/weight and D2H of labels and the flux
+         matrix are inside the timed region;
+roofline: the dominant kernel (K1, assign_dmma_kernel), algorithmic bytes / CUDA-event time measured
+         inside the timed steps on the launching stream;
+cpu_baseline / --impl reference: the reference's own CPU pattern (oracle literal loop: one sklearn
+         predict([x]) per segment + per-iteration scipy coo_matrix -> dense add) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "we_frames_per_sec_assigned_and_flux_accumulated"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample-iters", type=int, default=0, help="iterations of the workload timed on the CPU (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the reference's literal pattern, one process per iteration range
+# ----------------------------------------------------------------------------------------------
+
+def cpu_reference_pass(cfg_name, n_sample_iters, n_procs):
+    """Times the reference pattern on `n_sample_iters` iterations of the workload; returns
+    (frames, seconds, cores)."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("fork")
+    chunks = np.array_split(np.arange(n_sample_iters), n_procs)
+    chunks = [c for c in chunks if len(c)]
+    t0 = time.perf_counter()
+    with ctx.Pool(len(chunks)) as pool:
+        res = pool.map(_cpu_chunk, [(cfg_name, int(c[0]), int(c[-1]) + 1) for c in chunks])
+    dt = time.perf_counter() - t0
+    frames = sum(r[0] for r in res)
+    return frames, dt, len(chunks)
+
+
+_CPU_CACHE = {}
+
+
+def _cpu_inputs(cfg_name, n_iters):
+    """Host data for the CPU arm: the same generator and seed as the small-config tests, restricted to
+    `n_iters` iterations (built once in the parent, inherited by fork)."""
+    key = (cfg_name, n_iters)
+    if key not in _CPU_CACHE:
+        import dataclasses
+
+        from msm_we_b200 import synthetic
+
+        cfg = dataclasses.replace(synthetic.CONFIGS[cfg_name], n_iters=n_iters)
+        means, centers = synthetic.make_centers(cfg)
+        its = synthetic.generate_host(cfg, means)
+        _CPU_CACHE[key] = (cfg, centers, its)
+    return _CPU_CACHE[key]
+
+
+def _cpu_chunk(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from oracle import oracle as O
+    from msm_we_b200 import synthetic
+
+    cfg_name, lo, hi, n_total = args[0], args[1], args[2], None
+    cfg, centers, its = _cpu_inputs(cfg_name, _CPU_SAMPLE[0])
+    basis, target = synthetic.region_bounds(cfg)
+    om = O.RectilinearBinMapperOracle(synthetic.boundaries(cfg))
+    strat = O.StratifiedOracle(om, centers, basis, target)
+    models = [O.make_fitted_minibatch(c) for c in centers]
+    n = cfg.n_clusters
+    total = np.zeros((n + 2, n + 2))
+    frames = 0
+    for i in range(lo, hi):
+        d = its[i]
+        parent, child = O.discretize_iteration(strat, d["parent"], d["child"], d["pcoord0"], d["pcoord1"], literal=True,
+                                               models=models)
+        pairs = np.stack([parent, child], axis=1)
+        total = total + O.iter_flux_matrix(n, pairs, d["pcoord0"], d["pcoord1"], d["weights"], basis, target)
+        frames += len(parent)
+    return frames, float(total.sum())
+
+
+_CPU_SAMPLE = [0]
+
+
+def run_cpu_arm(cfg_name, sample_iters, cores):
+    _CPU_SAMPLE[0] = sample_iters
+    _cpu_inputs(cfg_name, sample_iters)  # build before forking
+    from oracle import oracle as O       # import sklearn/scipy in the parent so the forked workers inherit them
+    import sklearn.cluster  # noqa: F401
+
+    O.make_fitted_minibatch(np.zeros((2, 2))).predict([[0.0, 0.0]])
+    frames, dt, used = cpu_reference_pass(cfg_name, sample_iters, cores)
+    return frames, dt, used
+
+
+def auto_sample_iters(cfg, cores):
+    # ~155 us per sklearn predict([x]) call, 2 calls per frame; aim at ~15 s of CPU work per core-set
+    per_iter = cfg.n_segs * 2 * 160e-6 + 2e-9 * (cfg.n_clusters + 2) ** 2 * 8
+    want = max(cores, int(15.0 * cores / per_iter))
+    return int(min(cfg.n_iters, max(cores, (want // cores) * cores)))
+
+
+# ----------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    """SM clock + throttle reasons sampled through NVML (about 1 kHz) while the steps run; samples
+    taken between mark_timed(True) and mark_timed(False) belong to the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []          # (in_timed_region, sm_mhz, reasons_bitmask)
+        self.max_mhz = None
+        self._timed = False
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+
+    def mark_timed(self, on):
+        self._timed = on
+
+    def _run(self):
+        nv = self._nvml
+        while not self._stop.is_set():
+            try:
+                if nv is not None:
+                    mhz = float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                    self.samples.append((self._timed, mhz, reasons))
+                    self._stop.wait(0.001)
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    a, b = [float(x) for x in out.strip().split(",")[:2]]
+                    self.max_mhz = b
+                    self.samples.append((self._timed, a, 0))
+                    self._stop.wait(0.05)
+            except Exception:
+                self._stop.wait(0.01)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        timed = [s for s in self.samples if s[0]]
+        use = timed if timed else self.samples
+        if not use:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
+        sm = sorted(s[1] for s in use)
+        mask = 0
+        for s in use:
+            mask |= s[2]
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        reasons = [n for bit, n in names.items() if mask & bit]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(use),
+                "window": "timed region" if timed else "warm-up + timed region"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from msm_we_b200 import synthetic  # host-only import is fine without a GPU
+
+    cfg = synthetic.CONFIGS[args.workload]
+    cores = os.cpu_count() or 1
+
+    # ------------------------------------------------------------------ reference arm (CPU only)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sample = args.cpu_sample_iters or auto_sample_iters(cfg, cores)
+        times = []
+        frames = 0
+        for step in range(args.warmup + args.steps):
+            frames, dt, used = run_cpu_arm(args.workload, sample, cores)
+            if step >= args.warmup:
+                times.append(dt)
+        total = sum(times)
+        val = frames * len(times) / total
+        line = {
+            "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{cfg.name}: {cfg.n_iters} WE iters x {cfg.n_segs} segs x {cfg.dim}-dim, "
+                                   f"{cfg.n_bins} bins x {cfg.k_per_bin} clusters/bin, fp64"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": used, "kind": "port",
+                             "sample": f"{sample} of {cfg.n_iters} iterations per step ({frames} frames), literal "
+                                       f"reference loop (sklearn predict([x]) per segment + scipy coo->dense add per "
+                                       f"iteration), one process per iteration range (ray unavailable: multiprocessing)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device; the B200 arm has no CPU fallback"}))
+        return 2
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from msm_we_b200 import _lib, ops
+    from msm_we_b200.binning import RectilinearBinMapper
+    from msm_we_b200.engine import DeviceClusters
+
+    means, centers = synthetic.make_centers(cfg)
+    basis, target = synthetic.region_bounds(cfg)
+    mapper = RectilinearBinMapper(synthetic.boundaries(cfg))
+    remap = {b: b for b in range(cfg.n_bins)}
+    engine = DeviceClusters(mapper, centers, remap, basis, target, 1, device=dev)
+    data = synthetic.generate_device(cfg, dev, means=means, seed_offset=rank)   # this rank's iteration range
+    N = data["n"]
+    n_clusters = cfg.n_clusters
+    M = n_clusters + 2
+    X, pc, w, offs = data["X"], data["pcoord"], data["weights"], data["iter_offsets"]
+    dense = torch.zeros((M, M), dtype=torch.float64, device=dev)
+    labels = torch.empty(2 * N, dtype=torch.int64, device=dev)
+    l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    n_iters_total = cfg.n_iters * world
+    launches = {"n": 0}
+
+    def step(ev=None):
+        bins, flags = ops.bin_flags(pc, engine.mapper, engine.basis, engine.target, we_remap=engine.we_remap,
+                                    errors=engine.errors)
+        if ev is not None:
+            _lib.set_timing_events(ev[0], ev[1])
+        ops.assign_stratified(X, bins, flags, engine.centers, engine.csq, engine.bin_offset, engine.max_k,
+                              errors=engine.errors, label_out=labels)
+        if ev is not None:
+            _lib.set_timing_events(None, None)
+        dense.zero_()
+        ops.flux_accumulate(labels[:N], labels[N:], w, n_clusters, flag0=flags[:N], flag1=flags[N:],
+                            iter_offsets=offs, dense=dense, errors=engine.errors)
+        if world > 1:
+            dist.all_reduce(dense)
+        ops.divide_(dense, float(n_iters_total))
+
+    for _ in range(args.warmup):
+        l2_flush.zero_()
+        step()
+    torch.cuda.synchronize()
+    engine.check_errors()
+
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(local_rank) as clocks:
+        clocks.mark_timed(True)
+        for k in range(args.steps):
+            l2_flush.zero_()                       # flush L2 between timed steps (outside the events)
+            evs[k][0].record()
+            step(kevs[k])
+            evs[k][1].record()
+        torch.cuda.synchronize()
+        clocks.mark_timed(False)
+    if world > 1:
+        dist.barrier()
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in kevs) / args.steps
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    engine.check_errors()
+    frames_per_step = N * world
+    value = frames_per_step * args.steps / (total_ms * 1e-3)
+
+    # roofline of the dominant kernel (K1): algorithmic bytes per launch = per point D*8 (features) +
+    # 4 (bucket index) + 8 (int64 label); 2N points per launch
+    peak, peak_src = load_peaks()
+    alg_bytes = 2 * N * (cfg.dim * 8 + 4 + 8)
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "assign_dmma_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "fp64_tflops": 2 * N * 2.0 * cfg.k_per_bin * cfg.dim / (kernel_ms * 1e-3) / 1e12}
+
+    # ---------------------------------------------------------------- e2e through the plugin API
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(cfg, rank, world, dev, max(2, min(args.steps, 5)))
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample = args.cpu_sample_iters or auto_sample_iters(cfg, cores)
+        frames, dt, used = run_cpu_arm(args.workload, sample, cores)
+        cpu = {"value": frames / dt, "unit": UNIT, "cores": used, "kind": "port",
+               "sample": f"{sample} of {cfg.n_iters} iterations ({frames} frames) of the same workload shape, literal "
+                         f"reference loop, {dt:.1f} s wall"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{cfg.name}: {cfg.n_iters} WE iters x {cfg.n_segs} segs x {cfg.dim}-dim, "
+                                   f"{cfg.n_bins} bins x {cfg.k_per_bin} clusters/bin, fp64 (per GPU; iteration-range "
+                                   f"sharded, flux all-reduced)",
+                       "frames_per_step": frames_per_step, "l2": "flushed between timed steps (256 MiB memset)",
+                       "precision_path": "fp64 DMMA"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks.summary(),
+            "gpu_launches": LAUNCHES_PER_STEP_STATIC(cfg) * args.steps,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def LAUNCHES_PER_STEP_STATIC(cfg):
+    """Kernels of ours per step, counted from the launch sequences in csrc/: K0 (1) + K1 (count, scan,
+    scatter, dmma = 4) + K3 (keys 1 + 3 per radix pass + segsum 1) + divide 1."""
+    M = cfg.n_clusters + 2
+    bits = int(np.ceil(np.log2(M * M + 1)))
+    passes = (bits + 7) // 8
+    return 1 + 4 + (1 + 3 * passes + 1) + 1
+
+
+def run_e2e(cfg, rank, world, dev, steps):
+    """frames/s through the public modelWE API with HOST buffers (pinned staging inside the API)."""
+    import torch
+    import torch.distributed as dist
+
+    from msm_we_b200 import synthetic
+    from msm_we_b200.binning import RectilinearBinMapper
+    from msm_we_b200.msm_we import modelWE
+    from msm_we_b200.stratified_clustering import StratifiedClusters
+    import dataclasses
+
+    # host copy of a bounded number of iterations of the same shape (host generation is slow for big configs)
+    n_it = min(cfg.n_iters, 200)
+    hcfg = dataclasses.replace(cfg, n_iters=n_it, seed=cfg.seed + rank)
+    means, centers = synthetic.make_centers(cfg)
+    its = synthetic.generate_host(hcfg, means)
+    basis, target = synthetic.region_bounds(cfg)
+    model = modelWE()
+    model.initialize(synthetic.to_iteration_source(its), None, "bench", basis_pcoord_bounds=basis,
+                     target_pcoord_bounds=target, tau=1.0, pcoord_ndim=1)
+    model.get_iterations()
+    model.dimReduce()
+    clusters = StratifiedClusters(RectilinearBinMapper(synthetic.boundaries(cfg)), model, cfg.k_per_bin, [])
+    for b in range(cfg.n_bins):
+        clusters.cluster_models[b].cluster_centers_ = centers[b]
+    model.clusters = clusters
+    model.n_clusters = cfg.n_clusters
+    model.pre_discretization_model = model   # skip the deepcopy of the whole in-memory data set
+
+    def once():
+        model.launch_ray_discretization()
+        model.get_fluxMatrix(n_lag=0, first_iter=0)
+        return model.fluxMatrixRaw
+
+    once()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        once()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    frames = (n_it - 1) * cfg.n_segs          # launch_ray_discretization covers range(1, maxIter)
+    M = cfg.n_clusters + 2
+    h2d = frames * (2 * (cfg.dim + 1) * 8) + frames * (2 * 8 + 8 + 2 * 8)
+    d2h = frames * 2 * (8 + 4 + 1) + M * M * 8
+    return {"value": frames * world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "frames_per_step": frames * world,
+            "api": "modelWE.launch_ray_discretization + get_fluxMatrix, numpy in / numpy out"}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -62,6 +62,11 @@ MWE_API const char* mwe_last_error(void);
 /* number of SMs of the current device (grid sizing is done inside the library) */
 MWE_API int mwe_device_sm_count(void);
 
+/* Measurement hook: CUDA events (cudaEvent_t as void*, nullable) that the following calls on this
+ * host thread record immediately before / after their dominant kernel (K1: the DMMA assignment
+ * kernel), on the stream the kernel is launched on.  Pass NULL, NULL to switch it off. */
+MWE_API int mwe_set_timing_events(void* start, void* stop);
+
 /* ---- K0: WE-bin lookup + basis/target flags -------------------------------------------------
  * Replaces bin_mapper.assign(pcoords) + we_remap (msm_we/stratified_clustering.py:134-135,
  * msm_we/_hamsm/_clustering.py:877) and modelWE.is_WE_basis / is_WE_target

@@ -31,6 +31,7 @@ SIGNATURES = {
     "mwe_abi_version": (_int, []),
     "mwe_last_error": (C.c_char_p, []),
     "mwe_device_sm_count": (_int, []),
+    "mwe_set_timing_events": (_int, [_p, _p]),
     "mwe_bin_flags_f64": (_int, [_p, _i64, _int, _int, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "mwe_assign_workspace_bytes": (_sz, [_i64, _i32]),
     "mwe_centers_sqnorm_f64": (_int, [_p, _i64, _int, _p, _p]),
@@ -76,3 +77,15 @@ def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = lib.mwe_last_error()
         raise MweError(f"{what} failed (status {rc}): {msg.decode() if msg else ''}")
+
+
+def set_timing_events(start, stop) -> None:
+    """Ask the library to record these torch.cuda.Event objects around its dominant kernel (K1) in the
+    calls that follow on this thread; ``None, None`` switches it off."""
+    def handle(ev):
+        if ev is None:
+            return None
+        if not ev.cuda_event:
+            ev.record()          # torch creates the CUDA event lazily; the library re-records it
+        return ev.cuda_event
+    check(lib.mwe_set_timing_events(handle(start), handle(stop)), "mwe_set_timing_events")

@@ -410,8 +410,12 @@ static int launch_assign(const AssignParams& p, int64_t max_tiles, cudaStream_t 
     int64_t grid = (int64_t)sm_count() * occ;
     if (grid > max_tiles) grid = max_tiles;
     if (grid < 1) grid = 1;
+    cudaEvent_t ev0, ev1;
+    timing_events(&ev0, &ev1);
+    if (ev0) MWE_CHECK_CUDA(cudaEventRecord(ev0, stream));
     assign_dmma_kernel<NT, VEC><<<(unsigned)grid, AS_THREADS, smem, stream>>>(p);
     MWE_CHECK_LAUNCH();
+    if (ev1) MWE_CHECK_CUDA(cudaEventRecord(ev1, stream));
     return MWE_OK;
 }
 

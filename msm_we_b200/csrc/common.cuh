@@ -10,6 +10,8 @@ namespace mwe {
 
 void set_last_error(const char* fmt, ...);
 int sm_count();
+// optional CUDA events recorded around the dominant kernel of the next calls (bench roofline timing)
+void timing_events(cudaEvent_t* start, cudaEvent_t* stop);
 
 #define MWE_CHECK_CUDA(expr)                                                                   \
     do {                                                                                       \

@@ -81,28 +81,37 @@ __global__ void __launch_bounds__(256)
         const uint64_t k = keys[i];
         if (k == sentinel) continue;
         if (i > 0 && keys[i - 1] == k) continue;  // not a run head
-        double total = 0.0;
+        // `total` continues the running sum already in the dense matrix (chunked calls keep the serial
+        // association ((F + it_a) + it_b) + ...); `fresh` is the sum of this call alone (COO output)
+        double total = dense ? dense[k] : 0.0;
+        double fresh = 0.0;
         double part = 0.0;
+        bool have_part = false;
         int64_t it_end = -1;  // exclusive end (transition index) of the iteration being summed
         for (int64_t q = i; q < N && keys[q] == k; ++q) {
             const uint32_t idx = vals[q];
             const double wv = w ? w[idx] : 1.0;
             if (iter_offsets && (int64_t)idx >= it_end) {
                 // crossed into a later iteration: close the previous partial (dense add in the reference)
-                total = __dadd_rn(total, part);
+                if (have_part) {
+                    total = __dadd_rn(total, part);
+                    fresh = __dadd_rn(fresh, part);
+                }
                 part = 0.0;
                 it_end = iter_offsets[find_iter(iter_offsets, n_iters, (int64_t)idx) + 1];
             }
             part = __dadd_rn(part, wv);
+            have_part = true;
         }
         total = __dadd_rn(total, part);
+        fresh = __dadd_rn(fresh, part);
         const uint64_t r = k / CM, c = k - r * CM;
-        if (dense) dense[k] = __dadd_rn(dense[k], total);
+        if (dense) dense[k] = total;
         if (coo_val) {
             const int32_t pos = head_pos[i];
             coo_row[pos] = (int64_t)r;
             coo_col[pos] = (int64_t)c;
-            coo_val[pos] = total;
+            coo_val[pos] = fresh;
         }
     }
 }

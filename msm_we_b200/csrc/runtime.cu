@@ -14,6 +14,14 @@ void set_last_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static thread_local cudaEvent_t g_ev_start = nullptr;
+static thread_local cudaEvent_t g_ev_stop = nullptr;
+
+void timing_events(cudaEvent_t* start, cudaEvent_t* stop) {
+    *start = g_ev_start;
+    *stop = g_ev_stop;
+}
+
 int sm_count() {
     static thread_local int cached_dev = -1;
     static thread_local int cached = 148;
@@ -38,6 +46,12 @@ __global__ void divide_kernel(double* __restrict__ buf, int64_t n, double diviso
 }
 
 }  // namespace mwe
+
+extern "C" int mwe_set_timing_events(void* start, void* stop) {
+    mwe::g_ev_start = static_cast<cudaEvent_t>(start);
+    mwe::g_ev_stop = static_cast<cudaEvent_t>(stop);
+    return MWE_OK;
+}
 
 extern "C" int mwe_abi_version(void) { return MWE_ABI_VERSION; }
 extern "C" const char* mwe_last_error(void) { return mwe::g_last_error; }

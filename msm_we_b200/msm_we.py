@@ -1,0 +1,239 @@
+"""``modelWE``: the reference's model-builder class, restricted to the hot path this package accelerates.
+
+reference: msm_we/msm_we.py -- class composition (:35-42), ``initialize`` (:143-277), bounds setters
+(:279-440), ``is_WE_basis`` / ``is_WE_target`` (:462-527), ``build_analyze_model`` (:588-882).
+
+Kept: every name the discretization + flux path reads or writes.  Not re-implemented (out
+of scope, host-side small-matrix work in the reference): dimensionality-reduction fitting, flux-matrix
+cleaning, transition matrix / steady state / committors, block validation, plotting.  Those mixins of
+the reference can be combined with this class unchanged because the attributes they consume
+(``fluxMatrixRaw``, ``dtrajs``, ``pair_dtrajs``, ``clusters`` ...) have the reference's types.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ._hamsm._clustering import ClusteringMixin
+from ._hamsm._data import ArrayIterationSource, DataMixin, H5IterationSource
+from ._hamsm._fluxmatrix import FluxMatrixMixin
+from ._logging import log
+
+
+class Coordinates:
+    """Identity transform (reference: msm_we/_hamsm/_dimensionality.py:23-34)."""
+
+    def __init__(self):
+        self.explanation = "coordinate object"
+
+    def transform(self, coords):
+        return coords
+
+
+class LinearCoordinates:
+    """Fitted affine projection ``(X - mean_) @ components_.T`` -- what the reference's IncrementalPCA
+    ``coordinates.transform`` applies immediately before assignment (_dimensionality.py:243)."""
+
+    def __init__(self, components, mean=None):
+        self.components_ = np.asarray(components, dtype=np.float64)
+        self.mean_ = np.zeros(self.components_.shape[1]) if mean is None else np.asarray(mean, dtype=np.float64)
+
+    def transform(self, coords):
+        return (np.asarray(coords, dtype=np.float64) - self.mean_) @ self.components_.T
+
+
+class modelWE(ClusteringMixin, DataMixin, FluxMatrixMixin):
+    class BlockValidationError(Exception):
+        pass
+
+    def __init__(self):
+        self.modelName = None
+        self._n_lag = 0
+        self.pcoord_ndim = None
+        self.pcoord_len = None
+        self.tau = None
+        self._basis_pcoord_bounds = None
+        self._target_pcoord_bounds = None
+        self.nAtoms = None
+        self.coord_ndim = 3
+        self.coordinates = None
+        self.ndim = None
+        self.removed_clusters = []
+        self.cluster_structures = None
+        self.cluster_structure_weights = None
+        self.clustering_method = None
+        self.validation_models = []
+        self.pcoord_shape_warned = False
+        self.pre_discretization_model = None
+        self.dimReduceMethod = "none"
+        self.seg_weights = {}
+
+    # the reference expects users to monkey-patch this featurizer (docs/usage.rst:41-60)
+    def processCoordinates(self, coords):
+        coords = np.asarray(coords)
+        if coords.ndim == 3:
+            return coords.reshape(coords.shape[0], -1)
+        if coords.ndim == 2 and self.nAtoms is not None and coords.shape == (self.nAtoms, self.coord_ndim):
+            return coords.reshape(1, -1)
+        return coords
+
+    # ------------------------------------------------------------------------------------------
+    def initialize(self, fileSpecifier, refPDBfile=None, modelName=None, basis_pcoord_bounds=None,
+                   target_pcoord_bounds=None, dim_reduce_method="none", tau=None, pcoord_ndim=1, auxpath="coord",
+                   _suppress_boundary_warning=False, use_weights_in_clustering=False):
+        """reference: msm_we.py:143-277.  ``fileSpecifier`` is a list of WESTPA HDF5 paths (needs h5py) or an
+        iteration source object (``ArrayIterationSource``)."""
+        log.debug("Initializing msm_we model")
+        self.modelName = modelName
+        self.pcoord_ndim = pcoord_ndim
+        self.pcoord_len = 2
+        if basis_pcoord_bounds is None:
+            log.warning("No basis coord bounds provided to initialize().")
+        else:
+            self.basis_pcoord_bounds = basis_pcoord_bounds
+        if target_pcoord_bounds is None:
+            log.warning("No target coord bounds provided to initialize().")
+        else:
+            self.target_pcoord_bounds = target_pcoord_bounds
+        self.auxpath = auxpath
+        if hasattr(fileSpecifier, "get") and hasattr(fileSpecifier, "has"):
+            self.iteration_source = fileSpecifier
+            self.fileList = []
+        else:
+            files = fileSpecifier.split(" ") if isinstance(fileSpecifier, str) else list(fileSpecifier)
+            self.fileList = files
+            self.iteration_source = H5IterationSource(files, auxpath=auxpath, pcoord_ndim=pcoord_ndim)
+        self.n_data_files = len(self.fileList)
+        if tau is None:
+            log.warning("No tau provided, defaulting to 1.")
+            tau = 1.0
+        self.tau = float(tau)
+        self.dimReduceMethod = dim_reduce_method
+        if self.dimReduceMethod == "none":
+            self.coordinates = Coordinates()
+        self.use_weights_in_clustering = use_weights_in_clustering
+        try:
+            self.load_iter_data(1)
+            rec = self.iteration_source.get(1)
+            c = rec.child_coords
+            self.nAtoms = c.shape[1]
+            self.coord_ndim = c.shape[2] if c.ndim == 3 else 1
+            self.coordsExist = True
+        except KeyError:
+            log.error("Problem getting coordinates, they don't exist yet.")
+            self.coordsExist = False
+        log.debug("msm_we model successfully initialized")
+
+    def dimReduce(self, *args, **kwargs):
+        """Only the identity ('none') is fitted here; fitting PCA/TICA/VAMP is out of scope.  Assign a fitted
+        object with a ``.transform`` (e.g. ``LinearCoordinates``) to ``self.coordinates`` to use one."""
+        if self.dimReduceMethod == "none" or self.coordinates is None:
+            self.coordinates = Coordinates()
+
+    # ---- bounds (reference: msm_we.py:279-440) -------------------------------------------------
+    def _check_bounds(self, bounds):
+        bounds = np.array(bounds)
+        if len(bounds.shape) == 1:
+            log.warning("Please provide 1-D boundaries as a list of lists or 2-D array [[lower bound, upper bound]]. "
+                        "Automatically doing conversion for now.")
+            bounds = np.reshape(bounds, (1, 2))
+        assert bounds.shape == (self.pcoord_ndim, 2), \
+            f"Shape of bounds was {bounds.shape}, should've been ({self.pcoord_ndim}, 2)"
+        assert np.all([b[0] < b[1] for b in bounds]), "A boundary has a lower bound larger than its upper bound"
+        centers = np.full(self.pcoord_ndim, fill_value=np.nan)
+        for i, (lo, hi) in enumerate(bounds):
+            if not abs(lo) == np.inf and not abs(hi) == np.inf:
+                centers[i] = np.mean([lo, hi])
+            else:
+                centers[i] = [lo, hi][abs(lo) == np.inf]
+        return bounds, centers
+
+    @property
+    def basis_pcoord_bounds(self):
+        return self._basis_pcoord_bounds
+
+    @basis_pcoord_bounds.setter
+    def basis_pcoord_bounds(self, bounds):
+        self._basis_pcoord_bounds, self.basis_bin_centers = self._check_bounds(bounds)
+
+    @property
+    def target_pcoord_bounds(self):
+        return self._target_pcoord_bounds
+
+    @target_pcoord_bounds.setter
+    def target_pcoord_bounds(self, bounds):
+        self._target_pcoord_bounds, self.target_bin_centers = self._check_bounds(bounds)
+
+    @property
+    def WEbasisp1_bounds(self):
+        return self.basis_pcoord_bounds
+
+    @WEbasisp1_bounds.setter
+    def WEbasisp1_bounds(self, bounds):
+        self.basis_pcoord_bounds = bounds
+
+    @property
+    def WEtargetp1_bounds(self):
+        return self.target_pcoord_bounds
+
+    @WEtargetp1_bounds.setter
+    def WEtargetp1_bounds(self, bounds):
+        if None in bounds:
+            raise Exception("A target boundary has not been correctly provided")
+        self.target_pcoord_bounds = bounds
+
+    @property
+    def n_lag(self):
+        return self._n_lag
+
+    @n_lag.setter
+    def n_lag(self, lag):
+        if not lag == 0:
+            raise NotImplementedError("Only a lag of 1 tau (n_lag = 0) is currently supported")
+        self._n_lag = lag
+
+    # ---- region tests (reference: msm_we.py:462-527); host versions for the control flow ----------
+    def _in_region(self, pcoords, bounds):
+        pcoords = np.asarray(pcoords)
+        inside = np.full_like(pcoords, fill_value=np.nan, dtype=np.float64)
+        for d in range(self.pcoord_ndim):
+            inside[:, d] = np.logical_and(pcoords[:, d] > bounds[d, 0], pcoords[:, d] < bounds[d, 1])
+        return np.all(inside, axis=1)
+
+    def is_WE_basis(self, pcoords):
+        return self._in_region(pcoords, self.basis_pcoord_bounds)
+
+    def is_WE_target(self, pcoords):
+        return self._in_region(pcoords, self.target_pcoord_bounds)
+
+    # ---- one-shot driver (reference: msm_we.py:588-882), hot-path steps ----------------------------
+    def build_analyze_model(self, file_paths, ref_struct, modelName, basis_pcoord_bounds, target_pcoord_bounds,
+                            dimreduce_method, tau, n_clusters, ray_kwargs={}, max_coord_iter=-1, stratified=True,
+                            streaming=True, use_ray=True, fluxmatrix_iters=[1, -1], fluxmatrix_iters_to_use=None,
+                            cross_validation_groups=2, cross_validation_blocks=4, show_live_display=True,
+                            allow_validation_failure=False, step_kwargs={}):
+        model = self
+        model.initialize(fileSpecifier=file_paths, refPDBfile=ref_struct, modelName=modelName,
+                         basis_pcoord_bounds=basis_pcoord_bounds, target_pcoord_bounds=target_pcoord_bounds,
+                         dim_reduce_method=dimreduce_method, tau=tau, **step_kwargs.get("initialize", {}))
+        model.get_iterations()
+        model.dimReduce(**step_kwargs.get("dimReduce", {}))
+        model.cluster_coordinates(n_clusters=n_clusters, streaming=streaming, use_ray=use_ray, stratified=stratified,
+                                  store_validation_model=cross_validation_groups > 0,
+                                  **step_kwargs.get("clustering", {}))
+        # the reference mutates its default list here; work on a copy
+        _fluxmatrix_iters = list(fluxmatrix_iters)
+        if _fluxmatrix_iters[1] == -1:
+            _fluxmatrix_iters[1] = model.maxIter
+        model.get_fluxMatrix(n_lag=0, first_iter=_fluxmatrix_iters[0], last_iter=_fluxmatrix_iters[1],
+                             iters_to_use=fluxmatrix_iters_to_use, use_ray=use_ray, **step_kwargs.get("fluxmatrix", {}))
+        # downstream host steps run only when the corresponding reference mixins are present
+        for step, kw in (("organize_fluxMatrix", {"use_ray": use_ray, **step_kwargs.get("organize", {})}),
+                         ("get_Tmatrix", {}), ("get_steady_state", {}), ("get_steady_state_target_flux", {})):
+            if not hasattr(model, step):
+                log.info(f"{step} is not part of msm_we_b200 (host-side analysis); stopping after the flux matrix")
+                break
+            getattr(model, step)(**kw)
+        return model
+
+
+__all__ = ["modelWE", "Coordinates", "LinearCoordinates", "ArrayIterationSource"]
