@@ -33,27 +33,35 @@ static constexpr int AS_SPIN_LIMIT = 1 << 26;
 
 // ---- bucketing -----------------------------------------------------------------------------
 
+static constexpr int AS_SMEM_BINS = 2048;   // bins whose counters fit the shared-memory histogram
+static constexpr int AS_BK_ITEMS = 8;       // points per thread in the bucketing kernels
+
 __global__ void __launch_bounds__(256)
     assign_count_kernel(const int32_t* __restrict__ bin, const uint8_t* __restrict__ flag, int64_t N, int32_t nbins,
-                        const int64_t* __restrict__ bin_offset, int64_t* __restrict__ label_out,
-                        int32_t* __restrict__ local_out, int32_t* __restrict__ bin_count) {
-    const int64_t T = bin_offset[nbins];
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
-        const uint8_t f = flag ? flag[i] : (uint8_t)0;
-        const int32_t b = bin[i];
-        if (f) {
-            // target is tested before basis (stratified_clustering.py:159-169)
-            label_out[i] = (f & MWE_FLAG_TARGET) ? T + 1 : T;
-            if (local_out) local_out[i] = -1;
-        } else if (b < 0 || b >= nbins) {
-            label_out[i] = -1;
-            if (local_out) local_out[i] = -1;
-        } else {
-            // warp-aggregated count
-            const uint32_t peers = __match_any_sync(__activemask(), b);
-            if ((peers & ((1u << lane_id()) - 1u)) == 0) atomicAdd(&bin_count[b], __popc(peers));
+                        int32_t* __restrict__ bin_count) {
+    __shared__ int32_t s_cnt[AS_SMEM_BINS];
+    const bool use_smem = nbins <= AS_SMEM_BINS;
+    if (use_smem) {
+        for (int b = threadIdx.x; b < nbins; b += 256) s_cnt[b] = 0;
+        __syncthreads();
+    }
+    const int64_t base = (int64_t)blockIdx.x * (256 * AS_BK_ITEMS);
+#pragma unroll
+    for (int j = 0; j < AS_BK_ITEMS; ++j) {
+        const int64_t i = base + j * 256 + threadIdx.x;
+        if (i < N) {
+            const uint8_t f = flag ? flag[i] : (uint8_t)0;
+            const int32_t b = bin[i];
+            if (!f && b >= 0 && b < nbins) {
+                if (use_smem) atomicAdd(&s_cnt[b], 1);
+                else atomicAdd(&bin_count[b], 1);
+            }
         }
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < nbins; b += 256)
+            if (s_cnt[b]) atomicAdd(&bin_count[b], s_cnt[b]);
     }
 }
 
@@ -98,21 +106,56 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Writes the bucket permutation and the labels of flagged / out-of-space points.  Ranks inside a CTA come
+// from shared-memory atomics, one global atomic per (CTA, bin) reserves the CTA's slice of the bucket.
 __global__ void __launch_bounds__(256)
     assign_scatter_kernel(const int32_t* __restrict__ bin, const uint8_t* __restrict__ flag, int64_t N, int32_t nbins,
-                          int32_t* __restrict__ bin_cursor, int32_t* __restrict__ perm) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
-        const uint8_t f = flag ? flag[i] : (uint8_t)0;
-        const int32_t b = bin[i];
-        if (!f && b >= 0 && b < nbins) {
-            const uint32_t peers = __match_any_sync(__activemask(), b);
-            const uint32_t lt = peers & ((1u << lane_id()) - 1u);
-            const int leader = __ffs(peers) - 1;
-            int base = 0;
-            if (lt == 0) base = atomicAdd(&bin_cursor[b], __popc(peers));
-            base = __shfl_sync(peers, base, leader);
-            perm[base + __popc(lt)] = (int32_t)i;
+                          const int64_t* __restrict__ bin_offset, int32_t* __restrict__ bin_cursor,
+                          int32_t* __restrict__ perm, int64_t* __restrict__ label_out, int32_t* __restrict__ local_out) {
+    __shared__ int32_t s_cnt[AS_SMEM_BINS];
+    const bool use_smem = nbins <= AS_SMEM_BINS;
+    const int64_t T = bin_offset[nbins];
+    if (use_smem) {
+        for (int b = threadIdx.x; b < nbins; b += 256) s_cnt[b] = 0;
+        __syncthreads();
+    }
+    const int64_t base = (int64_t)blockIdx.x * (256 * AS_BK_ITEMS);
+    int32_t mybin[AS_BK_ITEMS];
+    int32_t rank[AS_BK_ITEMS];
+#pragma unroll
+    for (int j = 0; j < AS_BK_ITEMS; ++j) {
+        const int64_t i = base + j * 256 + threadIdx.x;
+        mybin[j] = -1;
+        rank[j] = 0;
+        if (i < N) {
+            const uint8_t f = flag ? flag[i] : (uint8_t)0;
+            const int32_t b = bin[i];
+            if (f) {
+                // target is tested before basis (stratified_clustering.py:159-169)
+                label_out[i] = (f & MWE_FLAG_TARGET) ? T + 1 : T;
+                if (local_out) local_out[i] = -1;
+            } else if (b < 0 || b >= nbins) {
+                label_out[i] = -1;
+                if (local_out) local_out[i] = -1;
+            } else {
+                mybin[j] = b;
+                rank[j] = use_smem ? atomicAdd(&s_cnt[b], 1) : atomicAdd(&bin_cursor[b], 1);
+            }
+        }
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < nbins; b += 256) {
+            const int32_t c = s_cnt[b];
+            s_cnt[b] = c ? atomicAdd(&bin_cursor[b], c) : 0;   // now the CTA's base inside the bucket
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < AS_BK_ITEMS; ++j) {
+        if (mybin[j] >= 0) {
+            const int64_t i = base + j * 256 + threadIdx.x;
+            perm[(use_smem ? s_cnt[mybin[j]] : 0) + rank[j]] = (int32_t)i;
         }
     }
 }
@@ -172,6 +215,9 @@ struct AssignParams {
     const int32_t* tile_prefix;
     int64_t* label_out;
     int32_t* local_out;
+    int32_t* recheck_list;   // points whose best two scores are within rounding noise
+    int32_t* recheck_count;
+    double tie_scale;        // TIE_C * (D + 8) * 2^-53
     int ncb;  // centre blocks of NT*8 per tile
     int nch;  // k-chunks of AS_DC per centre block
 };
@@ -279,8 +325,11 @@ __global__ void __launch_bounds__(AS_THREADS) assign_dmma_kernel(const AssignPar
         int stage = 0;
         uint32_t phase = 0;
         double acc[2][NT][2];
-        double best[2] = {0.0, 0.0};
+        double best[2] = {0.0, 0.0};     // smallest score seen by this thread, per m-tile
+        double second[2] = {0.0, 0.0};   // second smallest
         int32_t besti[2] = {0, 0};
+        double xx[2] = {0.0, 0.0};       // partial ||x||^2 of rows g and g+8 (this thread's k positions)
+        double cmaxsq = 0.0;             // largest ||c||^2 among this thread's columns
         int32_t pstart = 0, pcount = 0, kb = 0;
         int64_t coff = 0;
         for (int64_t step = 0; step < total_steps; ++step) {
@@ -297,8 +346,10 @@ __global__ void __launch_bounds__(AS_THREADS) assign_dmma_kernel(const AssignPar
                 pcount = min(AS_TP, (p.bin_start[b + 1] - p.bin_start[b]) - in_bin);
                 coff = p.bin_offset[b];
                 kb = (int32_t)(p.bin_offset[b + 1] - coff);
-                best[0] = best[1] = __longlong_as_double(0x7ff0000000000000ll);  // +inf
+                best[0] = best[1] = second[0] = second[1] = __longlong_as_double(0x7ff0000000000000ll);  // +inf
                 besti[0] = besti[1] = 0;
+                xx[0] = xx[1] = 0.0;
+                cmaxsq = 0.0;
             }
             if (kc == 0) {
 #pragma unroll
@@ -316,6 +367,10 @@ __global__ void __launch_bounds__(AS_THREADS) assign_dmma_kernel(const AssignPar
             for (int ks = 0; ks < AS_DC / 4; ++ks) {
                 const double a0 = xa0[ks * 4];
                 const double a1 = xa1[ks * 4];
+                if (cb == 0) {  // ||x||^2 once per tile (needed only for the tie tolerance)
+                    xx[0] = fma(a0, a0, xx[0]);
+                    xx[1] = fma(a1, a1, xx[1]);
+                }
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     const double bv = cb0[nt * 8 * AS_LD + ks * 4];
@@ -336,24 +391,35 @@ __global__ void __launch_bounds__(AS_THREADS) assign_dmma_kernel(const AssignPar
                         const int c = cb * CROWS + nt * 8 + 2 * t + j;
                         if (c < kb) {
                             const double cs = p.csq[coff + c];
+                            cmaxsq = fmax(cmaxsq, cs);
 #pragma unroll
                             for (int mt = 0; mt < 2; ++mt) {
                                 const double s = fma(-2.0, acc[mt][nt][j], cs);
-                                if (s < best[mt]) { best[mt] = s; besti[mt] = c; }
+                                if (s < best[mt]) { second[mt] = best[mt]; best[mt] = s; besti[mt] = c; }
+                                else if (s < second[mt]) second[mt] = s;
                             }
                         }
                     }
                 if (cb == p.ncb - 1) {
+                    // every quad sees all columns: reduce the column-wise quantities over its 4 lanes
+                    double cm = cmaxsq;
+                    cm = fmax(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
+                    cm = fmax(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
+                    const double cmax = sqrt(cm);
 #pragma unroll
                     for (int mt = 0; mt < 2; ++mt) {
-                        double bs = best[mt];
+                        double bs = best[mt], sc = second[mt], xs = xx[mt];
                         int32_t bi = besti[mt];
-                        // first column of the block seeds the scan in the reference; emulate its
-                        // "first minimum wins" across the 4 lanes of the quad
 #pragma unroll
                         for (int o = 1; o <= 2; o <<= 1) {
                             const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+                            const double o2 = __shfl_xor_sync(0xffffffffu, sc, o);
                             const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                            xs += __shfl_xor_sync(0xffffffffu, xs, o);
+                            // merged second = min(larger of the two bests, both seconds)
+                            const double hi = (os < bs) ? bs : os;
+                            sc = fmin(fmin(sc, o2), hi);
+                            // lowest index wins exact ties ("first minimum" of the reference's scan)
                             if (os < bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
                         }
                         const int r = warp * 16 + mt * 8 + g;
@@ -361,10 +427,81 @@ __global__ void __launch_bounds__(AS_THREADS) assign_dmma_kernel(const AssignPar
                             const int32_t pt = p.perm[pstart + r];
                             p.label_out[pt] = coff + bi;
                             if (p.local_out) p.local_out[pt] = bi;
+                            // near-tie within fp64 rounding noise -> exact re-check pass decides (2x margin here)
+                            const double tol = 2.0 * p.tie_scale * cmax * (2.0 * sqrt(xs) + cmax);
+                            if (sc - bs <= tol) p.recheck_list[atomicAdd(p.recheck_count, 1)] = pt;
                         }
                     }
                 }
             }
+        }
+    }
+}
+
+// Near-tie re-check.  One warp per flagged point: scores of ALL centres of the point's bin from a
+// sequential fp64 FMA chain over k (the order DMMA itself uses), then
+//     label = lowest j with score_j <= min_j score_j + tol,
+//     tol   = TIE_C (D+8) 2^-53 cmax (2 ||x|| + cmax),  cmax = max_j ||c_j||,
+// i.e. scores that differ by less than the rounding noise of their own evaluation count as tied and the
+// reference's "first minimum wins" rule applies to the tie set.  Exact duplicate centres (common after
+// MiniBatchKMeans' random reassignment) and ulp-level near-duplicates therefore resolve to the lowest index.
+__global__ void __launch_bounds__(128)
+    assign_recheck_kernel(const double* __restrict__ X, int64_t ldx, int D, const int32_t* __restrict__ bin,
+                          const double* __restrict__ centers, const double* __restrict__ csq,
+                          const int64_t* __restrict__ bin_offset, const int32_t* __restrict__ list,
+                          const int32_t* __restrict__ count, double tie_scale, int64_t* __restrict__ label_out,
+                          int32_t* __restrict__ local_out) {
+    const int n = *count;
+    const int lane = threadIdx.x & 31;
+    const int warps_total = gridDim.x * (blockDim.x >> 5);
+    for (int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps_total) {
+        const int32_t pt = list[e];
+        const int32_t b = bin[pt];
+        const int64_t coff = bin_offset[b];
+        const int kb = (int)(bin_offset[b + 1] - coff);
+        const double* x = X + (int64_t)pt * ldx;
+        double xx = 0.0;
+        for (int k = 0; k < D; ++k) xx = fma(x[k], x[k], xx);
+        const double inf = __longlong_as_double(0x7ff0000000000000ll);
+        double smin = inf, cm = 0.0;
+        for (int j0 = 0; j0 < kb; j0 += 32) {
+            const int j = j0 + lane;
+            if (j < kb) {
+                const double* c = centers + (coff + j) * D;
+                double acc = 0.0;
+                for (int k = 0; k < D; ++k) acc = fma(x[k], c[k], acc);
+                const double cs = csq[coff + j];
+                const double s = fma(-2.0, acc, cs);
+                if (s < smin) smin = s;
+                cm = fmax(cm, cs);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            smin = fmin(smin, __shfl_xor_sync(0xffffffffu, smin, o));
+            cm = fmax(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+        }
+        const double cmax = sqrt(cm);
+        const double tol = tie_scale * cmax * (2.0 * sqrt(xx) + cmax);
+        int best = 0x7fffffff;
+        for (int j0 = 0; j0 < kb && best == 0x7fffffff; j0 += 32) {
+            const int j = j0 + lane;
+            int cand = 0x7fffffff;
+            if (j < kb) {
+                const double* c = centers + (coff + j) * D;
+                double acc = 0.0;
+                for (int k = 0; k < D; ++k) acc = fma(x[k], c[k], acc);
+                const double s = fma(-2.0, acc, csq[coff + j]);
+                if (s <= smin + tol) cand = j;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+            best = cand;
+        }
+        if (best == 0x7fffffff) best = 0;  // all scores NaN: the reference's scan keeps index 0
+        if (lane == 0) {
+            label_out[pt] = coff + best;
+            if (local_out) local_out[pt] = best;
         }
     }
 }
@@ -381,7 +518,11 @@ __global__ void __launch_bounds__(256) centers_sqnorm_kernel(const double* __res
     if (lane_id() == 0) csq[row] = s;
 }
 
+static constexpr double AS_TIE_C = 4.0;
+
 struct AssignWs {
+    int32_t* recheck_list;
+    int32_t* recheck_count;
     int32_t* perm;
     int32_t* bin_count;
     int32_t* bin_cursor;
@@ -391,8 +532,8 @@ struct AssignWs {
 
 static size_t assign_ws_bytes(int64_t N, int32_t nbins) {
     size_t b = 0;
-    b += align_up((size_t)(N > 0 ? N : 1) * sizeof(int32_t), 256);
-    b += 4 * align_up((size_t)(nbins + 1) * sizeof(int32_t), 256);
+    b += 2 * align_up((size_t)(N > 0 ? N : 1) * sizeof(int32_t), 256);
+    b += 5 * align_up((size_t)(nbins + 1) * sizeof(int32_t), 256);
     return b + 1024;
 }
 
@@ -468,18 +609,19 @@ extern "C" int mwe_assign_stratified_f64(const double* X, int64_t N, int D, int6
     Carver cv(workspace, workspace_bytes);
     AssignWs ws;
     ws.perm = cv.take<int32_t>((size_t)N);
-    ws.bin_count = cv.take<int32_t>((size_t)nbins + 1);
+    ws.recheck_list = cv.take<int32_t>((size_t)N);
+    ws.bin_count = cv.take<int32_t>((size_t)nbins + 2);   // [nbins + 1] doubles as the re-check counter
+    ws.recheck_count = ws.bin_count + nbins + 1;
     ws.bin_cursor = cv.take<int32_t>((size_t)nbins + 1);
     ws.bin_start = cv.take<int32_t>((size_t)nbins + 1);
     ws.tile_prefix = cv.take<int32_t>((size_t)nbins + 1);
 
-    MWE_CHECK_CUDA(cudaMemsetAsync(ws.bin_count, 0, (size_t)(nbins + 1) * sizeof(int32_t), s));
-    int64_t blocks = (N + 255) / 256;
-    const int64_t cap = (int64_t)sm_count() * 8;
-    if (blocks > cap) blocks = cap;
-    assign_count_kernel<<<(unsigned)blocks, 256, 0, s>>>(bin, flag, N, nbins, bin_offset, label_out, local_out, ws.bin_count);
+    MWE_CHECK_CUDA(cudaMemsetAsync(ws.bin_count, 0, (size_t)(nbins + 2) * sizeof(int32_t), s));
+    const int64_t blocks = (N + 256 * AS_BK_ITEMS - 1) / (256 * AS_BK_ITEMS);
+    assign_count_kernel<<<(unsigned)blocks, 256, 0, s>>>(bin, flag, N, nbins, ws.bin_count);
     assign_scan_kernel<<<1, 256, 0, s>>>(ws.bin_count, bin_offset, nbins, ws.bin_start, ws.bin_cursor, ws.tile_prefix, err_count);
-    assign_scatter_kernel<<<(unsigned)blocks, 256, 0, s>>>(bin, flag, N, nbins, ws.bin_cursor, ws.perm);
+    assign_scatter_kernel<<<(unsigned)blocks, 256, 0, s>>>(bin, flag, N, nbins, bin_offset, ws.bin_cursor, ws.perm, label_out,
+                                                          local_out);
     MWE_CHECK_LAUNCH();
 
     // centre-block width: smallest instantiated NT covering max_k, capped at 16 (128 centres / block)
@@ -491,10 +633,17 @@ extern "C" int mwe_assign_stratified_f64(const double* X, int64_t N, int D, int6
     p.X = X; p.ldx = ldx; p.D = D; p.centers = centers; p.csq = csq; p.bin_offset = bin_offset; p.nbins = nbins;
     p.perm = ws.perm; p.bin_start = ws.bin_start; p.tile_prefix = ws.tile_prefix;
     p.label_out = label_out; p.local_out = local_out;
+    p.recheck_list = ws.recheck_list; p.recheck_count = ws.recheck_count;
+    p.tie_scale = AS_TIE_C * (double)(D + 8) * 1.1102230246251565e-16;
     p.ncb = (max_k + nt * 8 - 1) / (nt * 8);
     p.nch = (D + AS_DC - 1) / AS_DC;
     const int64_t max_tiles = (N + AS_TP - 1) / AS_TP + nbins;
     const bool vec2 = (D % 2 == 0) && (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(centers) & 15) == 0);
-    return vec2 ? dispatch_nt<2>(nt, p, max_tiles, s) : dispatch_nt<1>(nt, p, max_tiles, s);
+    const int rc = vec2 ? dispatch_nt<2>(nt, p, max_tiles, s) : dispatch_nt<1>(nt, p, max_tiles, s);
+    if (rc != MWE_OK) return rc;
+    assign_recheck_kernel<<<sm_count(), 128, 0, s>>>(X, ldx, D, bin, centers, csq, bin_offset, ws.recheck_list,
+                                                    ws.recheck_count, p.tie_scale, label_out, local_out);
+    MWE_CHECK_LAUNCH();
+    return MWE_OK;
 }

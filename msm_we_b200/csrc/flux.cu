@@ -11,10 +11,15 @@
 //             a sentinel cell that sorts last and is dropped
 //   sort    : stable LSD radix sort by cell (radix_sort.cu), value = transition index, so inside a
 //             cell the transitions stay in (iteration, segment) order
-//   segsum  : the thread at the head of each run of equal cells adds the weights in that order --
-//             per iteration first, then across iterations when iteration offsets are given, which
-//             is exactly the association of the reference's serial path -- and performs the single
-//             write of that cell (dense += or one COO triple).  No floating-point atomics anywhere.
+//   mark    : gather weights in sorted order; flag the first element of every cell and of every
+//             (cell, iteration) group
+//   group   : one thread per (cell, iteration) group adds its weights in segment order -- the value
+//             scipy's coo_matrix gives that iteration's matrix cell
+//   cell    : one thread per cell adds the cell's groups in iteration order onto the running matrix
+//             value and performs the single write (dense, or one COO triple)
+//             This two-level sum IS the association of the reference's serial path, the chains are
+//             bounded by segments-per-iteration and by the iteration count, and there are no
+//             floating-point atomics anywhere, so the result does not depend on thread scheduling.
 // Integer/HBM-bound: algorithmic bytes per transition = 2*8 (labels) + 8 (weight) [+2 flags +2 colours].
 #include "common.cuh"
 #include "sort.cuh"
@@ -52,15 +57,6 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-__global__ void __launch_bounds__(256)
-    flux_heads_kernel(const uint64_t* __restrict__ keys, int64_t N, uint64_t sentinel, int32_t* __restrict__ head) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
-        const uint64_t k = keys[i];
-        head[i] = (k != sentinel && (i == 0 || keys[i - 1] != k)) ? 1 : 0;
-    }
-}
-
 // iteration that owns transition idx: largest it with offsets[it] <= idx
 __device__ __forceinline__ int64_t find_iter(const int64_t* __restrict__ offsets, int64_t n_iters, int64_t idx) {
     int64_t lo = 0, hi = n_iters;  // answer in [lo, hi)
@@ -71,49 +67,116 @@ __device__ __forceinline__ int64_t find_iter(const int64_t* __restrict__ offsets
     return lo;
 }
 
+// Pass 1 (one thread per sorted position): gather the weight, mark where a new matrix cell starts
+// (cell head) and where a new (cell, iteration) group starts (sub head).
+//   flags[q] bit0 = sub head, bit1 = cell head.  Sentinel (dropped) transitions carry no flags.
 __global__ void __launch_bounds__(256)
-    flux_segsum_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t N,
-                       uint64_t sentinel, const double* __restrict__ w, const int64_t* __restrict__ iter_offsets,
-                       int64_t n_iters, uint64_t CM, double* __restrict__ dense, const int32_t* __restrict__ head_pos,
-                       int64_t* __restrict__ coo_row, int64_t* __restrict__ coo_col, double* __restrict__ coo_val) {
+    flux_mark_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t N,
+                     uint64_t sentinel, const double* __restrict__ w, const int64_t* __restrict__ iter_offsets,
+                     int64_t n_iters, double* __restrict__ wv, int32_t* __restrict__ sub_head,
+                     int32_t* __restrict__ cell_head) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
-        const uint64_t k = keys[i];
-        if (k == sentinel) continue;
-        if (i > 0 && keys[i - 1] == k) continue;  // not a run head
-        // `total` continues the running sum already in the dense matrix (chunked calls keep the serial
-        // association ((F + it_a) + it_b) + ...); `fresh` is the sum of this call alone (COO output)
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += stride) {
+        const uint64_t k = keys[q];
+        int sh = 0, ch = 0;
+        if (k != sentinel) {
+            const uint32_t idx = vals[q];
+            if (w) wv[q] = w[idx];
+            ch = (q == 0 || keys[q - 1] != k) ? 1 : 0;
+            sh = ch;
+            if (!ch && iter_offsets) {
+                // same cell as the previous element (which has a smaller transition index): a new group
+                // starts when the previous element belongs to an earlier iteration
+                const int64_t it = find_iter(iter_offsets, n_iters, (int64_t)idx);
+                sh = ((int64_t)vals[q - 1] < iter_offsets[it]) ? 1 : 0;
+            }
+        }
+        sub_head[q] = sh;
+        cell_head[q] = ch;
+    }
+}
+
+// Pass 2 (one thread per sub head): sum the weights of one (cell, iteration) group in segment order --
+// what scipy's coo_matrix -> dense does for that iteration's matrix.  Unit weights: the count, exactly.
+__global__ void __launch_bounds__(256)
+    flux_group_sum_kernel(const uint64_t* __restrict__ keys, int64_t N, uint64_t sentinel, const double* __restrict__ wv,
+                          bool have_w, const int32_t* __restrict__ sub_head, const int32_t* __restrict__ sub_pos,
+                          const int32_t* __restrict__ cell_head, double* __restrict__ group_sum,
+                          uint8_t* __restrict__ group_is_cell_head, uint64_t* __restrict__ group_key) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += stride) {
+        if (!sub_head[q]) continue;
+        const int32_t gidx = sub_pos[q];
+        double part = 0.0;
+        int64_t e = q;
+        if (have_w) {
+            part = wv[q];
+            e = q + 1;
+            // 4 loads in flight; the adds stay strictly sequential
+            while (e + 4 <= N && !(sub_head[e] | sub_head[e + 1] | sub_head[e + 2] | sub_head[e + 3]) &&
+                   keys[e + 3] != sentinel) {
+                const double a = wv[e], b = wv[e + 1], c = wv[e + 2], d = wv[e + 3];
+                part = __dadd_rn(part, a);
+                part = __dadd_rn(part, b);
+                part = __dadd_rn(part, c);
+                part = __dadd_rn(part, d);
+                e += 4;
+            }
+            while (e < N && !sub_head[e] && keys[e] != sentinel) {
+                part = __dadd_rn(part, wv[e]);
+                ++e;
+            }
+        } else {
+            e = q + 1;
+            while (e < N && !sub_head[e] && keys[e] != sentinel) ++e;
+            part = (double)(e - q);
+        }
+        group_sum[gidx] = part;
+        group_is_cell_head[gidx] = (uint8_t)cell_head[q];
+        group_key[gidx] = keys[q];
+    }
+}
+
+// Pass 3 (one thread per cell): add the cell's per-iteration groups in iteration order onto the running
+// value of the dense matrix (the reference's `fluxMatrix = fluxMatrix + fluxMatrixI`), single write.
+__global__ void __launch_bounds__(256)
+    flux_cell_sum_kernel(const double* __restrict__ group_sum, const uint8_t* __restrict__ group_is_cell_head,
+                         const uint64_t* __restrict__ group_key, const int64_t* __restrict__ n_groups_p, uint64_t CM,
+                         double* __restrict__ dense, const int32_t* __restrict__ cell_pos, int64_t* __restrict__ coo_row,
+                         int64_t* __restrict__ coo_col, double* __restrict__ coo_val) {
+    const int64_t n_groups = *n_groups_p;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < n_groups; gi += stride) {
+        if (!group_is_cell_head[gi]) continue;
+        const uint64_t k = group_key[gi];
         double total = dense ? dense[k] : 0.0;
         double fresh = 0.0;
-        double part = 0.0;
-        bool have_part = false;
-        int64_t it_end = -1;  // exclusive end (transition index) of the iteration being summed
-        for (int64_t q = i; q < N && keys[q] == k; ++q) {
-            const uint32_t idx = vals[q];
-            const double wv = w ? w[idx] : 1.0;
-            if (iter_offsets && (int64_t)idx >= it_end) {
-                // crossed into a later iteration: close the previous partial (dense add in the reference)
-                if (have_part) {
-                    total = __dadd_rn(total, part);
-                    fresh = __dadd_rn(fresh, part);
-                }
-                part = 0.0;
-                it_end = iter_offsets[find_iter(iter_offsets, n_iters, (int64_t)idx) + 1];
-            }
-            part = __dadd_rn(part, wv);
-            have_part = true;
-        }
-        total = __dadd_rn(total, part);
-        fresh = __dadd_rn(fresh, part);
-        const uint64_t r = k / CM, c = k - r * CM;
+        int64_t e = gi;
+        do {
+            const double v = group_sum[e];
+            total = __dadd_rn(total, v);
+            fresh = (e == gi) ? v : __dadd_rn(fresh, v);
+            ++e;
+        } while (e < n_groups && !group_is_cell_head[e]);
         if (dense) dense[k] = total;
         if (coo_val) {
-            const int32_t pos = head_pos[i];
+            const int32_t pos = cell_pos[gi];
+            const uint64_t r = k / CM;
             coo_row[pos] = (int64_t)r;
-            coo_col[pos] = (int64_t)c;
+            coo_col[pos] = (int64_t)(k - r * CM);
             coo_val[pos] = fresh;
         }
     }
+}
+
+// group -> 1 if it starts a cell (input of the COO position scan)
+__global__ void __launch_bounds__(256)
+    flux_cellflag_kernel(const uint8_t* __restrict__ group_is_cell_head, const int64_t* __restrict__ n_groups_p,
+                         int64_t cap, int32_t* __restrict__ out) {
+    const int64_t n_groups = *n_groups_p;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < cap; gi += stride)
+        out[gi] = (gi < n_groups && group_is_cell_head[gi]) ? 1 : 0;
 }
 
 static size_t flux_ws_bytes(int64_t N) {
@@ -121,7 +184,10 @@ static size_t flux_ws_bytes(int64_t N) {
     size_t b = 0;
     b += align_up((size_t)N * sizeof(uint64_t), 256);  // keys
     b += align_up((size_t)N * sizeof(uint32_t), 256);  // vals
-    b += align_up((size_t)N * sizeof(int32_t), 256);   // head flags / positions
+    b += 3 * align_up((size_t)N * sizeof(int32_t), 256);   // sub heads / cell heads / positions
+    b += 2 * align_up((size_t)N * sizeof(double), 256);    // gathered weights, group sums
+    b += align_up((size_t)N * sizeof(uint64_t), 256);      // group keys
+    b += align_up((size_t)N, 256) + 256;                   // group flags, group counter
     b += sort_workspace_bytes(N);
     b += scan_workspace_bytes(N);
     return b + 1024;
@@ -159,7 +225,14 @@ extern "C" int mwe_flux_accumulate_f64(const int64_t* start, const int64_t* end,
     Carver cv(workspace, workspace_bytes);
     uint64_t* keys = cv.take<uint64_t>((size_t)N);
     uint32_t* vals = cv.take<uint32_t>((size_t)N);
-    int32_t* head = cv.take<int32_t>((size_t)N);
+    int32_t* sub_head = cv.take<int32_t>((size_t)N);
+    int32_t* cell_head = cv.take<int32_t>((size_t)N);
+    int32_t* pos = cv.take<int32_t>((size_t)N);
+    double* wv = cv.take<double>((size_t)N);
+    double* group_sum = cv.take<double>((size_t)N);
+    uint64_t* group_key = cv.take<uint64_t>((size_t)N);
+    uint8_t* group_flag = cv.take<uint8_t>((size_t)N);
+    int64_t* n_groups = cv.take<int64_t>(1);
     const size_t sort_bytes = sort_workspace_bytes(N);
     void* sort_ws = cv.take<char>(sort_bytes);
     const size_t scan_bytes = scan_workspace_bytes(N);
@@ -177,14 +250,22 @@ extern "C" int mwe_flux_accumulate_f64(const int64_t* start, const int64_t* end,
     uint32_t* vs;
     int rc = sort_pairs(keys, vals, N, key_bits, sort_ws, sort_bytes, s, &ks, &vs);
     if (rc != MWE_OK) return rc;
+    flux_mark_kernel<<<(unsigned)blocks, 256, 0, s>>>(ks, vs, N, sentinel, w, iter_offsets, n_iters, wv, sub_head, cell_head);
+    MWE_CHECK_LAUNCH();
+    rc = exclusive_scan_i32(sub_head, pos, N, n_groups, scan_ws, scan_bytes, s);
+    if (rc != MWE_OK) return rc;
+    flux_group_sum_kernel<<<(unsigned)blocks, 256, 0, s>>>(ks, N, sentinel, wv, w != nullptr, sub_head, pos, cell_head,
+                                                          group_sum, group_flag, group_key);
+    MWE_CHECK_LAUNCH();
     if (coo_val) {
-        flux_heads_kernel<<<(unsigned)blocks, 256, 0, s>>>(ks, N, sentinel, head);
+        // COO slot of every cell = rank of its head group among the cell heads
+        flux_cellflag_kernel<<<(unsigned)blocks, 256, 0, s>>>(group_flag, n_groups, N, pos);
         MWE_CHECK_LAUNCH();
-        rc = exclusive_scan_i32(head, head, N, nnz_out, scan_ws, scan_bytes, s);
+        rc = exclusive_scan_i32(pos, pos, N, nnz_out, scan_ws, scan_bytes, s);
         if (rc != MWE_OK) return rc;
     }
-    flux_segsum_kernel<<<(unsigned)blocks, 256, 0, s>>>(ks, vs, N, sentinel, w, iter_offsets, n_iters, CM, dense_inout,
-                                                       head, coo_row, coo_col, coo_val);
+    flux_cell_sum_kernel<<<(unsigned)blocks, 256, 0, s>>>(group_sum, group_flag, group_key, n_groups, CM, dense_inout, pos,
+                                                         coo_row, coo_col, coo_val);
     MWE_CHECK_LAUNCH();
     return MWE_OK;
 }

@@ -142,6 +142,42 @@ def kmeans_assign(X: np.ndarray, centers: np.ndarray, return_margin: bool = Fals
     return labels, gap / scale
 
 
+TIE_C = 4.0
+
+
+def tie_tolerance(X, centers):
+    """Per-point width of the band inside which two scores count as tied on the GPU:
+    TIE_C (D+8) 2^-53 cmax (2 ||x|| + cmax), cmax = max_j ||c_j||  -- a few times the worst-case rounding
+    error of evaluating ``||c||^2 - 2 x.c`` in fp64 (msm_we_b200/csrc/assign.cu, assign_recheck_kernel)."""
+    X = np.asarray(X, dtype=np.float64)
+    centers = np.asarray(centers, dtype=np.float64)
+    D = X.shape[1]
+    xn = np.sqrt(np.einsum("ij,ij->i", X, X))
+    cmax = np.sqrt(np.einsum("ij,ij->i", centers, centers).max())
+    return TIE_C * (D + 8) * 2.0 ** -53 * cmax * (2.0 * xn + cmax)
+
+
+def kmeans_assign_tiebreak(X, centers, return_ambiguous=False):
+    """The GPU path's DEFINED resolution of floating-point near-ties: the lowest index among the centres
+    whose score is within ``tie_tolerance`` of the minimum.  Outside that band it is identical to
+    ``kmeans_assign`` (the reference's strict-< scan); inside it the reference's own answer depends on
+    the BLAS summation order, except for exactly equal scores where both pick the lowest index.
+    ``return_ambiguous`` marks rows where some score lies so close to the band's edge (0.5..1.5 tol)
+    that evaluation order could move it across."""
+    s = kmeans_scores(X, centers)
+    tol = tie_tolerance(X, centers)
+    smin = np.min(s, axis=1)
+    with np.errstate(invalid="ignore"):
+        rel = s - smin[:, None]
+        tied = rel <= tol[:, None]
+    labels = np.argmax(tied, axis=1)  # first True; an all-NaN row gives 0 like the reference's scan
+    if not return_ambiguous:
+        return labels
+    with np.errstate(invalid="ignore"):
+        amb = ((rel > 0.5 * tol[:, None]) & (rel < 1.5 * tol[:, None])).any(axis=1)
+    return labels, amb
+
+
 def kmeans_assign_exact(X, centers):
     """Slow exact-rational restatement for tiny tie-break cases (pure Python, fractions)."""
     from fractions import Fraction
@@ -242,7 +278,7 @@ class StratifiedOracle:
                 for i in sel:
                     out[i] = model.predict([coords[i]])[0] + offsets[b]
             else:
-                out[sel] = kmeans_assign(coords[sel], self.centers_per_bin[b]) + offsets[b]
+                out[sel] = kmeans_assign_tiebreak(coords[sel], self.centers_per_bin[b]) + offsets[b]
         return out
 
 
@@ -273,7 +309,7 @@ def minibatch_update(X, sample_weight, centers, counts, labels):
 
 def mini_batch_step(X, sample_weight, centers, counts, random_state, random_reassign, reassignment_ratio=0.01):
     """One ``_mini_batch_step`` (sklearn/cluster/_kmeans.py:1566-1684), dense, in place."""
-    labels = kmeans_assign(X, centers)
+    labels = kmeans_assign_tiebreak(X, centers)
     minibatch_update(X, sample_weight, centers, counts, labels)
     if random_reassign and reassignment_ratio > 0:
         to_reassign = counts < reassignment_ratio * counts.max()
