@@ -23,12 +23,12 @@
 
 namespace mwe {
 
-static constexpr int AS_TP = 64;                // points per tile
-static constexpr int AS_CWARPS = 4;             // consumer warps, 16 points each
-static constexpr int AS_THREADS = (AS_CWARPS + 1) * 32;
 static constexpr int AS_DC = 32;                // doubles per k-chunk
 static constexpr int AS_LD = AS_DC + 4;         // padded row: 72 words == 8 (mod 32): conflict-free LDS.64 fragments
-static constexpr int AS_STAGES = 3;
+static constexpr int AS_MAX_STAGES = 8;
+static constexpr int AS_TABLE_BINS = 1024;     // bins whose tile tables are cached in shared memory
+static constexpr size_t AS_SMEM_BUDGET = 200 * 1024;        // one 8-warp CTA per SM
+static constexpr size_t AS_SMEM_BUDGET_SMALL = 72 * 1024;   // three 4-warp CTAs per SM
 static constexpr int AS_SPIN_LIMIT = 1 << 26;
 
 // ---- bucketing -----------------------------------------------------------------------------
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     assign_scan_kernel(const int32_t* __restrict__ bin_count, const int64_t* __restrict__ bin_offset, int32_t nbins,
                        int32_t* __restrict__ bin_start, int32_t* __restrict__ bin_cursor,
-                       int32_t* __restrict__ tile_prefix, int32_t* __restrict__ err_count) {
+                       int32_t* __restrict__ tile_prefix, int32_t* __restrict__ err_count, int tile_points) {
     __shared__ int scratch[9];
     __shared__ int s_carry[2];
     if (threadIdx.x == 0) { s_carry[0] = 0; s_carry[1] = 0; }
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256)
                 atomicAdd(&err_count[MWE_ERR_NO_CENTERS], cnt);
                 tiles = 0;
             } else {
-                tiles = (cnt + AS_TP - 1) / AS_TP;
+                tiles = (cnt + tile_points - 1) / tile_points;
             }
         }
         int tot_c, tot_t;
@@ -196,6 +196,16 @@ __device__ __forceinline__ void cp_async_zfill(void* dst, const void* src, int s
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
     }
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+// TMA bulk copy global -> shared, completion (in bytes) signalled on an mbarrier
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
@@ -218,159 +228,227 @@ struct AssignParams {
     int32_t* recheck_list;   // points whose best two scores are within rounding noise
     int32_t* recheck_count;
     double tie_scale;        // TIE_C * (D + 8) * 2^-53
-    int ncb;  // centre blocks of NT*8 per tile
-    int nch;  // k-chunks of AS_DC per centre block
+    int ncb;      // centre blocks of NT*8 per tile
+    int nch;      // k-chunks of AS_DC per centre block
+    int nstages;  // depth of the shared-memory ring
 };
 
-// tile -> bin lookup; tiles handled by one CTA are increasing, so scan forward from the last bin
-struct TileCursor {
+// Tile bookkeeping tables (shared memory copies when the bin count allows, else the global arrays).
+struct TileTables {
+    const int32_t* tile_prefix;   // [nbins+1]
+    const int32_t* bin_start;     // [nbins+1]
+    const int64_t* bin_offset;    // [nbins+1]
+    int32_t nbins;
+};
+
+// Per-warp view of the tile sequence of this CTA.  Three walkers run at different distances: the tile
+// whose point indices are being prefetched, the tile whose copies are being issued, the tile being
+// computed.  Tiles handled by one CTA are increasing, so the bin is found by scanning forward.
+template <int TP>
+struct TileWalk {
+    int ti, cb, kc;      // tile ordinal inside the CTA, centre block, k-chunk
     int32_t bin;
-    __device__ __forceinline__ void seek(const int32_t* __restrict__ tile_prefix, int32_t nbins, int32_t tile) {
-        while (bin + 1 < nbins && tile >= tile_prefix[bin + 1]) ++bin;
+    int32_t pstart, pcount, kb;
+    int64_t coff;
+    __device__ __forceinline__ void load(const TileTables& tt, int my_tiles) {
+        if (ti >= my_tiles) { pcount = 0; return; }
+        const int32_t tile = (int32_t)blockIdx.x + ti * (int32_t)gridDim.x;
+        while (bin + 1 < tt.nbins && tile >= tt.tile_prefix[bin + 1]) ++bin;
+        const int32_t in_bin = (tile - tt.tile_prefix[bin]) * TP;
+        pstart = tt.bin_start[bin] + in_bin;
+        pcount = min(TP, (tt.bin_start[bin + 1] - tt.bin_start[bin]) - in_bin);
+        coff = tt.bin_offset[bin];
+        kb = (int32_t)(tt.bin_offset[bin + 1] - coff);
+    }
+    __device__ __forceinline__ void next_tile(const TileTables& tt, int my_tiles) {
+        ++ti;
+        load(tt, my_tiles);
+    }
+    // returns true when the walk entered a new tile
+    __device__ __forceinline__ bool advance(const TileTables& tt, int ncb, int nch, int my_tiles) {
+        if (++kc < nch) return false;
+        kc = 0;
+        if (++cb < ncb) return false;
+        cb = 0;
+        next_tile(tt, my_tiles);
+        return true;
     }
 };
 
-template <int NT, int VEC>
-__global__ void __launch_bounds__(AS_THREADS) assign_dmma_kernel(const AssignParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+// K1 main kernel.
+//   NT  : 8-column centre sub-tiles per centre block (block = NT*8 centres)
+//   VEC : 2 = 16-byte cp.async (LDGSTS; needs 16-byte aligned rows: even D and row stride), 1 = 8-byte
+//         cp.async for odd D / unaligned views.  Both zero-fill past the end of a row, so the k-tail and
+//         short tiles need no special casing in the math.
+//   CW  : warps per CTA; a tile is CW*16 points.  Small centre blocks run 4-warp CTAs, several per SM, so
+//         one CTA's latency stalls are covered by another; large blocks run one 8-warp CTA per SM.
+// Every warp computes; each also copies its own 16 point rows and 16 of the centre rows, nstages-1 steps
+// ahead of the step it computes (one step = one 32-column k-chunk of one centre block of one tile).
+// (A cp.async.bulk / UBLKCP row copy was tried first: one instruction per 256-byte row, issued lane by
+// lane through an ELECT loop, cost more issue slots than the vectorised LDGSTS below -- profiles/.)
+template <int NT, int VEC, int CW>
+__global__ void __launch_bounds__(CW * 32, (CW == 4 ? 3 : 1)) assign_dmma_kernel(const AssignParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int TP = CW * 16;
+    constexpr int THREADS = CW * 32;
     constexpr int CROWS = NT * 8;
-    constexpr int STAGE_DOUBLES = (AS_TP + CROWS) * AS_LD;
+    constexpr int STAGE_DOUBLES = (TP + CROWS) * AS_LD + CROWS;   // rows + the block's ||c||^2
+    constexpr int SEGS = AS_DC / VEC;          // copies per row chunk (16 or 32)
+    constexpr int RPI = 32 / SEGS;             // rows covered by one warp-wide copy instruction (2 or 1)
+    constexpr int XQ = 16 / RPI;               // copy instructions for the warp's 16 point rows
+    constexpr int CPW = (CROWS + CW - 1) / CW; // centre rows copied per warp
+    constexpr int CQ = (CPW + RPI - 1) / RPI;
     double* stage_base = reinterpret_cast<double*>(smem_raw);
-    __shared__ uint64_t full_bar[AS_STAGES];
-    __shared__ uint64_t empty_bar[AS_STAGES];
+    __shared__ uint64_t full_bar[AS_MAX_STAGES];
+    __shared__ uint64_t empty_bar[AS_MAX_STAGES];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int nstages = p.nstages;
     if (threadIdx.x == 0) {
-#pragma unroll
-        for (int s = 0; s < AS_STAGES; ++s) {
-            mbar_init(&full_bar[s], 32);         // every producer lane arrives (cp.async ... noinc)
-            mbar_init(&empty_bar[s], AS_CWARPS); // one elected lane per consumer warp
+        for (int s = 0; s < nstages; ++s) {
+            mbar_init(&full_bar[s], THREADS);   // every thread: cp.async.mbarrier.arrive.noinc
+            mbar_init(&empty_bar[s], CW);       // one elected lane per warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // bin tables -> shared memory (they are walked once per tile by every warp)
+    TileTables tt{p.tile_prefix, p.bin_start, p.bin_offset, p.nbins};
+    if (p.nbins <= AS_TABLE_BINS) {
+        int32_t* s_tp = reinterpret_cast<int32_t*>(stage_base + (size_t)nstages * STAGE_DOUBLES);
+        int32_t* s_bs = s_tp + (p.nbins + 1);
+        int64_t* s_bo = reinterpret_cast<int64_t*>(s_bs + (p.nbins + 1) + ((2 * (p.nbins + 1)) & 1));
+        for (int b = threadIdx.x; b <= p.nbins; b += THREADS) {
+            s_tp[b] = p.tile_prefix[b];
+            s_bs[b] = p.bin_start[b];
+            s_bo[b] = p.bin_offset[b];
+        }
+        tt = TileTables{s_tp, s_bs, s_bo, p.nbins};
+    }
     __syncthreads();
 
-    const int32_t n_tiles = p.tile_prefix[p.nbins];
+    const int32_t n_tiles = tt.tile_prefix[p.nbins];
     const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    const int spt = p.ncb * p.nch;  // pipeline steps per tile
-    const int64_t total_steps = (int64_t)my_tiles * spt;
+    const int64_t total_steps = (int64_t)my_tiles * p.ncb * p.nch;
+    const int g = lane >> 2;  // fragment row / column group
+    const int t = lane & 3;   // position inside the k4 step
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    const float finf = __int_as_float(0x7f800000);
 
-    if (warp == AS_CWARPS) {
-        // ===================== producer warp =====================
-        constexpr int SEGS = AS_DC / VEC;       // copies per row chunk
-        constexpr int RPI = 32 / SEGS;          // rows covered by one warp-wide copy instruction
-        const int seg = lane % SEGS;
-        const int rsub = lane / SEGS;
-        TileCursor cur{0};
-        int32_t perm_lo = 0, perm_hi = 0;
-        int32_t pcount = 0;
-        int64_t coff = 0;
-        int32_t kb = 0;
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int64_t step = 0; step < total_steps; ++step) {
-            const int ti = (int)(step / spt);
-            const int rem = (int)(step - (int64_t)ti * spt);
-            const int cb = rem / p.nch;
-            const int kc = rem - cb * p.nch;
-            if (rem == 0) {
-                const int32_t tile = (int32_t)blockIdx.x + ti * (int32_t)gridDim.x;
-                cur.seek(p.tile_prefix, p.nbins, tile);
-                const int32_t b = cur.bin;
-                const int32_t in_bin = (tile - p.tile_prefix[b]) * AS_TP;
-                const int32_t pstart = p.bin_start[b] + in_bin;
-                const int32_t bcount = p.bin_start[b + 1] - p.bin_start[b];
-                pcount = min(AS_TP, bcount - in_bin);
-                coff = p.bin_offset[b];
-                kb = (int32_t)(p.bin_offset[b + 1] - coff);
-                perm_lo = (lane < pcount) ? p.perm[pstart + lane] : -1;
-                perm_hi = (lane + 32 < pcount) ? p.perm[pstart + lane + 32] : -1;
-            }
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
-            double* sX = stage_base + (size_t)stage * STAGE_DOUBLES;
-            double* sC = sX + AS_TP * AS_LD;
-            const int k0 = kc * AS_DC;
-            const int kcol = k0 + seg * VEC;
-            int vbytes = (p.D - kcol) * 8;
-            vbytes = vbytes < 0 ? 0 : (vbytes > VEC * 8 ? VEC * 8 : vbytes);
-            // point rows
-#pragma unroll 4
-            for (int r0 = 0; r0 < AS_TP; r0 += RPI) {
-                const int r = r0 + rsub;
-                const int32_t idx = __shfl_sync(0xffffffffu, (r < 32) ? perm_lo : perm_hi, r & 31);
-                const bool ok = idx >= 0;
-                const double* src = ok ? (p.X + (int64_t)idx * p.ldx + kcol) : p.X;
-                cp_async_zfill<VEC>(sX + r * AS_LD + seg * VEC, src, ok ? vbytes : 0);
-            }
-            // centre rows of this block
-#pragma unroll 4
-            for (int r0 = 0; r0 < CROWS; r0 += RPI) {
-                const int r = r0 + rsub;
-                const int c = cb * CROWS + r;
-                const bool ok = c < kb;
-                const double* src = ok ? (p.centers + (coff + c) * p.D + kcol) : p.centers;
-                cp_async_zfill<VEC>(sC + r * AS_LD + seg * VEC, src, ok ? vbytes : 0);
-            }
-            cp_async_arrive_noinc(&full_bar[stage]);
-            if (++stage == AS_STAGES) { stage = 0; phase ^= 1u; }
+    TileWalk<TP> iw{0, 0, 0, 0, 0, 0, 0, 0};   // copies being issued
+    iw.load(tt, my_tiles);
+    TileWalk<TP> cw = iw;                     // tile being computed
+    TileWalk<TP> pw = iw;                     // tile whose point indices are being prefetched (one ahead of iw)
+    // copy geometry of this lane: column segment `seg`, row sub-index `rsub` inside each instruction
+    const int seg = lane % SEGS;
+    const int rsub = lane / SEGS;
+    const int kcol0 = seg * VEC;
+    int32_t pidx[XQ];        // point index of the rows this lane copies for the tile of iw (-1 = none)
+    int32_t pidx_next[XQ];   // same for the following tile (in flight while iw's tile is being issued)
+    auto fetch_pidx = [&](const TileWalk<TP>& w, int32_t* out) {
+#pragma unroll
+        for (int q = 0; q < XQ; ++q) {
+            const int r = warp * 16 + q * RPI + rsub;
+            out[q] = (r < w.pcount) ? p.perm[w.pstart + r] : -1;
         }
-        // drain outstanding copies before the CTA may exit
-        asm volatile("cp.async.wait_all;" ::: "memory");
-    } else {
-        // ===================== consumer warps =====================
-        const int g = lane >> 2;  // fragment row / column group
-        const int t = lane & 3;   // position inside the k4 step
-        TileCursor cur{0};
-        int stage = 0;
-        uint32_t phase = 0;
-        double acc[2][NT][2];
-        double best[2] = {0.0, 0.0};     // smallest score seen by this thread, per m-tile
-        double second[2] = {0.0, 0.0};   // second smallest
-        int32_t besti[2] = {0, 0};
-        double xx[2] = {0.0, 0.0};       // partial ||x||^2 of rows g and g+8 (this thread's k positions)
-        double cmaxsq = 0.0;             // largest ||c||^2 among this thread's columns
-        int32_t pstart = 0, pcount = 0, kb = 0;
-        int64_t coff = 0;
-        for (int64_t step = 0; step < total_steps; ++step) {
-            const int ti = (int)(step / spt);
-            const int rem = (int)(step - (int64_t)ti * spt);
-            const int cb = rem / p.nch;
-            const int kc = rem - cb * p.nch;
-            if (rem == 0) {
-                const int32_t tile = (int32_t)blockIdx.x + ti * (int32_t)gridDim.x;
-                cur.seek(p.tile_prefix, p.nbins, tile);
-                const int32_t b = cur.bin;
-                const int32_t in_bin = (tile - p.tile_prefix[b]) * AS_TP;
-                pstart = p.bin_start[b] + in_bin;
-                pcount = min(AS_TP, (p.bin_start[b + 1] - p.bin_start[b]) - in_bin);
-                coff = p.bin_offset[b];
-                kb = (int32_t)(p.bin_offset[b + 1] - coff);
-                best[0] = best[1] = second[0] = second[1] = __longlong_as_double(0x7ff0000000000000ll);  // +inf
-                besti[0] = besti[1] = 0;
-                xx[0] = xx[1] = 0.0;
-                cmaxsq = 0.0;
-            }
-            if (kc == 0) {
+    };
+    fetch_pidx(iw, pidx);
+    pw.next_tile(tt, my_tiles);
+    fetch_pidx(pw, pidx_next);
+    int istage = 0;
+    uint32_t iphase = 0;
+    int64_t issued = 0;
+
+    auto issue_one = [&]() {
+        mbar_wait(&empty_bar[istage], iphase ^ 1u);
+        double* st = stage_base + (size_t)istage * STAGE_DOUBLES;
+        double* sX = st + (warp * 16 + rsub) * AS_LD + kcol0;
+        const int k0 = iw.kc * AS_DC;
+        int vbytes = (p.D - k0 - kcol0) * 8;   // bytes of this lane's segment that exist in the row
+        vbytes = vbytes < 0 ? 0 : (vbytes > VEC * 8 ? VEC * 8 : vbytes);
+        const int crows = iw.kb - iw.cb * CROWS;   // centre rows of this block (<= 0 for a ragged trailing block)
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
+        for (int q = 0; q < XQ; ++q) {
+            const bool ok = pidx[q] >= 0;
+            const double* src = ok ? p.X + (int64_t)pidx[q] * p.ldx + k0 + kcol0 : p.X;
+            cp_async_zfill<VEC>(sX + q * RPI * AS_LD, src, ok ? vbytes : 0);
+        }
+        {
+            double* sC = st + (TP + warp * CPW + rsub) * AS_LD + kcol0;
+            const double* cbase = p.centers + (iw.coff + iw.cb * CROWS + warp * CPW + rsub) * p.D + k0 + kcol0;
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+            for (int q = 0; q < CQ; ++q) {
+                const int rr = q * RPI + rsub;          // row inside this warp's share
+                const int r = warp * CPW + rr;
+                if (rr < CPW && r < CROWS) {
+                    const bool ok = r < crows;
+                    cp_async_zfill<VEC>(sC + q * RPI * AS_LD, ok ? cbase + (int64_t)q * RPI * p.D : p.centers, ok ? vbytes : 0);
+                }
             }
-            mbar_wait(&full_bar[stage], phase);
-            const double* sX = stage_base + (size_t)stage * STAGE_DOUBLES;
-            const double* sC = sX + AS_TP * AS_LD;
-            const double* xa0 = sX + (warp * 16 + g) * AS_LD + t;
-            const double* xa1 = xa0 + 8 * AS_LD;
-            const double* cb0 = sC + g * AS_LD + t;
+        }
+        if (iw.kc == p.nch - 1) {
+            // the block's ||c||^2 rides in the stage of the last k-chunk (8-byte copies, zero-filled tail)
+            double* sQ = st + (TP + CROWS) * AS_LD;
+            for (int c = threadIdx.x; c < CROWS; c += THREADS) {
+                const bool ok = c < crows;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(sQ + c)),
+                             "l"(ok ? p.csq + iw.coff + iw.cb * CROWS + c : p.csq), "r"(ok ? 8 : 0) : "memory");
+            }
+        }
+        cp_async_arrive_noinc(&full_bar[istage]);
+        if (++istage == nstages) { istage = 0; iphase ^= 1u; }
+        ++issued;
+        if (iw.advance(tt, p.ncb, p.nch, my_tiles)) {
+            // entered the next tile: its indices were fetched a tile ago; start fetching the one after
+#pragma unroll
+            for (int q = 0; q < XQ; ++q) pidx[q] = pidx_next[q];
+            pw.next_tile(tt, my_tiles);
+            fetch_pidx(pw, pidx_next);
+        }
+    };
+
+    // prologue: fill nstages-1 slots
+    while (issued < total_steps && issued < nstages - 1) issue_one();
+
+    int stage = 0;
+    uint32_t phase = 0;
+    double best[2] = {inf, inf};      // smallest score seen by this thread, per m-tile (exact, fp64)
+    int32_t besti[2] = {0, 0};
+    float m1f[2] = {finf, finf};      // fp32 lower bounds of the smallest / second smallest score: a cheap,
+    float m2f[2] = {finf, finf};      // conservative filter for near-ties (the re-check kernel decides)
+    double xx[2] = {0.0, 0.0};        // partial ||x||^2 of rows g and g+8 (this thread's k positions)
+    float cmaxf = 0.f;                // upper bound of the largest ||c||^2 among this thread's columns
+    int32_t out_pt[2] = {-1, -1};     // point index of rows g / g+8 of the tile being computed (lanes t == 0)
+    double acc[2][NT][2];
+
+    for (int64_t step = 0; step < total_steps; ++step) {
+        if (issued < total_steps) issue_one();
+        if (cw.kc == 0) {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+            if (cw.cb == 0 && t == 0) {
+                // label destinations, fetched now so the load latency hides under the tile's math
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const int r = warp * 16 + mt * 8 + g;
+                    out_pt[mt] = (r < cw.pcount) ? p.perm[cw.pstart + r] : -1;
+                }
+            }
+        }
+        mbar_wait(&full_bar[stage], phase);
+        const double* st = stage_base + (size_t)stage * STAGE_DOUBLES;
+        const double* xa0 = st + (warp * 16 + g) * AS_LD + t;
+        const double* xa1 = xa0 + 8 * AS_LD;
+        const double* cb0 = st + (TP + g) * AS_LD + t;
+        if (cw.cb == 0) {
 #pragma unroll
             for (int ks = 0; ks < AS_DC / 4; ++ks) {
                 const double a0 = xa0[ks * 4];
                 const double a1 = xa1[ks * 4];
-                if (cb == 0) {  // ||x||^2 once per tile (needed only for the tie tolerance)
-                    xx[0] = fma(a0, a0, xx[0]);
-                    xx[1] = fma(a1, a1, xx[1]);
-                }
+                xx[0] = fma(a0, a0, xx[0]);   // ||x||^2, once per tile (only feeds the tie tolerance)
+                xx[1] = fma(a1, a1, xx[1]);
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     const double bv = cb0[nt * 8 * AS_LD + ks * 4];
@@ -378,64 +456,89 @@ __global__ void __launch_bounds__(AS_THREADS) assign_dmma_kernel(const AssignPar
                     dmma8x8x4(acc[1][nt][0], acc[1][nt][1], a1, bv);
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[stage]);
-            if (++stage == AS_STAGES) { stage = 0; phase ^= 1u; }
-
-            if (kc == p.nch - 1) {
-                // fold this centre block into the running argmin: score = ||c||^2 - 2 x.c
+        } else {
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt)
+            for (int ks = 0; ks < AS_DC / 4; ++ks) {
+                const double a0 = xa0[ks * 4];
+                const double a1 = xa1[ks * 4];
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int c = cb * CROWS + nt * 8 + 2 * t + j;
-                        if (c < kb) {
-                            const double cs = p.csq[coff + c];
-                            cmaxsq = fmax(cmaxsq, cs);
+                for (int nt = 0; nt < NT; ++nt) {
+                    const double bv = cb0[nt * 8 * AS_LD + ks * 4];
+                    dmma8x8x4(acc[0][nt][0], acc[0][nt][1], a0, bv);
+                    dmma8x8x4(acc[1][nt][0], acc[1][nt][1], a1, bv);
+                }
+            }
+        }
+        if (cw.kc == p.nch - 1) {
+            // fold this centre block into the running argmin: score = ||c||^2 - 2 x.c
+            const double* sQ = st + (TP + CROWS) * AS_LD;
 #pragma unroll
-                            for (int mt = 0; mt < 2; ++mt) {
-                                const double s = fma(-2.0, acc[mt][nt][j], cs);
-                                if (s < best[mt]) { second[mt] = best[mt]; best[mt] = s; besti[mt] = c; }
-                                else if (s < second[mt]) second[mt] = s;
-                            }
-                        }
-                    }
-                if (cb == p.ncb - 1) {
-                    // every quad sees all columns: reduce the column-wise quantities over its 4 lanes
-                    double cm = cmaxsq;
-                    cm = fmax(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
-                    cm = fmax(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
-                    const double cmax = sqrt(cm);
+            for (int nt = 0; nt < NT; ++nt) {
+                const double2 cs2 = *reinterpret_cast<const double2*>(sQ + nt * 8 + 2 * t);
 #pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
-                        double bs = best[mt], sc = second[mt], xs = xx[mt];
-                        int32_t bi = besti[mt];
+                for (int j = 0; j < 2; ++j) {
+                    const int c = cw.cb * CROWS + nt * 8 + 2 * t + j;
+                    if (c < cw.kb) {
+                        const double cs = j ? cs2.y : cs2.x;
+                        cmaxf = fmaxf(cmaxf, __double2float_ru(cs));
 #pragma unroll
-                        for (int o = 1; o <= 2; o <<= 1) {
-                            const double os = __shfl_xor_sync(0xffffffffu, bs, o);
-                            const double o2 = __shfl_xor_sync(0xffffffffu, sc, o);
-                            const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                            xs += __shfl_xor_sync(0xffffffffu, xs, o);
-                            // merged second = min(larger of the two bests, both seconds)
-                            const double hi = (os < bs) ? bs : os;
-                            sc = fmin(fmin(sc, o2), hi);
-                            // lowest index wins exact ties ("first minimum" of the reference's scan)
-                            if (os < bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
-                        }
-                        const int r = warp * 16 + mt * 8 + g;
-                        if (t == 0 && r < pcount) {
-                            const int32_t pt = p.perm[pstart + r];
-                            p.label_out[pt] = coff + bi;
-                            if (p.local_out) p.local_out[pt] = bi;
-                            // near-tie within fp64 rounding noise -> exact re-check pass decides (2x margin here)
-                            const double tol = 2.0 * p.tie_scale * cmax * (2.0 * sqrt(xs) + cmax);
-                            if (sc - bs <= tol) p.recheck_list[atomicAdd(p.recheck_count, 1)] = pt;
+                        for (int mt = 0; mt < 2; ++mt) {
+                            const double s = fma(-2.0, acc[mt][nt][j], cs);
+                            const float sf = __double2float_rd(s);
+                            m2f[mt] = fminf(m2f[mt], fmaxf(m1f[mt], sf));
+                            m1f[mt] = fminf(m1f[mt], sf);
+                            if (s < best[mt]) { best[mt] = s; besti[mt] = c; }
                         }
                     }
                 }
             }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == nstages) { stage = 0; phase ^= 1u; }
+
+        if (cw.kc == p.nch - 1 && cw.cb == p.ncb - 1) {
+            // every quad sees all columns of the tile: reduce over its 4 lanes
+            cmaxf = fmaxf(cmaxf, __shfl_xor_sync(0xffffffffu, cmaxf, 1));
+            cmaxf = fmaxf(cmaxf, __shfl_xor_sync(0xffffffffu, cmaxf, 2));
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                double bs = best[mt];
+                int32_t bi = besti[mt];
+                float xs = __double2float_ru(xx[mt]);
+#pragma unroll
+                for (int o = 1; o <= 2; o <<= 1) {
+                    const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+                    const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    xs += __shfl_xor_sync(0xffffffffu, xs, o);
+                    // lowest index wins exact ties ("first minimum" of the reference's scan)
+                    if (os < bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
+                }
+                // lower bound of the runner-up over the quad: the other lanes' best scores compete too
+                float ru = (besti[mt] == bi && best[mt] == bs) ? m2f[mt] : m1f[mt];
+                ru = fminf(ru, __shfl_xor_sync(0xffffffffu, ru, 1));
+                ru = fminf(ru, __shfl_xor_sync(0xffffffffu, ru, 2));
+                if (t == 0 && out_pt[mt] >= 0) {
+                    const int32_t pt = out_pt[mt];
+                    p.label_out[pt] = cw.coff + bi;
+                    if (p.local_out) p.local_out[pt] = bi;
+                    // possible near-tie within fp64 rounding noise -> the exact re-check pass decides.
+                    // fp32 bounds make this filter conservative (gap under-, tolerance over-estimated).
+                    const float cmax = sqrtf(cmaxf) * 1.000001f;
+                    const float tolf = 2.0f * (float)p.tie_scale * cmax * (2.0f * sqrtf(xs) * 1.000001f + cmax);
+                    const double gap = (double)ru - bs;
+                    if (!(gap > (double)tolf)) p.recheck_list[atomicAdd(p.recheck_count, 1)] = pt;
+                }
+                best[mt] = inf;
+                besti[mt] = 0;
+                m1f[mt] = m2f[mt] = finf;
+                xx[mt] = 0.0;
+            }
+            cmaxf = 0.f;
+        }
+        cw.advance(tt, p.ncb, p.nch, my_tiles);
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
 // Near-tie re-check.  One warp per flagged point: scores of ALL centres of the point's bin from a
@@ -537,39 +640,56 @@ static size_t assign_ws_bytes(int64_t N, int32_t nbins) {
     return b + 1024;
 }
 
-template <int NT, int VEC>
-static int launch_assign(const AssignParams& p, int64_t max_tiles, cudaStream_t stream) {
-    constexpr size_t smem = (size_t)AS_STAGES * (AS_TP + NT * 8) * AS_LD * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
-        MWE_CHECK_CUDA(cudaFuncSetAttribute(assign_dmma_kernel<NT, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+template <int NT, int VEC, int CW>
+static int launch_assign(AssignParams p, int64_t max_tiles, cudaStream_t stream) {
+    constexpr int TP = CW * 16;
+    constexpr size_t stage_bytes = ((size_t)(TP + NT * 8) * AS_LD + NT * 8) * sizeof(double);
+    const size_t table_bytes = (p.nbins <= AS_TABLE_BINS) ? (size_t)(p.nbins + 2) * 16 + 16 : 0;
+    const size_t budget = (CW == 4 ? AS_SMEM_BUDGET_SMALL : AS_SMEM_BUDGET) - table_bytes;
+    int nstages = (int)(budget / stage_bytes);
+    if (nstages > AS_MAX_STAGES) nstages = AS_MAX_STAGES;
+    if (nstages < 2) nstages = 2;
+    const size_t smem = stage_bytes * nstages + table_bytes;
+    static size_t configured = 0;
+    if (configured < smem) {
+        MWE_CHECK_CUDA(cudaFuncSetAttribute(assign_dmma_kernel<NT, VEC, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
     }
+    p.nstages = nstages;
     int occ = 1;
-    MWE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, assign_dmma_kernel<NT, VEC>, AS_THREADS, smem));
+    MWE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, assign_dmma_kernel<NT, VEC, CW>, CW * 32, smem));
     if (occ < 1) occ = 1;
-    int64_t grid = (int64_t)sm_count() * occ;
+    int64_t grid = (int64_t)sm_count() * occ;   // persistent: every resident CTA walks its share of the tiles
     if (grid > max_tiles) grid = max_tiles;
     if (grid < 1) grid = 1;
     cudaEvent_t ev0, ev1;
     timing_events(&ev0, &ev1);
     if (ev0) MWE_CHECK_CUDA(cudaEventRecord(ev0, stream));
-    assign_dmma_kernel<NT, VEC><<<(unsigned)grid, AS_THREADS, smem, stream>>>(p);
+    assign_dmma_kernel<NT, VEC, CW><<<(unsigned)grid, CW * 32, smem, stream>>>(p);
     MWE_CHECK_LAUNCH();
     if (ev1) MWE_CHECK_CUDA(cudaEventRecord(ev1, stream));
     return MWE_OK;
 }
 
+// centre-block widths that are instantiated, and the CTA shape used with each
+static const int kNtList[] = {2, 3, 4, 7, 8, 13, 16};
+static int pick_nt(int max_k) {
+    for (int i = 0; i < 7; ++i)
+        if (kNtList[i] * 8 >= max_k) return kNtList[i];
+    return 16;
+}
+static int tile_points_for(int nt) { return nt <= 4 ? 64 : 128; }
+
 template <int VEC>
 static int dispatch_nt(int nt, const AssignParams& p, int64_t max_tiles, cudaStream_t stream) {
     switch (nt) {
-        case 2: return launch_assign<2, VEC>(p, max_tiles, stream);
-        case 3: return launch_assign<3, VEC>(p, max_tiles, stream);
-        case 4: return launch_assign<4, VEC>(p, max_tiles, stream);
-        case 7: return launch_assign<7, VEC>(p, max_tiles, stream);
-        case 8: return launch_assign<8, VEC>(p, max_tiles, stream);
-        case 13: return launch_assign<13, VEC>(p, max_tiles, stream);
-        default: return launch_assign<16, VEC>(p, max_tiles, stream);
+        case 2: return launch_assign<2, VEC, 4>(p, max_tiles, stream);
+        case 3: return launch_assign<3, VEC, 4>(p, max_tiles, stream);
+        case 4: return launch_assign<4, VEC, 4>(p, max_tiles, stream);
+        case 7: return launch_assign<7, VEC, 8>(p, max_tiles, stream);
+        case 8: return launch_assign<8, VEC, 8>(p, max_tiles, stream);
+        case 13: return launch_assign<13, VEC, 8>(p, max_tiles, stream);
+        default: return launch_assign<16, VEC, 8>(p, max_tiles, stream);
     }
 }
 
@@ -616,19 +736,17 @@ extern "C" int mwe_assign_stratified_f64(const double* X, int64_t N, int D, int6
     ws.bin_start = cv.take<int32_t>((size_t)nbins + 1);
     ws.tile_prefix = cv.take<int32_t>((size_t)nbins + 1);
 
+    const int nt = pick_nt(max_k);
+    const int tile_points = tile_points_for(nt);
     MWE_CHECK_CUDA(cudaMemsetAsync(ws.bin_count, 0, (size_t)(nbins + 2) * sizeof(int32_t), s));
     const int64_t blocks = (N + 256 * AS_BK_ITEMS - 1) / (256 * AS_BK_ITEMS);
     assign_count_kernel<<<(unsigned)blocks, 256, 0, s>>>(bin, flag, N, nbins, ws.bin_count);
-    assign_scan_kernel<<<1, 256, 0, s>>>(ws.bin_count, bin_offset, nbins, ws.bin_start, ws.bin_cursor, ws.tile_prefix, err_count);
+    assign_scan_kernel<<<1, 256, 0, s>>>(ws.bin_count, bin_offset, nbins, ws.bin_start, ws.bin_cursor, ws.tile_prefix, err_count,
+                                         tile_points);
     assign_scatter_kernel<<<(unsigned)blocks, 256, 0, s>>>(bin, flag, N, nbins, bin_offset, ws.bin_cursor, ws.perm, label_out,
                                                           local_out);
     MWE_CHECK_LAUNCH();
 
-    // centre-block width: smallest instantiated NT covering max_k, capped at 16 (128 centres / block)
-    static const int nts[] = {2, 3, 4, 7, 8, 13, 16};
-    int nt = 16;
-    for (int i = 0; i < 7; ++i)
-        if (nts[i] * 8 >= max_k) { nt = nts[i]; break; }
     AssignParams p;
     p.X = X; p.ldx = ldx; p.D = D; p.centers = centers; p.csq = csq; p.bin_offset = bin_offset; p.nbins = nbins;
     p.perm = ws.perm; p.bin_start = ws.bin_start; p.tile_prefix = ws.tile_prefix;
@@ -637,7 +755,7 @@ extern "C" int mwe_assign_stratified_f64(const double* X, int64_t N, int D, int6
     p.tie_scale = AS_TIE_C * (double)(D + 8) * 1.1102230246251565e-16;
     p.ncb = (max_k + nt * 8 - 1) / (nt * 8);
     p.nch = (D + AS_DC - 1) / AS_DC;
-    const int64_t max_tiles = (N + AS_TP - 1) / AS_TP + nbins;
+    const int64_t max_tiles = (N + tile_points - 1) / tile_points + nbins;
     const bool vec2 = (D % 2 == 0) && (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(centers) & 15) == 0);
     const int rc = vec2 ? dispatch_nt<2>(nt, p, max_tiles, s) : dispatch_nt<1>(nt, p, max_tiles, s);
