@@ -18,6 +18,8 @@
 //
 // Algorithmic traffic per point: D*8 bytes of features (+4 B bucket index, +8 B label); centres
 // are re-read from L2.  FLOPs per point: 2*K_b*D.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sort.cuh"
 
@@ -28,7 +30,7 @@ static constexpr int AS_LD = AS_DC + 4;         // padded row: 72 words == 8 (mo
 static constexpr int AS_MAX_STAGES = 8;
 static constexpr int AS_TABLE_BINS = 1024;     // bins whose tile tables are cached in shared memory
 static constexpr size_t AS_SMEM_BUDGET = 200 * 1024;        // one 8-warp CTA per SM
-static constexpr size_t AS_SMEM_BUDGET_SMALL = 72 * 1024;   // three 4-warp CTAs per SM
+static constexpr size_t AS_SMEM_BUDGET_SMALL = 54 * 1024;   // four 4-warp CTAs per SM
 static constexpr int AS_SPIN_LIMIT = 1 << 26;
 
 // ---- bucketing -----------------------------------------------------------------------------
@@ -287,7 +289,7 @@ struct TileWalk {
 // (A cp.async.bulk / UBLKCP row copy was tried first: one instruction per 256-byte row, issued lane by
 // lane through an ELECT loop, cost more issue slots than the vectorised LDGSTS below -- profiles/.)
 template <int NT, int VEC, int CW>
-__global__ void __launch_bounds__(CW * 32, (CW == 4 ? 3 : 1)) assign_dmma_kernel(const AssignParams p) {
+__global__ void __launch_bounds__(CW * 32, (CW == 4 ? (NT <= 4 ? 4 : 2) : 1)) assign_dmma_kernel(const AssignParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int TP = CW * 16;
     constexpr int THREADS = CW * 32;
@@ -343,8 +345,8 @@ __global__ void __launch_bounds__(CW * 32, (CW == 4 ? 3 : 1)) assign_dmma_kernel
     const int seg = lane % SEGS;
     const int rsub = lane / SEGS;
     const int kcol0 = seg * VEC;
-    int32_t pidx[XQ];        // point index of the rows this lane copies for the tile of iw (-1 = none)
-    int32_t pidx_next[XQ];   // same for the following tile (in flight while iw's tile is being issued)
+    const double* xsrc[XQ];   // source of the rows this lane copies for the tile of iw (nullptr = no such row)
+    int32_t pidx_next[XQ];    // point indices for the following tile (in flight while iw's tile is being issued)
     auto fetch_pidx = [&](const TileWalk<TP>& w, int32_t* out) {
 #pragma unroll
         for (int q = 0; q < XQ; ++q) {
@@ -352,13 +354,21 @@ __global__ void __launch_bounds__(CW * 32, (CW == 4 ? 3 : 1)) assign_dmma_kernel
             out[q] = (r < w.pcount) ? p.perm[w.pstart + r] : -1;
         }
     };
-    fetch_pidx(iw, pidx);
+    auto set_xsrc = [&]() {
+#pragma unroll
+        for (int q = 0; q < XQ; ++q)
+            xsrc[q] = (pidx_next[q] >= 0) ? p.X + (int64_t)pidx_next[q] * p.ldx + kcol0 : nullptr;
+    };
+    fetch_pidx(iw, pidx_next);
+    set_xsrc();
     pw.next_tile(tt, my_tiles);
     fetch_pidx(pw, pidx_next);
     int istage = 0;
     uint32_t iphase = 0;
     int64_t issued = 0;
-
+    // rows outside the tile / centre block are simply not copied: rows and columns of the product are
+    // independent, the stale shared memory they leave only reaches accumulators that are never read.
+    // The k-tail of a row, however, is zero-filled (src-size < copy size), so the math needs no masks.
     auto issue_one = [&]() {
         mbar_wait(&empty_bar[istage], iphase ^ 1u);
         double* st = stage_base + (size_t)istage * STAGE_DOUBLES;
@@ -368,40 +378,30 @@ __global__ void __launch_bounds__(CW * 32, (CW == 4 ? 3 : 1)) assign_dmma_kernel
         vbytes = vbytes < 0 ? 0 : (vbytes > VEC * 8 ? VEC * 8 : vbytes);
         const int crows = iw.kb - iw.cb * CROWS;   // centre rows of this block (<= 0 for a ragged trailing block)
 #pragma unroll
-        for (int q = 0; q < XQ; ++q) {
-            const bool ok = pidx[q] >= 0;
-            const double* src = ok ? p.X + (int64_t)pidx[q] * p.ldx + k0 + kcol0 : p.X;
-            cp_async_zfill<VEC>(sX + q * RPI * AS_LD, src, ok ? vbytes : 0);
-        }
+        for (int q = 0; q < XQ; ++q)
+            if (xsrc[q]) cp_async_zfill<VEC>(sX + q * RPI * AS_LD, xsrc[q] + k0, vbytes);
         {
             double* sC = st + (TP + warp * CPW + rsub) * AS_LD + kcol0;
             const double* cbase = p.centers + (iw.coff + iw.cb * CROWS + warp * CPW + rsub) * p.D + k0 + kcol0;
 #pragma unroll
             for (int q = 0; q < CQ; ++q) {
                 const int rr = q * RPI + rsub;          // row inside this warp's share
-                const int r = warp * CPW + rr;
-                if (rr < CPW && r < CROWS) {
-                    const bool ok = r < crows;
-                    cp_async_zfill<VEC>(sC + q * RPI * AS_LD, ok ? cbase + (int64_t)q * RPI * p.D : p.centers, ok ? vbytes : 0);
-                }
+                if (rr < CPW && warp * CPW + rr < crows)
+                    cp_async_zfill<VEC>(sC + q * RPI * AS_LD, cbase + (int64_t)q * RPI * p.D, vbytes);
             }
         }
         if (iw.kc == p.nch - 1) {
-            // the block's ||c||^2 rides in the stage of the last k-chunk (8-byte copies, zero-filled tail)
+            // the block's ||c||^2 rides in the stage of the last k-chunk
             double* sQ = st + (TP + CROWS) * AS_LD;
-            for (int c = threadIdx.x; c < CROWS; c += THREADS) {
-                const bool ok = c < crows;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(sQ + c)),
-                             "l"(ok ? p.csq + iw.coff + iw.cb * CROWS + c : p.csq), "r"(ok ? 8 : 0) : "memory");
-            }
+            for (int c = threadIdx.x; c < crows && c < CROWS; c += THREADS)
+                cp_async_zfill<1>(sQ + c, p.csq + iw.coff + iw.cb * CROWS + c, 8);
         }
         cp_async_arrive_noinc(&full_bar[istage]);
         if (++istage == nstages) { istage = 0; iphase ^= 1u; }
         ++issued;
         if (iw.advance(tt, p.ncb, p.nch, my_tiles)) {
             // entered the next tile: its indices were fetched a tile ago; start fetching the one after
-#pragma unroll
-            for (int q = 0; q < XQ; ++q) pidx[q] = pidx_next[q];
+            set_xsrc();
             pw.next_tile(tt, my_tiles);
             fetch_pidx(pw, pidx_next);
         }
@@ -412,10 +412,12 @@ __global__ void __launch_bounds__(CW * 32, (CW == 4 ? 3 : 1)) assign_dmma_kernel
 
     int stage = 0;
     uint32_t phase = 0;
-    double best[2] = {inf, inf};      // smallest score seen by this thread, per m-tile (exact, fp64)
+    // Candidate tracking is done on fp32 roundings (toward -inf) of the fp64 scores: smallest, its column,
+    // and second smallest.  A point whose fp32 gap does not clear the tie tolerance plus one fp32 ulp is
+    // handed to the exact fp64 re-check kernel, so the fp32 filter never decides a close call.
+    float m1f[2] = {finf, finf};
+    float m2f[2] = {finf, finf};
     int32_t besti[2] = {0, 0};
-    float m1f[2] = {finf, finf};      // fp32 lower bounds of the smallest / second smallest score: a cheap,
-    float m2f[2] = {finf, finf};      // conservative filter for near-ties (the re-check kernel decides)
     double xx[2] = {0.0, 0.0};        // partial ||x||^2 of rows g and g+8 (this thread's k positions)
     float cmaxf = 0.f;                // upper bound of the largest ||c||^2 among this thread's columns
     int32_t out_pt[2] = {-1, -1};     // point index of rows g / g+8 of the tile being computed (lanes t == 0)
@@ -483,11 +485,11 @@ __global__ void __launch_bounds__(CW * 32, (CW == 4 ? 3 : 1)) assign_dmma_kernel
                         cmaxf = fmaxf(cmaxf, __double2float_ru(cs));
 #pragma unroll
                         for (int mt = 0; mt < 2; ++mt) {
-                            const double s = fma(-2.0, acc[mt][nt][j], cs);
-                            const float sf = __double2float_rd(s);
-                            m2f[mt] = fminf(m2f[mt], fmaxf(m1f[mt], sf));
-                            m1f[mt] = fminf(m1f[mt], sf);
-                            if (s < best[mt]) { best[mt] = s; besti[mt] = c; }
+                            const float sf = __double2float_rd(fma(-2.0, acc[mt][nt][j], cs));
+                            const bool lt = sf < m1f[mt];          // strict: the first of equal roundings stays
+                            m2f[mt] = lt ? m1f[mt] : fminf(m2f[mt], sf);
+                            besti[mt] = lt ? c : besti[mt];
+                            m1f[mt] = lt ? sf : m1f[mt];
                         }
                     }
                 }
@@ -503,35 +505,31 @@ __global__ void __launch_bounds__(CW * 32, (CW == 4 ? 3 : 1)) assign_dmma_kernel
             cmaxf = fmaxf(cmaxf, __shfl_xor_sync(0xffffffffu, cmaxf, 2));
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
-                double bs = best[mt];
+                float bs = m1f[mt], ru = m2f[mt];
                 int32_t bi = besti[mt];
                 float xs = __double2float_ru(xx[mt]);
 #pragma unroll
                 for (int o = 1; o <= 2; o <<= 1) {
-                    const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+                    const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+                    const float o2 = __shfl_xor_sync(0xffffffffu, ru, o);
                     const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
                     xs += __shfl_xor_sync(0xffffffffu, xs, o);
-                    // lowest index wins exact ties ("first minimum" of the reference's scan)
+                    // runner-up of the union = min(both runner-ups, the larger of the two bests)
+                    ru = fminf(fminf(ru, o2), fmaxf(bs, os));
                     if (os < bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
                 }
-                // lower bound of the runner-up over the quad: the other lanes' best scores compete too
-                float ru = (besti[mt] == bi && best[mt] == bs) ? m2f[mt] : m1f[mt];
-                ru = fminf(ru, __shfl_xor_sync(0xffffffffu, ru, 1));
-                ru = fminf(ru, __shfl_xor_sync(0xffffffffu, ru, 2));
                 if (t == 0 && out_pt[mt] >= 0) {
                     const int32_t pt = out_pt[mt];
                     p.label_out[pt] = cw.coff + bi;
                     if (p.local_out) p.local_out[pt] = bi;
-                    // possible near-tie within fp64 rounding noise -> the exact re-check pass decides.
-                    // fp32 bounds make this filter conservative (gap under-, tolerance over-estimated).
+                    // true gap > (ru - bs) - ulp32(bs); flag unless that clears the (over-estimated) tolerance
                     const float cmax = sqrtf(cmaxf) * 1.000001f;
                     const float tolf = 2.0f * (float)p.tie_scale * cmax * (2.0f * sqrtf(xs) * 1.000001f + cmax);
-                    const double gap = (double)ru - bs;
-                    if (!(gap > (double)tolf)) p.recheck_list[atomicAdd(p.recheck_count, 1)] = pt;
+                    const double gap_lb = ((double)ru - (double)bs) - 1.2e-7 * fabs((double)bs);
+                    if (!(gap_lb > (double)tolf)) p.recheck_list[atomicAdd(p.recheck_count, 1)] = pt;
                 }
-                best[mt] = inf;
-                besti[mt] = 0;
                 m1f[mt] = m2f[mt] = finf;
+                besti[mt] = 0;
                 xx[mt] = 0.0;
             }
             cmaxf = 0.f;
@@ -647,6 +645,7 @@ static int launch_assign(AssignParams p, int64_t max_tiles, cudaStream_t stream)
     const size_t table_bytes = (p.nbins <= AS_TABLE_BINS) ? (size_t)(p.nbins + 2) * 16 + 16 : 0;
     const size_t budget = (CW == 4 ? AS_SMEM_BUDGET_SMALL : AS_SMEM_BUDGET) - table_bytes;
     int nstages = (int)(budget / stage_bytes);
+    if (const char* e = getenv("MWE_ASSIGN_STAGES")) nstages = atoi(e);   // tuning knob
     if (nstages > AS_MAX_STAGES) nstages = AS_MAX_STAGES;
     if (nstages < 2) nstages = 2;
     const size_t smem = stage_bytes * nstages + table_bytes;
@@ -678,14 +677,27 @@ static int pick_nt(int max_k) {
         if (kNtList[i] * 8 >= max_k) return kNtList[i];
     return 16;
 }
-static int tile_points_for(int nt) { return nt <= 4 ? 64 : 128; }
+static bool small_cta(int nt) {
+    if (const char* e = getenv("MWE_ASSIGN_CW")) return atoi(e) == 4;   // tuning knob
+    return nt <= 4;
+}
+static int tile_points_for(int nt) { return small_cta(nt) ? 64 : 128; }
 
 template <int VEC>
 static int dispatch_nt(int nt, const AssignParams& p, int64_t max_tiles, cudaStream_t stream) {
+    if (small_cta(nt)) {
+        switch (nt) {
+            case 2: return launch_assign<2, VEC, 4>(p, max_tiles, stream);
+            case 3: return launch_assign<3, VEC, 4>(p, max_tiles, stream);
+            case 4: return launch_assign<4, VEC, 4>(p, max_tiles, stream);
+            case 7: return launch_assign<7, VEC, 4>(p, max_tiles, stream);
+            default: break;
+        }
+    }
     switch (nt) {
-        case 2: return launch_assign<2, VEC, 4>(p, max_tiles, stream);
-        case 3: return launch_assign<3, VEC, 4>(p, max_tiles, stream);
-        case 4: return launch_assign<4, VEC, 4>(p, max_tiles, stream);
+        case 2: return launch_assign<2, VEC, 8>(p, max_tiles, stream);
+        case 3: return launch_assign<3, VEC, 8>(p, max_tiles, stream);
+        case 4: return launch_assign<4, VEC, 8>(p, max_tiles, stream);
         case 7: return launch_assign<7, VEC, 8>(p, max_tiles, stream);
         case 8: return launch_assign<8, VEC, 8>(p, max_tiles, stream);
         case 13: return launch_assign<13, VEC, 8>(p, max_tiles, stream);
