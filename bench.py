@@ -289,20 +289,17 @@ def main():
     launches = {"n": 0}
 
     def step(ev=None):
-        bins, flags = ops.bin_flags(pc, engine.mapper, engine.basis, engine.target, we_remap=engine.we_remap,
-                                    errors=engine.errors)
         if ev is not None:
             _lib.set_timing_events(ev[0], ev[1])
-        ops.assign_stratified(X, bins, flags, engine.centers, engine.csq, engine.bin_offset, engine.max_k,
-                              errors=engine.errors, label_out=labels)
+        dense.zero_()
+        # one C call enqueues K0 -> K1 -> K3 (-> / nI when single-GPU)
+        engine.hotpath_step(X, pc, w, n_clusters, iter_offsets=offs, dense=dense,
+                            divisor=float(n_iters_total) if world == 1 else 0.0, labels_out=labels)
         if ev is not None:
             _lib.set_timing_events(None, None)
-        dense.zero_()
-        ops.flux_accumulate(labels[:N], labels[N:], w, n_clusters, flag0=flags[:N], flag1=flags[N:],
-                            iter_offsets=offs, dense=dense, errors=engine.errors)
         if world > 1:
             dist.all_reduce(dense)
-        ops.divide_(dense, float(n_iters_total))
+            ops.divide_(dense, float(n_iters_total))
 
     for _ in range(args.warmup):
         l2_flush.zero_()
@@ -380,12 +377,12 @@ def main():
 
 
 def LAUNCHES_PER_STEP_STATIC(cfg):
-    """Kernels of ours per step, counted from the launch sequences in csrc/: K0 (1) + K1 (count, scan,
-    scatter, dmma = 4) + K3 (keys 1 + 3 per radix pass + segsum 1) + divide 1."""
+    """Kernels of ours per step, counted from the launch sequences in csrc/: K0 (1) + K1 (count, scan, scatter,
+    dmma, re-check = 5) + K3 (keys 1 + 3 per radix pass + mark 1 + scan 3 + group sum 1 + cell sum 1) + divide 1."""
     M = cfg.n_clusters + 2
     bits = int(np.ceil(np.log2(M * M + 1)))
     passes = (bits + 7) // 8
-    return 1 + 4 + (1 + 3 * passes + 1) + 1
+    return 1 + 5 + (1 + 3 * passes + 1 + 3 + 1 + 1) + 1
 
 
 def run_e2e(cfg, rank, world, dev, steps):

@@ -97,15 +97,20 @@ MWE_API int mwe_bin_flags_f64(const double* pcoord, int64_t N, int P, int mapper
  *   (mwe_centers_sqnorm_f64); bin_offset [nbins+1] int64 prefix of per-bin centre counts.
  *   label_out [N] int64: target -> T+1, basis -> T (target tested first), else
  *   bin_offset[bin] + argmin, T = bin_offset[nbins]   (stratified_clustering.py:143-196).
+ *   bin_count_in nullable [nbins] int32: per-bin count of unflagged points as written by
+ *   mwe_bin_flags_f64 (saves one pass over bin/flag).
  *   local_out  nullable [N] int32: argmin local to the bin (what partial_fit's E step needs).
+ *   Near-ties: scores that differ by less than tol = 4 (D+8) 2^-53 cmax (2||x|| + cmax) -- the rounding
+ *   noise of their own evaluation -- count as tied and the lowest index wins (exact duplicates of a
+ *   centre therefore resolve as in the reference; see DESIGN.md "near-tie re-check").
  */
 MWE_API size_t mwe_assign_workspace_bytes(int64_t N, int32_t nbins);
 MWE_API int mwe_centers_sqnorm_f64(const double* centers, int64_t sumK, int D, double* csq, void* stream);
 MWE_API int mwe_assign_stratified_f64(const double* X, int64_t N, int D, int64_t ldx, const int32_t* bin,
                               const uint8_t* flag, const double* centers, const double* csq,
                               const int64_t* bin_offset, int32_t nbins, int32_t max_k, int precision_path,
-                              int64_t* label_out, int32_t* local_out, void* workspace, size_t workspace_bytes,
-                              int32_t* err_count, void* stream);
+                              const int32_t* bin_count_in, int64_t* label_out, int32_t* local_out, void* workspace,
+                              size_t workspace_bytes, int32_t* err_count, void* stream);
 
 /* ---- K2: centroid accumulation / update -----------------------------------------------------
  * Replaces update_center_dense (sklearn/cluster/_k_means_minibatch.pyx:59-111, reached from
@@ -159,6 +164,28 @@ MWE_API int mwe_flux_accumulate_f64(const int64_t* start, const int64_t* end, co
                             void* stream);
 /* buf[i] = buf[i] / divisor      (fluxMatrix / nI, _fluxmatrix.py:342) */
 MWE_API int mwe_divide_f64(double* buf, int64_t count, double divisor, void* stream);
+
+/* ---- one-call hot path ------------------------------------------------------------------------
+ * K0 -> K1 -> K3 (-> / divisor) for a batch of WE iterations, enqueued without returning to the host
+ * language between kernels.  Replaces the per-iteration body of do_stratified_ray_discretization
+ * (msm_we/_hamsm/_clustering.py:1278-1316) plus get_fluxMatrix's accumulation
+ * (msm_we/_hamsm/_fluxmatrix.py:232-260, 342) over that batch.
+ *   X2 [2*n_frames, D] f64: parent features of every frame, then child features (row stride ldx);
+ *   pcoord2 [2*n_frames, P] f64: pcoord0 of every frame, then pcoord1; w [n_frames] (nullable = 1);
+ *   iter_offsets [n_iters+1] nullable; mapper_* / bounds / we_remap as mwe_bin_flags_f64;
+ *   centers / csq / bin_offset / max_k / precision_path as mwe_assign_stratified_f64.
+ *   labels2_out [2*n_frames] int64 (parents then children, predict convention);
+ *   dense_inout nullable [(n_clusters+2)^2]: += this batch's transitions, then /= divisor when
+ *   divisor is neither 0 nor 1 (pass the total iteration count on the last batch). */
+MWE_API size_t mwe_hotpath_workspace_bytes(int64_t n_frames, int32_t nbins);
+MWE_API int mwe_hotpath_step_f64(const double* X2, int64_t ldx, int D, const double* pcoord2, int P, const double* w,
+                         int64_t n_frames, const int64_t* iter_offsets, int64_t n_iters, int mapper_kind,
+                         const float* mapper_data, const int32_t* mapper_lens_host, int32_t nbins,
+                         const double* basis_lohi_host, const double* target_lohi_host, const int32_t* we_remap,
+                         const double* centers, const double* csq, const int64_t* bin_offset, int32_t max_k,
+                         int precision_path, int64_t n_clusters, double divisor, int64_t* labels2_out,
+                         double* dense_inout, void* workspace, size_t workspace_bytes, int32_t* err_count,
+                         void* stream);
 
 /* ---- shared primitive, exported for tests ---------------------------------------------------
  * Stable LSD radix sort of (key, value) pairs on the low `key_bits` bits of the key.

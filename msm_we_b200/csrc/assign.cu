@@ -721,8 +721,8 @@ extern "C" int mwe_centers_sqnorm_f64(const double* centers, int64_t sumK, int D
 extern "C" int mwe_assign_stratified_f64(const double* X, int64_t N, int D, int64_t ldx, const int32_t* bin,
                                          const uint8_t* flag, const double* centers, const double* csq,
                                          const int64_t* bin_offset, int32_t nbins, int32_t max_k, int precision_path,
-                                         int64_t* label_out, int32_t* local_out, void* workspace,
-                                         size_t workspace_bytes, int32_t* err_count, void* stream) {
+                                         const int32_t* bin_count_in, int64_t* label_out, int32_t* local_out,
+                                         void* workspace, size_t workspace_bytes, int32_t* err_count, void* stream) {
     using namespace mwe;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     MWE_REQUIRE(N >= 0 && N < ((int64_t)1 << 31), "assign: N must be < 2^31 per call");
@@ -752,8 +752,8 @@ extern "C" int mwe_assign_stratified_f64(const double* X, int64_t N, int D, int6
     const int tile_points = tile_points_for(nt);
     MWE_CHECK_CUDA(cudaMemsetAsync(ws.bin_count, 0, (size_t)(nbins + 2) * sizeof(int32_t), s));
     const int64_t blocks = (N + 256 * AS_BK_ITEMS - 1) / (256 * AS_BK_ITEMS);
-    assign_count_kernel<<<(unsigned)blocks, 256, 0, s>>>(bin, flag, N, nbins, ws.bin_count);
-    assign_scan_kernel<<<1, 256, 0, s>>>(ws.bin_count, bin_offset, nbins, ws.bin_start, ws.bin_cursor, ws.tile_prefix, err_count,
+    if (!bin_count_in) assign_count_kernel<<<(unsigned)blocks, 256, 0, s>>>(bin, flag, N, nbins, ws.bin_count);
+    assign_scan_kernel<<<1, 256, 0, s>>>(bin_count_in ? bin_count_in : ws.bin_count, bin_offset, nbins, ws.bin_start, ws.bin_cursor, ws.tile_prefix, err_count,
                                          tile_points);
     assign_scatter_kernel<<<(unsigned)blocks, 256, 0, s>>>(bin, flag, N, nbins, bin_offset, ws.bin_cursor, ws.perm, label_out,
                                                           local_out);

@@ -12,6 +12,7 @@ namespace mwe {
 static constexpr int BF_THREADS = 256;
 static constexpr int BF_MAX_P = 8;
 static constexpr int BF_SMEM_BINS = 2048;
+static constexpr int BF_SMEM_BOUNDS = 2048;
 
 struct BinFlagParams {
     const double* pcoord;
@@ -20,6 +21,7 @@ struct BinFlagParams {
     int kind;
     const float* mapper_data;
     int32_t nbins;
+    int32_t n_bounds;
     const int32_t* we_remap;
     int32_t* bin_out;
     uint8_t* flag_out;
@@ -33,11 +35,16 @@ struct BinFlagParams {
 
 __global__ void __launch_bounds__(BF_THREADS) bin_flags_kernel(const BinFlagParams p) {
     __shared__ int32_t s_count[BF_SMEM_BINS];
+    __shared__ float s_bounds[BF_SMEM_BOUNDS];
     const bool use_smem = p.bin_count != nullptr && p.nbins <= BF_SMEM_BINS;
-    if (use_smem) {
+    if (use_smem)
         for (int b = threadIdx.x; b < p.nbins; b += BF_THREADS) s_count[b] = 0;
-        __syncthreads();
-    }
+    // rectilinear boundaries are searched once per point and dimension: keep them in shared memory
+    const bool smem_bounds = p.kind == MWE_MAPPER_RECTILINEAR && p.n_bounds <= BF_SMEM_BOUNDS;
+    if (smem_bounds)
+        for (int b = threadIdx.x; b < p.n_bounds; b += BF_THREADS) s_bounds[b] = p.mapper_data[b];
+    __syncthreads();
+    const float* bounds = smem_bounds ? s_bounds : p.mapper_data;
     const int64_t stride = (int64_t)gridDim.x * BF_THREADS;
     for (int64_t i = (int64_t)blockIdx.x * BF_THREADS + threadIdx.x; i < p.N; i += stride) {
         double pc[BF_MAX_P];
@@ -59,7 +66,7 @@ __global__ void __launch_bounds__(BF_THREADS) bin_flags_kernel(const BinFlagPara
             for (int d = 0; d < BF_MAX_P; ++d)
                 if (d < p.P) {
                     const float x = (float)pc[d];  // westpa casts coordinates to float32
-                    const float* b = p.mapper_data + p.starts[d];
+                    const float* b = bounds + p.starts[d];
                     const int nb = p.lens[d];
                     // number of boundaries <= x (upper_bound), minus one
                     int lo = 0, hi = nb;
@@ -128,6 +135,7 @@ extern "C" int mwe_bin_flags_f64(const double* pcoord, int64_t N, int P, int map
     p.we_remap = we_remap; p.bin_out = bin_out; p.flag_out = flag_out; p.bin_count = bin_count; p.err_count = err_count;
     int32_t start = 0;
     int64_t prod = 1;
+    p.n_bounds = 0;
     for (int d = 0; d < BF_MAX_P; ++d) {
         p.lens[d] = 0; p.starts[d] = 0;
         p.basis[d][0] = p.basis[d][1] = p.target[d][0] = p.target[d][1] = 0.0;
@@ -139,6 +147,7 @@ extern "C" int mwe_bin_flags_f64(const double* pcoord, int64_t N, int P, int map
                 p.lens[d] = mapper_lens_host[d];
                 p.starts[d] = start;
                 start += mapper_lens_host[d];
+                p.n_bounds = start;
                 prod *= (mapper_lens_host[d] - 1);
             }
         }

@@ -151,13 +151,29 @@ __global__ void __launch_bounds__(256)
         const uint64_t k = group_key[gi];
         double total = dense ? dense[k] : 0.0;
         double fresh = 0.0;
+        // the adds stay strictly sequential (iteration order); the loads are issued 8 at a time
         int64_t e = gi;
-        do {
-            const double v = group_sum[e];
-            total = __dadd_rn(total, v);
-            fresh = (e == gi) ? v : __dadd_rn(fresh, v);
-            ++e;
-        } while (e < n_groups && !group_is_cell_head[e]);
+        bool done = false;
+        bool first = true;
+        while (!done) {
+            double v[8];
+            uint8_t h[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int64_t q = (e + u < n_groups) ? e + u : n_groups - 1;
+                v[u] = group_sum[q];
+                h[u] = group_is_cell_head[q];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (done) break;
+                if (e + u >= n_groups || (h[u] && !(first && u == 0))) { done = true; break; }
+                total = __dadd_rn(total, v[u]);
+                fresh = (first && u == 0) ? v[u] : __dadd_rn(fresh, v[u]);
+            }
+            first = false;
+            e += 8;
+        }
         if (dense) dense[k] = total;
         if (coo_val) {
             const int32_t pos = cell_pos[gi];

@@ -22,6 +22,7 @@ static constexpr int RS_ITEMS = 8;
 static constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048
 static constexpr int RS_RADIX = 256;
 static constexpr int RS_WARPS = RS_THREADS / 32;
+static constexpr int RS_FUSED_SCAN_MAX_G = 160;   // up to here the scatter kernel scans the histograms itself
 
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t* __restrict__ keys, int64_t N, int shift,
                                                             int tiles_per_cta, uint32_t* __restrict__ hist) {
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(RS_RADIX) rs_scan_kernel(uint32_t* __restrict_
 __global__ void __launch_bounds__(RS_THREADS)
     rs_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                       uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t N, int shift,
-                      int tiles_per_cta, const uint32_t* __restrict__ offsets) {
+                      int tiles_per_cta, const uint32_t* __restrict__ offsets, int fused_scan) {
     __shared__ uint32_t s_base[RS_RADIX];
     __shared__ uint32_t s_warp_cnt[RS_WARPS][RS_RADIX];
     __shared__ uint32_t s_tile_excl[RS_RADIX];
@@ -68,7 +69,22 @@ __global__ void __launch_bounds__(RS_THREADS)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    s_base[tid] = offsets[(size_t)blockIdx.x * RS_RADIX + tid];
+    if (fused_scan) {
+        // small grids: every CTA derives its own digit offsets from the raw per-CTA histograms
+        // (offsets[c][d] = count) instead of waiting for a separate one-CTA scan kernel
+        uint32_t below = 0, total = 0;
+        const int G = (int)gridDim.x;
+        for (int c = 0; c < G; ++c) {
+            const uint32_t v = offsets[(size_t)c * RS_RADIX + tid];
+            if (c < (int)blockIdx.x) below += v;
+            total += v;
+        }
+        int blk_total;
+        const uint32_t digit_base = (uint32_t)block_excl_scan_256((int)total, scratch, &blk_total);
+        s_base[tid] = digit_base + below;
+    } else {
+        s_base[tid] = offsets[(size_t)blockIdx.x * RS_RADIX + tid];
+    }
 
     const int64_t span_begin = (int64_t)blockIdx.x * tiles_per_cta * RS_TILE;
     for (int t = 0; t < tiles_per_cta; ++t) {
@@ -194,9 +210,10 @@ int sort_pairs(uint64_t* keys, uint32_t* vals, int64_t N, int key_bits, void* ws
     const int passes = (key_bits + 7) / 8;
     for (int p = 0; p < passes; ++p) {
         const int shift = p * 8;
+        const int fused = G <= RS_FUSED_SCAN_MAX_G;
         rs_hist_kernel<<<G, RS_THREADS, 0, stream>>>(kin, N, shift, tpc, hist);
-        rs_scan_kernel<<<1, RS_RADIX, 0, stream>>>(hist, G);
-        rs_scatter_kernel<<<G, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, N, shift, tpc, hist);
+        if (!fused) rs_scan_kernel<<<1, RS_RADIX, 0, stream>>>(hist, G);
+        rs_scatter_kernel<<<G, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, N, shift, tpc, hist, fused);
         MWE_CHECK_LAUNCH();
         uint64_t* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;

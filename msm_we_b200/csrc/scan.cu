@@ -91,6 +91,36 @@ __global__ void __launch_bounds__(SC_THREADS) scan_apply_kernel(const int32_t* _
     }
 }
 
+// small inputs: one CTA walks the array in tiles, carrying the running total (one launch instead of three)
+__global__ void __launch_bounds__(SC_THREADS) scan_small_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
+                                                               int64_t n, int64_t* __restrict__ total_out) {
+    __shared__ int scratch[9];
+    long long carry = 0;
+    for (int64_t base = 0; base < n; base += SC_TILE) {
+        int v[SC_ITEMS];
+        int tsum = 0;
+#pragma unroll
+        for (int j = 0; j < SC_ITEMS; ++j) {
+            const int64_t i = base + (int64_t)threadIdx.x * SC_ITEMS + j;
+            v[j] = (i < n) ? in[i] : 0;
+            tsum += v[j];
+        }
+        int blk_total;
+        const int excl = block_excl_scan_256(tsum, scratch, &blk_total);
+        long long run = carry + excl;
+#pragma unroll
+        for (int j = 0; j < SC_ITEMS; ++j) {
+            const int64_t i = base + (int64_t)threadIdx.x * SC_ITEMS + j;
+            if (i < n) out[i] = (int32_t)run;
+            run += v[j];
+        }
+        carry += blk_total;
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+static constexpr int64_t SC_SMALL_MAX = 1 << 16;
+
 size_t scan_workspace_bytes(int64_t n) {
     int64_t nblocks = (n + SC_TILE - 1) / SC_TILE;
     if (nblocks < 1) nblocks = 1;
@@ -106,6 +136,11 @@ int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int64_t* tota
     if (ws_bytes < scan_workspace_bytes(n)) {
         set_last_error("scan: workspace too small");
         return MWE_E_WORKSPACE;
+    }
+    if (n <= SC_SMALL_MAX) {
+        scan_small_kernel<<<1, SC_THREADS, 0, stream>>>(in, out, n, total_out);
+        MWE_CHECK_LAUNCH();
+        return MWE_OK;
     }
     Carver cv(ws, ws_bytes);
     const int64_t nblocks = (n + SC_TILE - 1) / SC_TILE;

@@ -89,5 +89,31 @@ class DeviceClusters:
         return ops.flux_accumulate(parent_labels, child_labels, weights, n_clusters, flag0=flag0, flag1=flag1,
                                    iter_offsets=iter_offsets, dense=dense, errors=self.errors)
 
+    # -- K0 + K1 + K3 in one C call -----------------------------------------------------------
+    def hotpath_step(self, X2, pcoord2, weights, n_clusters, iter_offsets=None, dense=None, divisor=0.0,
+                     labels_out=None, path=_lib.ASSIGN_FP64):
+        """Stacked batch (parents then children): labels of both halves and, when ``dense`` is given,
+        the batch's transitions added into it (then divided by ``divisor`` if it is neither 0 nor 1)."""
+        if self.mapper.kind == _lib.MAPPER_PRECOMPUTED:
+            raise ValueError("hotpath_step needs a mapper the GPU evaluates (rectilinear / Euclidean Voronoi)")
+        n2, D = X2.shape
+        n = n2 // 2
+        P = pcoord2.shape[1]
+        if labels_out is None:
+            labels_out = torch.empty(n2, dtype=torch.int64, device=self.device)
+        nbytes = _lib.lib.mwe_hotpath_workspace_bytes(n, self.nbins)
+        ws = ops.Workspace.get(self.device, nbytes)
+        n_iters = 0 if iter_offsets is None else iter_offsets.numel() - 1
+        lens_p = self.mapper.lens.ctypes.data if self.mapper.lens is not None else None
+        _lib.check(_lib.lib.mwe_hotpath_step_f64(
+            X2.data_ptr(), X2.stride(0), D, pcoord2.data_ptr(), P, None if weights is None else weights.data_ptr(), n,
+            None if iter_offsets is None else iter_offsets.data_ptr(), n_iters, self.mapper.kind, self.mapper.data.data_ptr(),
+            lens_p, self.nbins, self.basis.ctypes.data, self.target.ctypes.data, self.we_remap.data_ptr(),
+            self.centers.data_ptr(), self.csq.data_ptr(), self.bin_offset.data_ptr(), self.max_k, int(path),
+            int(n_clusters), float(divisor), labels_out.data_ptr(), None if dense is None else dense.data_ptr(),
+            ws.data_ptr(), ws.numel(), self.errors.counts.data_ptr(), torch.cuda.current_stream().cuda_stream),
+            "mwe_hotpath_step_f64")
+        return labels_out
+
     def check_errors(self):
         self.errors.check()

@@ -146,7 +146,7 @@ def centers_sqnorm(centers):
 
 
 def assign_stratified(X, bin, flag, centers, csq, bin_offset, max_k, path=_lib.ASSIGN_FP64, want_local=False,
-                      errors: DeviceErrors = None, label_out=None):
+                      errors: DeviceErrors = None, label_out=None, bin_count=None):
     """K1.  X [N,D] f64 (row stride may exceed D) -> labels int64 [N] (and per-bin local argmin)."""
     if not X.is_cuda or X.dtype != torch.float64 or X.dim() != 2 or X.stride(1) != 1:
         raise TypeError("X: expected a CUDA float64 [N, D] tensor with unit column stride")
@@ -164,7 +164,8 @@ def assign_stratified(X, bin, flag, centers, csq, bin_offset, max_k, path=_lib.A
     nbytes = lib.mwe_assign_workspace_bytes(N, nbins)
     ws = Workspace.get(dev, nbytes)
     check(lib.mwe_assign_stratified_f64(_ptr(X), N, D, ldx, _ptr(bin), _ptr(flag), _ptr(centers), _ptr(csq),
-                                        _ptr(bin_offset), nbins, int(max_k), int(path), _ptr(label_out), _ptr(local),
+                                        _ptr(bin_offset), nbins, int(max_k), int(path), _ptr(bin_count), _ptr(label_out),
+                                        _ptr(local),
                                         _ptr(ws), ws.numel(), _ptr(errors.counts), _stream()),
           "mwe_assign_stratified_f64")
     return (label_out, local) if want_local else label_out

@@ -256,3 +256,28 @@ def test_ntl9_fixture_replay_sparsity(golden_dir):
     ref = set(zip(g["flux_raw_nz_i"].tolist(), g["flux_raw_nz_j"].tolist()))
     assert got == ref and len(ref) == 4575
     assert dense.sum() == len(s) == 10340
+
+
+def test_hotpath_step_matches_separate_kernels_and_oracle():
+    """The one-call C entry (K0 -> K1 -> K3 -> / nI) on a stacked batch equals the modelWE-level results."""
+    import torch
+    from msm_we_b200 import synthetic
+
+    cfg, model, its, centers, basis, target, om = _with_fixed_centers()
+    model.launch_ray_discretization()
+    model.get_fluxMatrix(n_lag=0, first_iter=0)          # iterations 1 .. maxIter-1, as the stacked batch below
+    dev = model.clusters.device_state()
+    use = its[: cfg.n_iters - 1]
+    X2 = torch.from_numpy(np.concatenate([d["parent"] for d in use] + [d["child"] for d in use])).to(dev.device)
+    P2 = torch.from_numpy(np.concatenate([d["pcoord0"] for d in use] + [d["pcoord1"] for d in use])).to(dev.device)
+    w = torch.from_numpy(np.concatenate([d["weights"] for d in use])).to(dev.device)
+    offs = torch.from_numpy(np.concatenate([[0], np.cumsum([len(d["weights"]) for d in use])]).astype(np.int64)).to(dev.device)
+    M = model.n_clusters + 2
+    dense = torch.zeros((M, M), dtype=torch.float64, device=dev.device)
+    labels = dev.hotpath_step(X2, P2, w, model.n_clusters, iter_offsets=offs, dense=dense, divisor=float(len(use)))
+    dev.check_errors()
+    n = w.numel()
+    lab = labels.cpu().numpy()
+    assert np.array_equal(lab[n:], np.concatenate(model.dtrajs))
+    assert np.array_equal(lab[:n], np.concatenate([np.asarray(p)[:, 0] for p in model.pair_dtrajs]))
+    assert np.array_equal(dense.cpu().numpy(), model.fluxMatrixRaw)
