@@ -67,17 +67,29 @@ def load_peaks():
 # CPU arm: the reference's literal pattern, one process per iteration range
 # ----------------------------------------------------------------------------------------------
 
+_POOL = {}
+
+
+def _close_pools():
+    for pool in _POOL.values():
+        pool.close()
+        pool.join()
+    _POOL.clear()
+
+
 def cpu_reference_pass(cfg_name, n_sample_iters, n_procs):
     """Times the reference pattern on `n_sample_iters` iterations of the workload; returns
-    (frames, seconds, cores)."""
+    (frames, seconds, cores).  The worker pool is created once (fork) and reused by every step."""
     import multiprocessing as mp
 
-    ctx = mp.get_context("fork")
     chunks = np.array_split(np.arange(n_sample_iters), n_procs)
     chunks = [c for c in chunks if len(c)]
+    key = (cfg_name, n_sample_iters, len(chunks))
+    if key not in _POOL:
+        _POOL[key] = mp.get_context("fork").Pool(len(chunks))
+    pool = _POOL[key]
     t0 = time.perf_counter()
-    with ctx.Pool(len(chunks)) as pool:
-        res = pool.map(_cpu_chunk, [(cfg_name, int(c[0]), int(c[-1]) + 1) for c in chunks])
+    res = pool.map(_cpu_chunk, [(cfg_name, int(c[0]), int(c[-1]) + 1) for c in chunks], chunksize=1)
     dt = time.perf_counter() - t0
     frames = sum(r[0] for r in res)
     return frames, dt, len(chunks)
@@ -140,80 +152,82 @@ def run_cpu_arm(cfg_name, sample_iters, cores):
     return frames, dt, used
 
 
-def auto_sample_iters(cfg, cores):
-    # ~155 us per sklearn predict([x]) call, 2 calls per frame; aim at ~15 s of CPU work per core-set
-    per_iter = cfg.n_segs * 2 * 160e-6 + 2e-9 * (cfg.n_clusters + 2) ** 2 * 8
-    want = max(cores, int(15.0 * cores / per_iter))
-    return int(min(cfg.n_iters, max(cores, (want // cores) * cores)))
+def auto_sample_iters(cfg, cores, n_steps=1, budget_s=20.0):
+    """Iterations of the workload one CPU step covers: the whole (warm-up + timed) run is sized to about
+    `budget_s` seconds of wall time per core set, at least one iteration per core, at most the workload."""
+    per_iter = cfg.n_segs * 2 * 230e-6 + 4e-9 * (cfg.n_clusters + 2) ** 2   # measured: ~0.45 core-s per cfg2 iteration
+    per_core = max(1, int(budget_s / max(n_steps, 1) / per_iter))
+    return int(min(cfg.n_iters, per_core * cores))
 
 
 # ----------------------------------------------------------------------------------------------
 
 class ClockSampler:
-    """SM clock + throttle reasons sampled through NVML (about 1 kHz) while the steps run; samples
-    taken between mark_timed(True) and mark_timed(False) belong to the timed region."""
+    """SM clock + throttle reasons sampled by an `nvidia-smi -lms` subprocess started before the warm-up and
+    stopped after the timed region (B200_PROFILING.md recipe); samples are split by wall-clock time into
+    the timed window and the rest."""
+
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
-        self.samples = []          # (in_timed_region, sm_mhz, reasons_bitmask)
-        self.max_mhz = None
-        self._timed = False
-        self._stop = threading.Event()
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._nvml = None
-        try:
-            import pynvml
-
-            pynvml.nvmlInit()
-            self._nvml = pynvml
-            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
-        except Exception:
-            self._nvml = None
-
-    def mark_timed(self, on):
-        self._timed = on
-
-    def _run(self):
-        nv = self._nvml
-        while not self._stop.is_set():
-            try:
-                if nv is not None:
-                    mhz = float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
-                    reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
-                    self.samples.append((self._timed, mhz, reasons))
-                    self._stop.wait(0.001)
-                else:
-                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
-                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                    a, b = [float(x) for x in out.strip().split(",")[:2]]
-                    self.max_mhz = b
-                    self.samples.append((self._timed, a, 0))
-                    self._stop.wait(0.05)
-            except Exception:
-                self._stop.wait(0.01)
+        self.proc = None
+        self.path = os.path.join("/tmp", f"mwe_clocks_{os.getpid()}_{index}.csv")
+        self.t_on = self.t_off = None
 
     def __enter__(self):
-        self._t.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "10", "-f", self.path],
+                                         stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            time.sleep(0.15)   # let it take its first samples
+        except Exception:
+            self.proc = None
         return self
 
+    def mark_timed(self, on):
+        if on:
+            self.t_on = time.time()
+        else:
+            self.t_off = time.time()
+
     def __exit__(self, *exc):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
 
     def summary(self):
-        timed = [s for s in self.samples if s[0]]
-        use = timed if timed else self.samples
-        if not use:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
-        sm = sorted(s[1] for s in use)
-        mask = 0
-        for s in use:
-            mask |= s[2]
-        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
-        reasons = [n for bit, n in names.items() if mask & bit]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(use),
-                "window": "timed region" if timed else "warm-up + timed region"}
+        import datetime
+
+        rows = []
+        try:
+            with open(self.path) as f:
+                for line in f:
+                    parts = [x.strip() for x in line.split(",")]
+                    if len(parts) >= 7:
+                        try:
+                            ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                            rows.append((ts, float(parts[1]), float(parts[2]), parts[3:7]))
+                        except ValueError:
+                            pass
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        timed = [r for r in rows if self.t_on is not None and self.t_on - 0.02 <= r[0] <= (self.t_off or 1e18) + 0.02]
+        use = timed if timed else rows
+        sm = sorted(r[1] for r in use)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3][i].lower().startswith("active") for r in use)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": use[0][2], "reasons": reasons, "samples": len(use),
+                "window": "timed region" if timed else "warm-up + timed region (timed region shorter than the sampling period)"}
 
 
 def main():
@@ -231,7 +245,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        sample = args.cpu_sample_iters or auto_sample_iters(cfg, cores)
+        sample = args.cpu_sample_iters or auto_sample_iters(cfg, cores, args.steps + args.warmup, budget_s=120.0)
         times = []
         frames = 0
         for step in range(args.warmup + args.steps):
@@ -301,6 +315,8 @@ def main():
             dist.all_reduce(dense)
             ops.divide_(dense, float(n_iters_total))
 
+    clocks = ClockSampler(local_rank)
+    clocks.__enter__()
     for _ in range(args.warmup):
         l2_flush.zero_()
         step()
@@ -312,15 +328,15 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    with ClockSampler(local_rank) as clocks:
-        clocks.mark_timed(True)
-        for k in range(args.steps):
-            l2_flush.zero_()                       # flush L2 between timed steps (outside the events)
-            evs[k][0].record()
-            step(kevs[k])
-            evs[k][1].record()
-        torch.cuda.synchronize()
-        clocks.mark_timed(False)
+    clocks.mark_timed(True)
+    for k in range(args.steps):
+        l2_flush.zero_()                       # flush L2 between timed steps (outside the events)
+        evs[k][0].record()
+        step(kevs[k])
+        evs[k][1].record()
+    torch.cuda.synchronize()
+    clocks.mark_timed(False)
+    clocks.__exit__()
     if world > 1:
         dist.barrier()
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
@@ -442,4 +458,8 @@ def run_e2e(cfg, rank, world, dev, steps):
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    try:
+        rc = main()
+    finally:
+        _close_pools()
+    sys.exit(rc)

@@ -299,62 +299,88 @@ class ClusteringMixin:
         D = dev.D
         P = self.pcoord_ndim
         row_bytes = 2 * (D + P) * 8
+        seg_counts = [int(self.numSegments[it - 1]) if self.numSegments is not None and it <= len(self.numSegments)
+                      else None for it in range(1, self.maxIter)]
+
+        # plan chunks of whole iterations; each chunk is staged in ONE pinned buffer (features | pcoords),
+        # copied with one async H2D and labelled by one K0 + K1 launch sequence.  Two staging buffers
+        # alternate, so the host fills chunk i+1 while the GPU copies and labels chunk i.
+        chunks, cur, cur_rows = [], [], 0
+        for it in range(1, self.maxIter):
+            s = seg_counts[it - 1]
+            if s is None:
+                self.load_iter_data(it)
+                s = self.nSeg
+            if s == 0:
+                continue
+            if cur and (cur_rows + s) * row_bytes > chunk_bytes:
+                chunks.append(cur)
+                cur, cur_rows = [], 0
+            cur.append((it, s))
+            cur_rows += s
+        if cur:
+            chunks.append(cur)
+
+        stream = torch.cuda.current_stream()
+        slots = [dict(event=None, host=None, n=0), dict(event=None, host=None, n=0)]
+        inflight = []   # (chunk, n, labels_host, bins_host, flags_host, done_event)
+
+        def stage(ci, chunk):
+            n = sum(s for _, s in chunk)
+            slot = slots[ci % 2]
+            if slot["event"] is not None:
+                slot["event"].synchronize()          # the H2D that last read this buffer has finished
+            need = 2 * n * (D + P)
+            if slot["host"] is None or slot["host"].numel() < need:
+                slot["host"] = torch.empty(need, dtype=torch.float64, pin_memory=True)
+            host = slot["host"]
+            hx = host[: 2 * n * D].view(2 * n, D).numpy()
+            hp = host[2 * n * D: need].view(2 * n, P).numpy()
+            pos = 0
+            for it, s in chunk:
+                self.load_iter_data(it)
+                parent_coords, child_coords = self.iter_coordinate_pair(it)
+                hx[pos:pos + s] = self.coordinates.transform(self.processCoordinates(parent_coords))
+                hx[n + pos:n + pos + s] = self.coordinates.transform(self.processCoordinates(child_coords))
+                hp[pos:pos + s] = np.asarray(self.pcoord0List, dtype=np.float64).reshape(-1, P)
+                hp[n + pos:n + pos + s] = np.asarray(self.pcoord1List, dtype=np.float64).reshape(-1, P)
+                pos += s
+            d = host[:need].to(dev.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            slot["event"] = ev
+            X = d[: 2 * n * D].view(2 * n, D)
+            Pc = d[2 * n * D:].view(2 * n, P)
+            labels, bins, flags = dev.predict(X, Pc, pcoord_host=hp)
+            lh = torch.empty(2 * n, dtype=torch.int64, pin_memory=True)
+            bh = torch.empty(2 * n, dtype=torch.int32, pin_memory=True)
+            fh = torch.empty(2 * n, dtype=torch.uint8, pin_memory=True)
+            lh.copy_(labels, non_blocking=True); bh.copy_(bins, non_blocking=True); fh.copy_(flags, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(stream)
+            inflight.append((chunk, n, lh, bh, fh, done))
 
         with ProgressBar(progress_bar) as progress:
             task = progress.add_task(description="Discretizing trajectories", total=n_iters)
-            pending = []  # (iteration, nseg)
-            feats_p, feats_c, pcs0, pcs1 = [], [], [], []
-
-            def flush():
-                if not pending:
-                    return
-                n = sum(s for _, s in pending)
-                host_x = torch.empty((2 * n, D), dtype=torch.float64, pin_memory=True)
-                host_p = torch.empty((2 * n, P), dtype=torch.float64, pin_memory=True)
-                hx, hp = host_x.numpy(), host_p.numpy()
-                np.concatenate(feats_p, axis=0, out=hx[:n])
-                np.concatenate(feats_c, axis=0, out=hx[n:])
-                np.concatenate(pcs0, axis=0, out=hp[:n])
-                np.concatenate(pcs1, axis=0, out=hp[n:])
-                X = host_x.to(dev.device, non_blocking=True)
-                Pc = host_p.to(dev.device, non_blocking=True)
-                labels, bins, flags = dev.predict(X, Pc, pcoord_host=hp)
-                labels_h = labels.cpu().numpy()
-                bins_h = bins.cpu().numpy()
-                flags_h = flags.cpu().numpy()
-                dev.check_errors()
+            for ci, chunk in enumerate(chunks):
+                stage(ci, chunk)
+            for chunk, n, lh, bh, fh, done in inflight:
+                done.synchronize()
+                labels_h, bins_h, flags_h = lh.numpy(), bh.numpy(), fh.numpy()
                 is_target = (flags_h & 2) != 0
                 is_basis = ((flags_h & 1) != 0) & ~is_target
                 clusters.target_bins.update(int(b) for b in np.unique(bins_h[is_target]))
                 clusters.basis_bins.update(int(b) for b in np.unique(bins_h[is_basis]))
                 pos = 0
-                for it, s in pending:
-                    parent = labels_h[pos:pos + s]
-                    child = labels_h[n + pos:n + pos + s]
-                    dtrajs[it - 1] = child.copy()
-                    pair_dtrajs[it - 1] = np.stack([parent, child], axis=1)
+                for it, s in chunk:
+                    pair = np.empty((s, 2), dtype=np.int64)
+                    pair[:, 0] = labels_h[pos:pos + s]
+                    pair[:, 1] = labels_h[n + pos:n + pos + s]
+                    dtrajs[it - 1] = pair[:, 1].copy()
+                    pair_dtrajs[it - 1] = pair
                     pos += s
                     progress.update(task, advance=1)
-                pending.clear(); feats_p.clear(); feats_c.clear(); pcs0.clear(); pcs1.clear()
-
-            staged = 0
-            for iteration in range(1, self.maxIter):
-                self.load_iter_data(iteration)
-                self.get_transition_data_lag0()
-                parent_coords, child_coords = self.coordPairList[..., 0], self.coordPairList[..., 1]
-                if child_coords.shape[0] == 0:
-                    progress.update(task, advance=1)
-                    continue
-                feats_p.append(np.asarray(self.coordinates.transform(self.processCoordinates(parent_coords)), dtype=np.float64))
-                feats_c.append(np.asarray(self.coordinates.transform(self.processCoordinates(child_coords)), dtype=np.float64))
-                pcs0.append(np.asarray(self.pcoord0List, dtype=np.float64).reshape(-1, P))
-                pcs1.append(np.asarray(self.pcoord1List, dtype=np.float64).reshape(-1, P))
-                pending.append((iteration, child_coords.shape[0]))
-                staged += child_coords.shape[0] * row_bytes
-                if staged >= chunk_bytes:
-                    flush()
-                    staged = 0
-            flush()
+            dev.check_errors()
 
         self.dtrajs = [d for d in dtrajs if d is not None]
         self.pair_dtrajs = [d for d in pair_dtrajs if d is not None]

@@ -181,6 +181,36 @@ class DataMixin:
         self.transitionWeights = weightList.copy()
         self.departureWeights = weightList.copy()
 
+    # ---- bulk accessors used by the batched GPU paths (no [nSeg, nAtoms, 3, 2] intermediate) ----------
+    def iter_coordinate_pair(self, n_iter):
+        """(parent, child) structures ``[S, nAtoms, coord_ndim]`` of one iteration, straight from the source."""
+        rec = self._record(n_iter)
+        return self._as_structures(rec.parent_coords), self._as_structures(rec.child_coords)
+
+    def iter_nan_segments(self, n_iter):
+        """Indices of segments with a NaN start or end coordinate (the reference zeroes their weights,
+        _data.py:302-313).  Cached per iteration: the discretization pass touches the coordinates anyway."""
+        cache = self.__dict__.setdefault("_nan_segments_cache", {})
+        if n_iter not in cache:
+            parent, child = self.iter_coordinate_pair(n_iter)
+            S = parent.shape[0]
+            # one pass, no temporaries: a row sum is NaN whenever the row holds a NaN; the (rare) candidates
+            # are then checked exactly, so inf - inf cannot produce a false positive
+            cand = np.where(np.isnan(parent.reshape(S, -1).sum(axis=1)) | np.isnan(child.reshape(S, -1).sum(axis=1)))[0]
+            if cand.shape[0]:
+                exact = np.isnan(parent[cand]).any(axis=(1, 2)) | np.isnan(child[cand]).any(axis=(1, 2))
+                cand = cand[exact]
+            cache[n_iter] = cand
+        return cache[n_iter]
+
+    def iter_transition_weights(self, n_iter):
+        """``transitionWeights`` of get_transition_data_lag0 without materialising coordPairList."""
+        w = self._record(n_iter).weights.copy()
+        bad = self.iter_nan_segments(n_iter)
+        if bad.shape[0] > 0:
+            w[bad] = 0.0
+        return w
+
     def load_iter_coordinates(self):
         """reference: _data.py:557-618 (end-of-segment coordinates of the loaded iteration)."""
         if self.nSeg == 0:

@@ -99,11 +99,17 @@ class FluxMatrixMixin:
     def _gather_flux_inputs(self, n_iter):
         """Host-side per-iteration inputs, exactly what the reference collects (:23-30, :277-288)."""
         self.load_iter_data(n_iter)
-        parent_pcoords = self.pcoord0List.copy()
-        child_pcoords = self.pcoord1List.copy()
-        self.get_transition_data_lag0()
-        transition_weights = self.transitionWeights.copy()
-        index_pairs = np.array(self.pair_dtrajs[n_iter - 1])
+        parent_pcoords = self.pcoord0List
+        child_pcoords = self.pcoord1List
+        if self.nSeg == 0:
+            self.get_transition_data_lag0()
+            transition_weights = self.transitionWeights.copy()
+        else:
+            # same values as get_transition_data_lag0().transitionWeights (NaN-coordinate segments -> 0),
+            # without rebuilding the coordinate-pair array the reference reloads only for this purpose
+            transition_weights = self.iter_transition_weights(n_iter)
+            self.transitionWeights = transition_weights
+        index_pairs = np.asarray(self.pair_dtrajs[n_iter - 1])
         return index_pairs, parent_pcoords, child_pcoords, transition_weights
 
     def _flux_device(self, iters, progress=None, task=None):
