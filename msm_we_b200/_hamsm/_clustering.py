@@ -25,7 +25,7 @@ from ..stratified_clustering import StratifiedClusters
 # user-extensible, as in the reference (_clustering.py:22)
 SUPPORTED_MAPPERS = set(_NATIVE_MAPPERS)
 
-DEFAULT_CHUNK_BYTES = 1 << 30
+DEFAULT_CHUNK_BYTES = 64 << 20
 
 
 class _RemoteShim:
