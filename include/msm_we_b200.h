@@ -104,7 +104,8 @@ MWE_API int mwe_bin_flags_f64(const double* pcoord, int64_t N, int P, int mapper
  *   noise of their own evaluation -- count as tied and the lowest index wins (exact duplicates of a
  *   centre therefore resolve as in the reference; see DESIGN.md "near-tie re-check").
  */
-MWE_API size_t mwe_assign_workspace_bytes(int64_t N, int32_t nbins);
+MWE_API size_t mwe_assign_workspace_bytes(int64_t N, int32_t nbins);            /* MWE_ASSIGN_FP64 */
+MWE_API size_t mwe_assign_workspace_bytes_ex(int64_t N, int32_t nbins, int D, int32_t max_k, int precision_path);
 MWE_API int mwe_centers_sqnorm_f64(const double* centers, int64_t sumK, int D, double* csq, void* stream);
 MWE_API int mwe_assign_stratified_f64(const double* X, int64_t N, int D, int64_t ldx, const int32_t* bin,
                               const uint8_t* flag, const double* centers, const double* csq,
@@ -177,7 +178,8 @@ MWE_API int mwe_divide_f64(double* buf, int64_t count, double divisor, void* str
  *   labels2_out [2*n_frames] int64 (parents then children, predict convention);
  *   dense_inout nullable [(n_clusters+2)^2]: += this batch's transitions, then /= divisor when
  *   divisor is neither 0 nor 1 (pass the total iteration count on the last batch). */
-MWE_API size_t mwe_hotpath_workspace_bytes(int64_t n_frames, int32_t nbins);
+MWE_API size_t mwe_hotpath_workspace_bytes(int64_t n_frames, int32_t nbins);      /* MWE_ASSIGN_FP64 */
+MWE_API size_t mwe_hotpath_workspace_bytes_ex(int64_t n_frames, int32_t nbins, int D, int32_t max_k, int precision_path);
 MWE_API int mwe_hotpath_step_f64(const double* X2, int64_t ldx, int D, const double* pcoord2, int P, const double* w,
                          int64_t n_frames, const int64_t* iter_offsets, int64_t n_iters, int mapper_kind,
                          const float* mapper_data, const int32_t* mapper_lens_host, int32_t nbins,
@@ -186,6 +188,12 @@ MWE_API int mwe_hotpath_step_f64(const double* X2, int64_t ldx, int D, const dou
                          int precision_path, int64_t n_clusters, double divisor, int64_t* labels2_out,
                          double* dense_inout, void* workspace, size_t workspace_bytes, int32_t* err_count,
                          void* stream);
+
+/* ---- test hooks for the tcgen05 assignment path ------------------------------------------------
+ * mwe_debug_set_tc_scores: device buffer [N][mwe_debug_tc_columns(max_k)] fp32 (or NULL) that the next
+ * MWE_ASSIGN_TF32X3 calls fill with the scores the tensor cores produced (error-bound validation). */
+MWE_API int mwe_debug_set_tc_scores(float* buf);
+MWE_API int mwe_debug_tc_columns(int32_t max_k);
 
 /* ---- shared primitive, exported for tests ---------------------------------------------------
  * Stable LSD radix sort of (key, value) pairs on the low `key_bits` bits of the key.

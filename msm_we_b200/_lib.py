@@ -34,6 +34,7 @@ SIGNATURES = {
     "mwe_set_timing_events": (_int, [_p, _p]),
     "mwe_bin_flags_f64": (_int, [_p, _i64, _int, _int, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "mwe_assign_workspace_bytes": (_sz, [_i64, _i32]),
+    "mwe_assign_workspace_bytes_ex": (_sz, [_i64, _i32, _int, _i32, _int]),
     "mwe_centers_sqnorm_f64": (_int, [_p, _i64, _int, _p, _p]),
     "mwe_assign_stratified_f64": (_int, [_p, _i64, _int, _i64, _p, _p, _p, _p, _p, _i32, _i32, _int, _p, _p, _p, _p, _sz, _p, _p]),
     "mwe_centroid_workspace_bytes": (_sz, [_i64, _i64]),
@@ -45,8 +46,11 @@ SIGNATURES = {
     "mwe_flux_accumulate_f64": (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _int, _p, _i64, _p, _p, _p, _p, _p, _p, _sz, _p, _p]),
     "mwe_divide_f64": (_int, [_p, _i64, _f64, _p]),
     "mwe_hotpath_workspace_bytes": (_sz, [_i64, _i32]),
+    "mwe_hotpath_workspace_bytes_ex": (_sz, [_i64, _i32, _int, _i32, _int]),
     "mwe_hotpath_step_f64": (_int, [_p, _i64, _int, _p, _int, _p, _i64, _p, _i64, _int, _p, _p, _i32, _p, _p, _p, _p, _p, _p,
                                     _i32, _int, _i64, _f64, _p, _p, _p, _sz, _p, _p]),
+    "mwe_debug_set_tc_scores": (_int, [_p]),
+    "mwe_debug_tc_columns": (_int, [_i32]),
     "mwe_sort_workspace_bytes": (_sz, [_i64]),
     "mwe_sort_pairs_u64_u32": (_int, [_p, _p, _i64, _int, _p, _sz, _p]),
 }

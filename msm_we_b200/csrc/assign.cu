@@ -20,7 +20,7 @@
 // are re-read from L2.  FLOPs per point: 2*K_b*D.
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "assign_common.cuh"
 #include "sort.cuh"
 
 namespace mwe {
@@ -28,10 +28,8 @@ namespace mwe {
 static constexpr int AS_DC = 32;                // doubles per k-chunk
 static constexpr int AS_LD = AS_DC + 4;         // padded row: 72 words == 8 (mod 32): conflict-free LDS.64 fragments
 static constexpr int AS_MAX_STAGES = 8;
-static constexpr int AS_TABLE_BINS = 1024;     // bins whose tile tables are cached in shared memory
 static constexpr size_t AS_SMEM_BUDGET = 200 * 1024;        // one 8-warp CTA per SM
 static constexpr size_t AS_SMEM_BUDGET_SMALL = 54 * 1024;   // four 4-warp CTAs per SM
-static constexpr int AS_SPIN_LIMIT = 1 << 26;
 
 // ---- bucketing -----------------------------------------------------------------------------
 
@@ -161,121 +159,6 @@ __global__ void __launch_bounds__(256)
         }
     }
 }
-
-// ---- PTX helpers -----------------------------------------------------------------------------
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done = 0;
-    int spins = 0;
-    while (true) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (done) break;
-        if (++spins > AS_SPIN_LIMIT) __trap();  // never hang the GPU on a protocol bug
-    }
-}
-__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-template <int VEC>
-__device__ __forceinline__ void cp_async_zfill(void* dst, const void* src, int src_bytes) {
-    if (VEC == 2) {
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
-    } else {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
-    }
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-// TMA bulk copy global -> shared, completion (in bytes) signalled on an mbarrier
-__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
-
-struct AssignParams {
-    const double* X;
-    int64_t ldx;
-    int D;
-    const double* centers;
-    const double* csq;
-    const int64_t* bin_offset;
-    int32_t nbins;
-    const int32_t* perm;
-    const int32_t* bin_start;
-    const int32_t* tile_prefix;
-    int64_t* label_out;
-    int32_t* local_out;
-    int32_t* recheck_list;   // points whose best two scores are within rounding noise
-    int32_t* recheck_count;
-    double tie_scale;        // TIE_C * (D + 8) * 2^-53
-    int ncb;      // centre blocks of NT*8 per tile
-    int nch;      // k-chunks of AS_DC per centre block
-    int nstages;  // depth of the shared-memory ring
-};
-
-// Tile bookkeeping tables (shared memory copies when the bin count allows, else the global arrays).
-struct TileTables {
-    const int32_t* tile_prefix;   // [nbins+1]
-    const int32_t* bin_start;     // [nbins+1]
-    const int64_t* bin_offset;    // [nbins+1]
-    int32_t nbins;
-};
-
-// Per-warp view of the tile sequence of this CTA.  Three walkers run at different distances: the tile
-// whose point indices are being prefetched, the tile whose copies are being issued, the tile being
-// computed.  Tiles handled by one CTA are increasing, so the bin is found by scanning forward.
-template <int TP>
-struct TileWalk {
-    int ti, cb, kc;      // tile ordinal inside the CTA, centre block, k-chunk
-    int32_t bin;
-    int32_t pstart, pcount, kb;
-    int64_t coff;
-    __device__ __forceinline__ void load(const TileTables& tt, int my_tiles) {
-        if (ti >= my_tiles) { pcount = 0; return; }
-        const int32_t tile = (int32_t)blockIdx.x + ti * (int32_t)gridDim.x;
-        while (bin + 1 < tt.nbins && tile >= tt.tile_prefix[bin + 1]) ++bin;
-        const int32_t in_bin = (tile - tt.tile_prefix[bin]) * TP;
-        pstart = tt.bin_start[bin] + in_bin;
-        pcount = min(TP, (tt.bin_start[bin + 1] - tt.bin_start[bin]) - in_bin);
-        coff = tt.bin_offset[bin];
-        kb = (int32_t)(tt.bin_offset[bin + 1] - coff);
-    }
-    __device__ __forceinline__ void next_tile(const TileTables& tt, int my_tiles) {
-        ++ti;
-        load(tt, my_tiles);
-    }
-    // returns true when the walk entered a new tile
-    __device__ __forceinline__ bool advance(const TileTables& tt, int ncb, int nch, int my_tiles) {
-        if (++kc < nch) return false;
-        kc = 0;
-        if (++cb < ncb) return false;
-        cb = 0;
-        next_tile(tt, my_tiles);
-        return true;
-    }
-};
 
 // K1 main kernel.
 //   NT  : 8-column centre sub-tiles per centre block (block = NT*8 centres)
@@ -619,7 +502,6 @@ __global__ void __launch_bounds__(256) centers_sqnorm_kernel(const double* __res
     if (lane_id() == 0) csq[row] = s;
 }
 
-static constexpr double AS_TIE_C = 4.0;
 
 struct AssignWs {
     int32_t* recheck_list;
@@ -709,6 +591,12 @@ static int dispatch_nt(int nt, const AssignParams& p, int64_t max_tiles, cudaStr
 
 extern "C" size_t mwe_assign_workspace_bytes(int64_t N, int32_t nbins) { return mwe::assign_ws_bytes(N, nbins); }
 
+extern "C" size_t mwe_assign_workspace_bytes_ex(int64_t N, int32_t nbins, int D, int32_t max_k, int precision_path) {
+    size_t b = mwe::assign_ws_bytes(N, nbins);
+    if (precision_path == MWE_ASSIGN_TF32X3) b += mwe::assign_tc_prep_bytes(nbins, D, max_k) + 256;
+    return b;
+}
+
 extern "C" int mwe_centers_sqnorm_f64(const double* centers, int64_t sumK, int D, double* csq, void* stream) {
     MWE_REQUIRE(sumK >= 0 && D >= 1, "centers_sqnorm: bad shape");
     if (sumK == 0) return MWE_OK;
@@ -729,13 +617,15 @@ extern "C" int mwe_assign_stratified_f64(const double* X, int64_t N, int D, int6
     MWE_REQUIRE(D >= 1 && ldx >= D, "assign: bad D / ldx");
     MWE_REQUIRE(nbins >= 1 && max_k >= 1, "assign: bad nbins / max_k");
     MWE_REQUIRE(bin && centers && csq && bin_offset && label_out && err_count, "assign: null pointer");
-    if (precision_path != MWE_ASSIGN_FP64) {
-        set_last_error("assign: precision path %d is not built in this version", precision_path);
+    if (precision_path != MWE_ASSIGN_FP64 && precision_path != MWE_ASSIGN_TF32X3) {
+        set_last_error("assign: unknown precision path %d", precision_path);
         return MWE_E_UNSUPPORTED;
     }
     if (N == 0) return MWE_OK;
-    if (workspace_bytes < assign_ws_bytes(N, nbins)) {
-        set_last_error("assign: workspace too small (%zu < %zu)", workspace_bytes, assign_ws_bytes(N, nbins));
+    const bool use_tc = precision_path == MWE_ASSIGN_TF32X3;
+    const size_t need = assign_ws_bytes(N, nbins) + (use_tc ? assign_tc_prep_bytes(nbins, D, max_k) : 0);
+    if (workspace_bytes < need) {
+        set_last_error("assign: workspace too small (%zu < %zu)", workspace_bytes, need);
         return MWE_E_WORKSPACE;
     }
     Carver cv(workspace, workspace_bytes);
@@ -749,7 +639,7 @@ extern "C" int mwe_assign_stratified_f64(const double* X, int64_t N, int D, int6
     ws.tile_prefix = cv.take<int32_t>((size_t)nbins + 1);
 
     const int nt = pick_nt(max_k);
-    const int tile_points = tile_points_for(nt);
+    const int tile_points = use_tc ? 128 : tile_points_for(nt);
     MWE_CHECK_CUDA(cudaMemsetAsync(ws.bin_count, 0, (size_t)(nbins + 2) * sizeof(int32_t), s));
     const int64_t blocks = (N + 256 * AS_BK_ITEMS - 1) / (256 * AS_BK_ITEMS);
     if (!bin_count_in) assign_count_kernel<<<(unsigned)blocks, 256, 0, s>>>(bin, flag, N, nbins, ws.bin_count);
@@ -770,7 +660,14 @@ extern "C" int mwe_assign_stratified_f64(const double* X, int64_t N, int D, int6
     const int64_t max_tiles = (N + tile_points - 1) / tile_points + nbins;
     const bool vec2 = (D % 2 == 0) && (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(centers) & 15) == 0);
-    const int rc = vec2 ? dispatch_nt<2>(nt, p, max_tiles, s) : dispatch_nt<1>(nt, p, max_tiles, s);
+    int rc;
+    if (use_tc) {
+        const size_t prep_bytes = assign_tc_prep_bytes(nbins, D, max_k);
+        void* prep = cv.take<char>(prep_bytes);
+        rc = launch_assign_tc(p, max_k, N, prep, prep_bytes, s);
+    } else {
+        rc = vec2 ? dispatch_nt<2>(nt, p, max_tiles, s) : dispatch_nt<1>(nt, p, max_tiles, s);
+    }
     if (rc != MWE_OK) return rc;
     assign_recheck_kernel<<<sm_count(), 128, 0, s>>>(X, ldx, D, bin, centers, csq, bin_offset, ws.recheck_list,
                                                     ws.recheck_count, p.tie_scale, label_out, local_out);

@@ -1,0 +1,604 @@
+// K1, fast path: tcgen05 (5th-gen tensor core) candidate pass + exact fp64 re-check of close calls.
+//
+// reference arithmetic: sklearn/cluster/_k_means_lloyd.pyx:168-218 (score_j = ||c_j||^2 - 2 x.c_j, first
+// minimum wins), reached from msm_we/stratified_clustering.py:152-203.
+//
+// Why: the fp64 tensor pipe (DMMA, 37 TFLOP/s measured) cannot keep up with HBM once K_b*D grows
+// (BASELINE cfg3/cfg5 need 4x the fp64 FLOPs HBM time allows; even cfg2 sits on the ridge).  The labels only
+// need the ORDER of the scores, and an order decided with a margin larger than the evaluation error is the
+// fp64 order.  So: evaluate x.c on the tensor cores with split TF32 operands (x = hi + lo, each TF32;
+// hi.hi + hi.lo + lo.hi accumulated in fp32 in TMEM, ~2^-20 relative), take the argmin and the runner-up,
+// and hand every point whose margin does not clear a rigorous error bound to the same fp64 re-check
+// kernel the DMMA path uses (assign.cu, assign_recheck_kernel).  Result: identical labels, HBM-bound kernel.
+//
+// Data flow of one CTA (persistent, one per SM, 128 points per tile, all of one WE bin):
+//   loader warps (8)  : gather the tile's fp64 rows straight from HBM into registers (2 x LDG.128 per
+//                       thread and row chunk), subtract the bin's mean centre (translation invariance ->
+//                       smaller norms -> tighter error bound), split into TF32 hi / lo and store them in the
+//                       UMMA canonical K-major layout (8-row x 16-byte core matrices, no swizzle, padded
+//                       leading offset so the stores are bank-conflict free); also accumulate ||x||^2
+//   centre warp (1)   : one cp.async.bulk (TMA) per k-chunk brings the bin's PRE-SPLIT centre block
+//                       (prepared once per call, already in the canonical layout) into the same stage
+//   MMA warp (1 lane) : per k-chunk 4 k-steps x 3 tcgen05.mma.kind::tf32 (M=128, N=padded K_b, K=8) into a
+//                       TMEM accumulator; tcgen05.commit releases the smem stage / publishes the accumulator
+//   epilogue warps (4): tcgen05.ld their 32 TMEM lanes (one point per thread), scores = ||c'||^2 - 2 dot,
+//                       running best / runner-up, label store, near-tie list for the re-check
+// Two TMEM accumulators alternate so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "assign_common.cuh"
+
+namespace mwe {
+
+static constexpr int TC_TP = 128;                          // points per tile (UMMA M)
+static constexpr int TC_KC = 32;                           // TF32 elements per k-chunk
+static constexpr int TC_LBO = 144;                         // bytes between K-adjacent core matrices (128 + 16 pad)
+static constexpr int TC_SBO = 8 * TC_LBO;                  // bytes between 8-row groups (8 core matrices / chunk)
+static constexpr int TC_A_BYTES = (TC_TP / 8) * TC_SBO;    // one hi or lo point tile
+static constexpr int TC_LOADER_WARPS = 8;
+static constexpr int TC_EPI_WARP0 = 4;                     // epilogue warps 4..7 (warp % 4 == TMEM lane quarter)
+static constexpr int TC_LOAD_WARP0 = 8;
+static constexpr int TC_THREADS = 16 * 32;
+static constexpr int TC_MAX_STAGES = 6;
+static constexpr size_t TC_SMEM_BUDGET = 222 * 1024;
+
+struct TcParams {
+    AssignParams a;
+    const unsigned char* bprep;   // [bin][cb][kc] -> hi block, lo block (canonical layout, TC_SBO per 8 rows)
+    const double* mean;           // [bin][d_pad]   bin mean centre (zero padded)
+    const float* csqf;            // [bin][ncb * n_pad]  centred ||c'||^2 (+inf for padding columns)
+    const float* cmaxf;           // [bin][2]  upper bounds of max ||c'||^2 (centred) and max ||c||^2 (raw)
+    int n_pad;                    // UMMA N: centres per block, multiple of 16, <= 256
+    int d_pad;                    // nch * TC_KC
+    int nstages;
+    uint32_t tmem_cols;           // power of two >= 2 * n_pad
+    float err_coef;               // bound of |score error| / (cmax' (2 ||x'|| + cmax'))
+    float* dbg_scores;            // tests only: [N][ncb * n_pad] fp32 scores as the tensor cores produced them
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// preparation: bin means, pre-split centres in the canonical layout, centred norms
+// ---------------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(128)
+    tc_mean_kernel(const double* __restrict__ centers, const int64_t* __restrict__ bin_offset, int D, int d_pad,
+                   double* __restrict__ mean) {
+    const int b = blockIdx.x;
+    const int k = blockIdx.y * 128 + threadIdx.x;
+    if (k >= d_pad) return;
+    const int64_t c0 = bin_offset[b], c1 = bin_offset[b + 1];
+    double s = 0.0;
+    if (k < D)
+        for (int64_t j = c0; j < c1; ++j) s += centers[j * D + k];
+    mean[(size_t)b * d_pad + k] = (c1 > c0 && k < D) ? s / (double)(c1 - c0) : 0.0;
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// one thread per (bin, centre block, row of the block, 4-element k group)
+__global__ void __launch_bounds__(256)
+    tc_split_centers_kernel(const double* __restrict__ centers, const int64_t* __restrict__ bin_offset, int32_t nbins,
+                            int D, int d_pad, int n_pad, int ncb, const double* __restrict__ mean,
+                            unsigned char* __restrict__ bprep) {
+    const int k4n = d_pad / 4;
+    const int64_t total = (int64_t)nbins * ncb * n_pad * k4n;
+    const int nch = d_pad / TC_KC;
+    const int ng = n_pad / 8;
+    const size_t block_bytes = (size_t)2 * ng * TC_SBO;   // hi + lo of one (bin, cb, kc)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k4 = (int)(i % k4n);
+        int64_t r = i / k4n;
+        const int n = (int)(r % n_pad);
+        r /= n_pad;
+        const int cb = (int)(r % ncb);
+        const int b = (int)(r / ncb);
+        const int64_t c0 = bin_offset[b];
+        const int kb = (int)(bin_offset[b + 1] - c0);
+        const int c = cb * n_pad + n;
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = k4 * 4 + e;
+            double v = 0.0;
+            if (c < kb && k < D) v = centers[(c0 + c) * D + k] - mean[(size_t)b * d_pad + k];
+            const float vf = (float)v;
+            hi[e] = tf32_rna(vf);
+            lo[e] = vf - hi[e];
+        }
+        const int kc = k4 / 8, kc8 = k4 % 8;
+        unsigned char* base = bprep + ((size_t)(b * ncb + cb) * nch + kc) * block_bytes;
+        const size_t off = (size_t)(n / 8) * TC_SBO + (size_t)kc8 * TC_LBO + (size_t)(n % 8) * 16;
+        *reinterpret_cast<float4*>(base + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(base + (size_t)ng * TC_SBO + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// one warp per (bin, padded column): centred squared norm (fp64 sum, rounded to fp32) and per-bin maxima
+__global__ void __launch_bounds__(256)
+    tc_csq_kernel(const double* __restrict__ centers, const double* __restrict__ csq_raw,
+                  const int64_t* __restrict__ bin_offset, int32_t nbins, int D, int d_pad, int ncols,
+                  const double* __restrict__ mean, float* __restrict__ csqf, float* __restrict__ cmaxf) {
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= (int64_t)nbins * ncols) return;
+    const int b = (int)(w / ncols), c = (int)(w % ncols);
+    const int64_t c0 = bin_offset[b];
+    const int kb = (int)(bin_offset[b + 1] - c0);
+    const int lane = threadIdx.x & 31;
+    float out = __int_as_float(0x7f800000);  // +inf: padding columns can never win
+    if (c < kb) {
+        double s = 0.0;
+        for (int k = lane; k < D; k += 32) {
+            const double v = centers[(c0 + c) * D + k] - mean[(size_t)b * d_pad + k];
+            s = fma(v, v, s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        out = (float)s;
+        if (lane == 0) {
+            // positive floats order like their bit patterns
+            atomicMax(reinterpret_cast<int*>(cmaxf + 2 * b), __float_as_int(__double2float_ru(s)));
+            atomicMax(reinterpret_cast<int*>(cmaxf + 2 * b + 1), __float_as_int(__double2float_ru(csq_raw[c0 + c])));
+        }
+    }
+    if (lane == 0) csqf[(size_t)b * ncols + c] = out;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tcgen05 helpers
+// ---------------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    // K-major, no swizzle: start address, leading (K) byte offset, stride (8-row group) byte offset, version 1
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(TC_LBO >> 4) << 16;
+    d |= (uint64_t)(TC_SBO >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------------------
+
+template <int VEC>
+__global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams q) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const AssignParams& p = q.a;
+    __shared__ uint64_t full_bar[TC_MAX_STAGES];
+    __shared__ uint64_t empty_bar[TC_MAX_STAGES];
+    __shared__ uint64_t tmem_full[2], tmem_empty[2], xn_full[2], xn_empty[2];
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ float s_xn[2][2][TC_TP];   // [buffer][0: centred ||x'||^2, 1: raw ||x||^2][row]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nstages = q.nstages;
+    const int ng = q.n_pad / 8;
+    const uint32_t b_bytes = (uint32_t)(2 * ng * TC_SBO);
+    const uint32_t stage_bytes = 2u * TC_A_BYTES + b_bytes;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nstages; ++s) {
+            mbar_init(&full_bar[s], TC_LOADER_WARPS + 1);   // 8 loader warps + the centre warp's expect_tx arrive
+            mbar_init(&empty_bar[s], 1);                    // tcgen05.commit
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);    // tcgen05.commit
+            mbar_init(&tmem_empty[i], 4);   // one lane per epilogue warp
+            mbar_init(&xn_full[i], TC_LOADER_WARPS);
+            mbar_init(&xn_empty[i], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // bin tables -> shared memory
+    TileTables tt{p.tile_prefix, p.bin_start, p.bin_offset, p.nbins};
+    if (p.nbins <= AS_TABLE_BINS) {
+        int32_t* s_tp = reinterpret_cast<int32_t*>(smem_raw + (size_t)nstages * stage_bytes);
+        int32_t* s_bs = s_tp + (p.nbins + 1);
+        int64_t* s_bo = reinterpret_cast<int64_t*>(s_bs + (p.nbins + 1));
+        for (int b = threadIdx.x; b <= p.nbins; b += TC_THREADS) {
+            s_tp[b] = p.tile_prefix[b];
+            s_bs[b] = p.bin_start[b];
+            s_bo[b] = p.bin_offset[b];
+        }
+        tt = TileTables{s_tp, s_bs, s_bo, p.nbins};
+    }
+    if (warp == 0) {
+        // TMEM allocation (whole warp), address lands in shared memory
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(q.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    const int32_t n_tiles = tt.tile_prefix[p.nbins];
+    const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int ncb = p.ncb, nch = p.nch;
+
+    if (warp == 0) {
+        // =========================== MMA issuer (one lane) ===========================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(q.n_pad >> 3) << 17) | ((uint32_t)(TC_TP >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t tphase[2] = {0, 0};
+            int unit = 0;
+            for (int ti = 0; ti < my_tiles; ++ti)
+                for (int cb = 0; cb < ncb; ++cb, ++unit) {
+                    const int ab = unit & 1;
+                    mbar_wait(&tmem_empty[ab], tphase[ab] ^ 1u);   // epilogue has drained this accumulator
+                    tphase[ab] ^= 1u;
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(ab * q.n_pad);
+                    for (int kc = 0; kc < nch; ++kc) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem_raw + (size_t)stage * stage_bytes);
+                        const uint32_t a_hi = sa, a_lo = sa + TC_A_BYTES;
+                        const uint32_t b_hi = sa + 2 * TC_A_BYTES, b_lo = b_hi + (uint32_t)(ng * TC_SBO);
+#pragma unroll
+                        for (int j = 0; j < TC_KC / 8; ++j) {
+                            const uint32_t ko = (uint32_t)(j * 2 * TC_LBO);
+                            const uint64_t dah = make_smem_desc(a_hi + ko), dal = make_smem_desc(a_lo + ko);
+                            const uint64_t dbh = make_smem_desc(b_hi + ko), dbl = make_smem_desc(b_lo + ko);
+                            umma_tf32(d_tmem, dah, dbh, idesc, (kc | j) != 0);   // hi.hi (first MMA overwrites)
+                            umma_tf32(d_tmem, dah, dbl, idesc, 1);              // hi.lo
+                            umma_tf32(d_tmem, dal, dbh, idesc, 1);              // lo.hi
+                        }
+                        umma_commit(&empty_bar[stage]);   // stage reusable once these MMAs have read it
+                        if (kc == nch - 1) umma_commit(&tmem_full[ab]);
+                        if (++stage == nstages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+        }
+    } else if (warp == 1) {
+        // =========================== centre-block producer (one lane) ===========================
+        if (lane == 0) {
+            TileWalk<TC_TP> w{0, 0, 0, 0, 0, 0, 0, 0};
+            w.load(tt, my_tiles);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                for (int cb = 0; cb < ncb; ++cb)
+                    for (int kc = 0; kc < nch; ++kc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        unsigned char* dst = smem_raw + (size_t)stage * stage_bytes + 2 * TC_A_BYTES;
+                        const unsigned char* src = q.bprep + ((size_t)(w.bin * ncb + cb) * nch + kc) * b_bytes;
+                        mbar_expect_tx(&full_bar[stage], b_bytes);
+                        bulk_copy_g2s(dst, src, b_bytes, &full_bar[stage]);
+                        if (++stage == nstages) { stage = 0; phase ^= 1u; }
+                    }
+                w.next_tile(tt, my_tiles);
+            }
+        }
+    } else if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + 4) {
+        // =========================== epilogue: one point per thread ===========================
+        const int row = (warp - TC_EPI_WARP0) * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)((warp - TC_EPI_WARP0) * 32) << 16;
+        const float finf = __int_as_float(0x7f800000);
+        TileWalk<TC_TP> w{0, 0, 0, 0, 0, 0, 0, 0};
+        w.load(tt, my_tiles);
+        uint32_t tphase[2] = {0, 0};
+        uint32_t xphase[2] = {0, 0};
+        int unit = 0;
+        const int ncols = ncb * q.n_pad;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int32_t pt = (row < w.pcount) ? p.perm[w.pstart + row] : -1;   // label destination, fetched early
+            const float* csqf = q.csqf + (size_t)w.bin * ncols;
+            float m1 = finf, m2 = finf;
+            int32_t bi = 0;
+            for (int cb = 0; cb < ncb; ++cb, ++unit) {
+                const int ab = unit & 1;
+                mbar_wait(&tmem_full[ab], tphase[ab]);
+                tphase[ab] ^= 1u;
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(ab * q.n_pad);
+                for (int c0 = 0; c0 < q.n_pad; c0 += 16) {
+                    if (cb * q.n_pad + c0 >= w.kb) break;   // only padding beyond here (warp-uniform)
+                    float v[16];
+                    tmem_ld16(taddr + (uint32_t)c0, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int c = cb * q.n_pad + c0 + j;
+                        const float sf = fmaf(-2.0f, v[j], __ldg(csqf + c));   // +inf on padding columns
+                        if (q.dbg_scores && pt >= 0) q.dbg_scores[(size_t)pt * ncols + c] = sf;
+                        const bool lt = sf < m1;
+                        m2 = lt ? m1 : fminf(m2, sf);
+                        bi = lt ? c : bi;
+                        m1 = lt ? sf : m1;
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[ab]);
+            }
+            // norms of this tile's rows from the loader warps
+            const int xb = ti & 1;
+            mbar_wait(&xn_full[xb], xphase[xb]);
+            xphase[xb] ^= 1u;
+            const float xn2c = s_xn[xb][0][row], xn2r = s_xn[xb][1][row];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&xn_empty[xb]);
+            if (pt >= 0) {
+                p.label_out[pt] = w.coff + bi;
+                if (p.local_out) p.local_out[pt] = bi;
+                const float cmc = sqrtf(q.cmaxf[2 * w.bin]) * 1.000001f;       // centred max ||c'||
+                const float cmr = sqrtf(q.cmaxf[2 * w.bin + 1]) * 1.000001f;   // raw max ||c||
+                const float err = q.err_coef * cmc * (2.0f * sqrtf(xn2c) * 1.000001f + cmc);   // tensor-core evaluation error
+                const float tol = (float)p.tie_scale * cmr * (2.0f * sqrtf(xn2r) * 1.000001f + cmr);   // fp64 tie band
+                // both scores may be off by err: the order is certain only beyond 2 err (+ the tie band)
+                if (!(m2 - m1 > 2.0f * err + 2.0f * tol)) p.recheck_list[atomicAdd(p.recheck_count, 1)] = pt;
+            }
+            w.next_tile(tt, my_tiles);
+        }
+    } else if (warp >= TC_LOAD_WARP0) {
+        // =========================== loaders: HBM fp64 rows -> TF32 hi/lo tiles ===========================
+        const int lt = threadIdx.x - TC_LOAD_WARP0 * 32;   // 0..255
+        const int slot = lt & 7;                           // 4-element k group inside the chunk
+        const int rbase = lt >> 3;                         // 0..31; this thread's rows: rbase + 32 * pass
+        TileWalk<TC_TP> w{0, 0, 0, 0, 0, 0, 0, 0};
+        w.load(tt, my_tiles);
+        TileWalk<TC_TP> nw = w;
+        int32_t pidx[4], pidx_next[4];
+        auto fetch = [&](const TileWalk<TC_TP>& t, int32_t* out) {
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+                const int r = rbase + 32 * ps;
+                out[ps] = (r < t.pcount) ? p.perm[t.pstart + r] : -1;
+            }
+        };
+        fetch(w, pidx);
+        nw.next_tile(tt, my_tiles);
+        fetch(nw, pidx_next);
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t xphase[2] = {0, 0};
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            float xc[4] = {0.f, 0.f, 0.f, 0.f}, xr[4] = {0.f, 0.f, 0.f, 0.f};
+            const double* mean = q.mean + (size_t)w.bin * q.d_pad;
+            for (int cb = 0; cb < ncb; ++cb)
+                for (int kc = 0; kc < nch; ++kc) {
+                    const int k0 = kc * TC_KC + slot * 4;
+                    double mu[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) mu[e] = mean[k0 + e];   // d_pad is a multiple of the chunk: in range
+                    double xv[4][4];
+#pragma unroll
+                    for (int ps = 0; ps < 4; ++ps) {
+                        if (pidx[ps] >= 0) {
+                            const double* src = p.X + (int64_t)pidx[ps] * p.ldx + k0;
+                            if (VEC == 2 && k0 + 4 <= p.D) {
+                                const double2 u0 = *reinterpret_cast<const double2*>(src);
+                                const double2 u1 = *reinterpret_cast<const double2*>(src + 2);
+                                xv[ps][0] = u0.x; xv[ps][1] = u0.y; xv[ps][2] = u1.x; xv[ps][3] = u1.y;
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) xv[ps][e] = (k0 + e < p.D) ? src[e] : 0.0;
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) xv[ps][e] = 0.0;
+                        }
+                    }
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    unsigned char* sa = smem_raw + (size_t)stage * stage_bytes;
+#pragma unroll
+                    for (int ps = 0; ps < 4; ++ps) {
+                        const int r = rbase + 32 * ps;
+                        float hi[4], lo[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const bool in = (k0 + e < p.D) && pidx[ps] >= 0;
+                            const float xf = in ? (float)(xv[ps][e] - mu[e]) : 0.f;
+                            hi[e] = tf32_rna(xf);
+                            lo[e] = xf - hi[e];
+                            if (cb == 0) {
+                                const float xraw = (float)xv[ps][e];
+                                xc[ps] = fmaf(xf, xf, xc[ps]);
+                                xr[ps] = fmaf(xraw, xraw, xr[ps]);
+                            }
+                        }
+                        const uint32_t off = (uint32_t)(r >> 3) * TC_SBO + (uint32_t)slot * TC_LBO + (uint32_t)(r & 7) * 16;
+                        *reinterpret_cast<float4*>(sa + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<float4*>(sa + TC_A_BYTES + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[stage]);
+                    if (++stage == nstages) { stage = 0; phase ^= 1u; }
+                }
+            // ||x'||^2 and ||x||^2 of this tile's rows -> epilogue (slightly inflated: fp32 sums of fp32 roundings)
+            const int xb = ti & 1;
+            mbar_wait(&xn_empty[xb], xphase[xb] ^ 1u);
+            xphase[xb] ^= 1u;
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+                float a = xc[ps], b2 = xr[ps];
+#pragma unroll
+                for (int o = 1; o <= 4; o <<= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, o);
+                    b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+                }
+                if (slot == 0) {
+                    s_xn[xb][0][rbase + 32 * ps] = a * 1.0001f;
+                    s_xn[xb][1][rbase + 32 * ps] = b2 * 1.0001f;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&xn_full[xb]);
+            w.next_tile(tt, my_tiles);
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) pidx[ps] = pidx_next[ps];
+            nw.next_tile(tt, my_tiles);
+            fetch(nw, pidx_next);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(q.tmem_cols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+
+static int tc_n_pad(int32_t max_k) {
+    int n = (max_k + 15) / 16 * 16;
+    return n > 256 ? 256 : (n < 16 ? 16 : n);
+}
+
+struct TcLayout {
+    int n_pad, ncb, nch, d_pad;
+    size_t bprep_bytes, mean_bytes, csqf_bytes, cmax_bytes;
+};
+static TcLayout tc_layout(int32_t nbins, int D, int32_t max_k) {
+    TcLayout L;
+    L.n_pad = tc_n_pad(max_k);
+    L.ncb = (max_k + L.n_pad - 1) / L.n_pad;
+    L.nch = (D + TC_KC - 1) / TC_KC;
+    L.d_pad = L.nch * TC_KC;
+    L.bprep_bytes = (size_t)nbins * L.ncb * L.nch * 2 * (L.n_pad / 8) * TC_SBO;
+    L.mean_bytes = (size_t)nbins * L.d_pad * sizeof(double);
+    L.csqf_bytes = (size_t)nbins * L.ncb * L.n_pad * sizeof(float);
+    L.cmax_bytes = (size_t)nbins * 2 * sizeof(float);
+    return L;
+}
+
+size_t assign_tc_prep_bytes(int32_t nbins, int D, int32_t max_k) {
+    const TcLayout L = tc_layout(nbins, D, max_k);
+    return align_up(L.bprep_bytes, 256) + align_up(L.mean_bytes, 256) + align_up(L.csqf_bytes, 256) +
+           align_up(L.cmax_bytes, 256) + 1024;
+}
+
+static float* g_dbg_scores = nullptr;   // set through mwe_debug_set_tc_scores (tests only)
+
+int launch_assign_tc(const AssignParams& p_in, int32_t max_k, int64_t N, void* prep, size_t prep_bytes, cudaStream_t stream) {
+    const TcLayout L = tc_layout(p_in.nbins, p_in.D, max_k);
+    if (prep_bytes < assign_tc_prep_bytes(p_in.nbins, p_in.D, max_k)) {
+        set_last_error("assign(tc): preparation workspace too small");
+        return MWE_E_WORKSPACE;
+    }
+    Carver cv(prep, prep_bytes);
+    unsigned char* bprep = cv.take<unsigned char>(L.bprep_bytes);
+    double* mean = cv.take<double>((size_t)p_in.nbins * L.d_pad);
+    float* csqf = cv.take<float>((size_t)p_in.nbins * L.ncb * L.n_pad);
+    float* cmaxf = cv.take<float>((size_t)p_in.nbins * 2);
+
+    // ---- preparation (depends on the centres only) ----
+    MWE_CHECK_CUDA(cudaMemsetAsync(cmaxf, 0, L.cmax_bytes, stream));
+    tc_mean_kernel<<<dim3((unsigned)p_in.nbins, (unsigned)((L.d_pad + 127) / 128)), 128, 0, stream>>>(p_in.centers, p_in.bin_offset,
+                                                                                                  p_in.D, L.d_pad, mean);
+    {
+        const int64_t total = (int64_t)p_in.nbins * L.ncb * L.n_pad * (L.d_pad / 4);
+        int64_t blocks = (total + 255) / 256;
+        const int64_t cap = (int64_t)sm_count() * 16;
+        if (blocks > cap) blocks = cap;
+        tc_split_centers_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p_in.centers, p_in.bin_offset, p_in.nbins, p_in.D, L.d_pad,
+                                                                     L.n_pad, L.ncb, mean, bprep);
+        const int64_t warps = (int64_t)p_in.nbins * L.ncb * L.n_pad;
+        tc_csq_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(p_in.centers, p_in.csq, p_in.bin_offset, p_in.nbins, p_in.D,
+                                                                      L.d_pad, L.ncb * L.n_pad, mean, csqf, cmaxf);
+    }
+    MWE_CHECK_LAUNCH();
+
+    // ---- main kernel ----
+    TcParams q;
+    q.a = p_in;
+    q.a.ncb = L.ncb;
+    q.a.nch = L.nch;
+    q.bprep = bprep; q.mean = mean; q.csqf = csqf; q.cmaxf = cmaxf;
+    q.n_pad = L.n_pad; q.d_pad = L.d_pad;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * L.n_pad)) cols <<= 1;
+    q.tmem_cols = cols;
+    // |score error| <= err_coef * cmax' (2 ||x'|| + cmax'):
+    //   operands: fp32 rounding (2^-24) + TF32 split residual (<= 2^-21 each)      -> 2^-20 on a product
+    //   dropped lo.lo term                                                       -> 2^-22
+    //   fp32 accumulation in the tensor core: <= 2 ulp per MMA, 3 D/8 MMAs         -> 3 ceil(D/8) 2^-22
+    //   fp32 score arithmetic (csq rounding, the fma)                            -> 2^-21
+    q.err_coef = (float)(1.0 / 1048576.0 + (3.0 * ((p_in.D + 7) / 8) + 10.0) / 4194304.0);
+    q.dbg_scores = g_dbg_scores;
+    const size_t stage_bytes = 2 * (size_t)TC_A_BYTES + (size_t)2 * (L.n_pad / 8) * TC_SBO;
+    const size_t table_bytes = (p_in.nbins <= AS_TABLE_BINS) ? (size_t)(p_in.nbins + 2) * 16 + 16 : 0;
+    int nstages = (int)((TC_SMEM_BUDGET - table_bytes) / stage_bytes);
+    if (nstages > TC_MAX_STAGES) nstages = TC_MAX_STAGES;
+    if (nstages < 2) {
+        set_last_error("assign(tc): a pipeline stage does not fit in shared memory");
+        return MWE_E_UNSUPPORTED;
+    }
+    q.nstages = nstages;
+    const size_t smem = stage_bytes * nstages + table_bytes;
+    const bool vec2 = (p_in.D % 2 == 0) && (p_in.ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(p_in.X) & 15) == 0);
+    const int64_t max_tiles = (N + TC_TP - 1) / TC_TP + p_in.nbins;
+    int64_t grid = sm_count();
+    if (grid > max_tiles) grid = max_tiles;
+    if (grid < 1) grid = 1;
+    cudaEvent_t ev0, ev1;
+    timing_events(&ev0, &ev1);
+    if (vec2) {
+        static size_t configured = 0;
+        if (configured < smem) {
+            MWE_CHECK_CUDA(cudaFuncSetAttribute(assign_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        if (ev0) MWE_CHECK_CUDA(cudaEventRecord(ev0, stream));
+        assign_tc_kernel<2><<<(unsigned)grid, TC_THREADS, smem, stream>>>(q);
+    } else {
+        static size_t configured = 0;
+        if (configured < smem) {
+            MWE_CHECK_CUDA(cudaFuncSetAttribute(assign_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        if (ev0) MWE_CHECK_CUDA(cudaEventRecord(ev0, stream));
+        assign_tc_kernel<1><<<(unsigned)grid, TC_THREADS, smem, stream>>>(q);
+    }
+    MWE_CHECK_LAUNCH();
+    if (ev1) MWE_CHECK_CUDA(cudaEventRecord(ev1, stream));
+    return MWE_OK;
+}
+
+}  // namespace mwe
+
+// tests only: device buffer [N][ncb * n_pad] that receives the fp32 scores of the next tcgen05 assignment calls
+extern "C" int mwe_debug_set_tc_scores(float* buf) {
+    mwe::g_dbg_scores = buf;
+    return MWE_OK;
+}
+extern "C" int mwe_debug_tc_columns(int32_t max_k) {
+    const int n = mwe::tc_n_pad(max_k);
+    return ((max_k + n - 1) / n) * n;
+}

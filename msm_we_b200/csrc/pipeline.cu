@@ -8,6 +8,11 @@
 // launch-bound: BASELINE cfg2 is 32 us of HBM time).
 #include "common.cuh"
 
+extern "C" size_t mwe_hotpath_workspace_bytes_ex(int64_t n_frames, int32_t nbins, int D, int32_t max_k, int precision_path) {
+    return mwe_hotpath_workspace_bytes(n_frames, nbins) +
+           (mwe_assign_workspace_bytes_ex(2 * n_frames, nbins, D, max_k, precision_path) - mwe_assign_workspace_bytes(2 * n_frames, nbins));
+}
+
 extern "C" size_t mwe_hotpath_workspace_bytes(int64_t n_frames, int32_t nbins) {
     const int64_t N2 = 2 * n_frames;
     size_t b = 0;
@@ -29,7 +34,7 @@ extern "C" int mwe_hotpath_step_f64(const double* X2, int64_t ldx, int D, const 
                                     size_t workspace_bytes, int32_t* err_count, void* stream) {
     using namespace mwe;
     MWE_REQUIRE(n_frames >= 0, "hotpath: negative frame count");
-    if (workspace_bytes < mwe_hotpath_workspace_bytes(n_frames, nbins)) {
+    if (workspace_bytes < mwe_hotpath_workspace_bytes_ex(n_frames, nbins, D, max_k, precision_path)) {
         set_last_error("hotpath: workspace too small");
         return MWE_E_WORKSPACE;
     }
@@ -38,7 +43,7 @@ extern "C" int mwe_hotpath_step_f64(const double* X2, int64_t ldx, int D, const 
     int32_t* bins = cv.take<int32_t>((size_t)(N2 > 0 ? N2 : 1));
     uint8_t* flags = cv.take<uint8_t>((size_t)(N2 > 0 ? N2 : 1));
     int32_t* bin_count = cv.take<int32_t>((size_t)nbins + 1);
-    const size_t aws = mwe_assign_workspace_bytes(N2, nbins);
+    const size_t aws = mwe_assign_workspace_bytes_ex(N2, nbins, D, max_k, precision_path);
     void* assign_ws = cv.take<char>(aws);
     const size_t fws = mwe_flux_workspace_bytes(n_frames);
     void* flux_ws = cv.take<char>(fws);

@@ -101,7 +101,7 @@ class DeviceClusters:
         P = pcoord2.shape[1]
         if labels_out is None:
             labels_out = torch.empty(n2, dtype=torch.int64, device=self.device)
-        nbytes = _lib.lib.mwe_hotpath_workspace_bytes(n, self.nbins)
+        nbytes = _lib.lib.mwe_hotpath_workspace_bytes_ex(n, self.nbins, D, self.max_k, int(path))
         ws = ops.Workspace.get(self.device, nbytes)
         n_iters = 0 if iter_offsets is None else iter_offsets.numel() - 1
         lens_p = self.mapper.lens.ctypes.data if self.mapper.lens is not None else None

@@ -161,7 +161,7 @@ def assign_stratified(X, bin, flag, centers, csq, bin_offset, max_k, path=_lib.A
     if label_out is None:
         label_out = torch.empty(N, dtype=torch.int64, device=dev)
     local = torch.empty(N, dtype=torch.int32, device=dev) if want_local else None
-    nbytes = lib.mwe_assign_workspace_bytes(N, nbins)
+    nbytes = lib.mwe_assign_workspace_bytes_ex(N, nbins, D, int(max_k), int(path))
     ws = Workspace.get(dev, nbytes)
     check(lib.mwe_assign_stratified_f64(_ptr(X), N, D, ldx, _ptr(bin), _ptr(flag), _ptr(centers), _ptr(csq),
                                         _ptr(bin_offset), nbins, int(max_k), int(path), _ptr(bin_count), _ptr(label_out),

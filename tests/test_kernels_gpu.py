@@ -140,6 +140,70 @@ def test_assign_matches_oracle(N, D, nbins, K, ragged):
     assert np.array_equal(local.cpu().numpy()[free & safe], (ref - offs[bins])[free & safe])
 
 
+@pytest.mark.parametrize("N,D,nbins,K,ragged", [
+    (1, 3, 1, 1, False),
+    (1000, 13, 12, 25, False),      # NTL9 shape; odd D -> scalar loader path
+    (5000, 64, 30, 20, False),      # BASELINE cfg2 shape
+    (3000, 7, 5, 100, True),
+    (2000, 34, 3, 130, False),      # UMMA N = 144
+    (1500, 24, 2, 300, False),      # K > 256: two centre blocks, points re-streamed
+    (700, 300, 4, 50, True),        # ten k-chunks
+    (4000, 256, 6, 100, False),     # BASELINE cfg5 shape
+])
+def test_assign_tcgen05_path_gives_identical_labels(N, D, nbins, K, ragged):
+    """precision path 1 (tcgen05 split-TF32 candidate pass + fp64 re-check) must label exactly like the
+    fp64 path: the fast pass only decides what its error bound allows, the rest is re-evaluated in fp64."""
+    from msm_we_b200 import _lib
+    ops = _ops()
+    rng = np.random.default_rng(N * 11 + D)
+    X, bins, flags, centers, offs, ks = _strat_case(rng, N, D, nbins, K, ragged)
+    X += 5.0                                    # a common offset: the kernel centres by the bin mean
+    centers = centers + 5.0
+    c = t(centers)
+    csq = ops.centers_sqnorm(c)
+    lab_tc, loc_tc = ops.assign_stratified(t(X), t(bins), t(flags), c, csq, t(offs), int(ks.max()),
+                                           path=_lib.ASSIGN_TF32X3, want_local=True)
+    lab_64 = ops.assign_stratified(t(X), t(bins), t(flags), c, csq, t(offs), int(ks.max()), path=_lib.ASSIGN_FP64)
+    assert np.array_equal(lab_tc.cpu().numpy(), lab_64.cpu().numpy())
+    ref, margins = _ref_labels(X, bins, flags, centers, offs)
+    assert np.array_equal(lab_tc.cpu().numpy()[margins > 0], ref[margins > 0])
+
+
+def test_assign_tcgen05_scores_within_error_bound():
+    """The rigorous part of the fast path is its error bound: dump the scores the tensor cores produced and
+    compare them with fp64 (centred by the bin mean, as the kernel does)."""
+    import ctypes
+    from msm_we_b200 import _lib
+    ops = _ops()
+    rng = np.random.default_rng(99)
+    worst = 0.0
+    for N, D, K in [(600, 64, 20), (500, 300, 50), (400, 13, 25)]:
+        centers = rng.normal(size=(K, D)) * 3 + 10.0
+        X = centers[rng.integers(0, K, N)] + rng.normal(size=(N, D))
+        bins = np.zeros(N, dtype=np.int32); flags = np.zeros(N, dtype=np.uint8)
+        offs = np.array([0, K], dtype=np.int64)
+        ncols = _lib.lib.mwe_debug_tc_columns(K)
+        dbg = torch.full((N, ncols), float("nan"), dtype=torch.float32, device=dev())
+        _lib.check(_lib.lib.mwe_debug_set_tc_scores(dbg.data_ptr()), "dbg")
+        try:
+            c = t(centers)
+            ops.assign_stratified(t(X), t(bins), t(flags), c, ops.centers_sqnorm(c), t(offs), K, path=_lib.ASSIGN_TF32X3)
+            torch.cuda.synchronize()
+        finally:
+            _lib.lib.mwe_debug_set_tc_scores(None)
+        got = dbg.cpu().numpy()[:, :K].astype(np.float64)
+        m = centers.mean(axis=0)
+        Xc, Cc = X - m, centers - m
+        ref = (Cc * Cc).sum(axis=1)[None, :] - 2.0 * Xc @ Cc.T
+        cmax = np.sqrt((Cc * Cc).sum(axis=1).max()); xn = np.sqrt((Xc * Xc).sum(axis=1))
+        coef = 2.0 ** -20 + (3 * ((D + 7) // 8) + 10) * 2.0 ** -22
+        bound = coef * cmax * (2 * xn + cmax)
+        ratio = (np.abs(got - ref) / bound[:, None]).max()
+        assert np.isfinite(got).all()
+        worst = max(worst, ratio)
+    assert worst < 1.0, worst          # measured ratio is reported in profiles/; the bound must never be exceeded
+
+
 def test_assign_ties_pick_lowest_index():
     ops = _ops()
     rng = np.random.default_rng(5)
