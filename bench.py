@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample-iters", type=int, default=0, help="iterations of the workload timed on the CPU (0 = auto)")
+    ap.add_argument("--precision-path", default="tf32x3", choices=["fp64", "tf32x3"],
+                    help="K1 evaluation: fp64 DMMA, or tcgen05 split-TF32 candidates + fp64 re-check (same labels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -300,7 +302,7 @@ def main():
     labels = torch.empty(2 * N, dtype=torch.int64, device=dev)
     l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     n_iters_total = cfg.n_iters * world
-    launches = {"n": 0}
+    path = _lib.ASSIGN_TF32X3 if args.precision_path == "tf32x3" else _lib.ASSIGN_FP64
 
     def step(ev=None):
         if ev is not None:
@@ -308,7 +310,7 @@ def main():
         dense.zero_()
         # one C call enqueues K0 -> K1 -> K3 (-> / nI when single-GPU)
         engine.hotpath_step(X, pc, w, n_clusters, iter_offsets=offs, dense=dense,
-                            divisor=float(n_iters_total) if world == 1 else 0.0, labels_out=labels)
+                            divisor=float(n_iters_total) if world == 1 else 0.0, labels_out=labels, path=path)
         if ev is not None:
             _lib.set_timing_events(None, None)
         if world > 1:
@@ -354,7 +356,7 @@ def main():
     peak, peak_src = load_peaks()
     alg_bytes = 2 * N * (cfg.dim * 8 + 4 + 8)
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "assign_dmma_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "assign_tc_kernel" if path == _lib.ASSIGN_TF32X3 else "assign_dmma_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "fp64_tflops": 2 * N * 2.0 * cfg.k_per_bin * cfg.dim / (kernel_ms * 1e-3) / 1e12}
@@ -382,7 +384,8 @@ def main():
                                    f"{cfg.n_bins} bins x {cfg.k_per_bin} clusters/bin, fp64 (per GPU; iteration-range "
                                    f"sharded, flux all-reduced)",
                        "frames_per_step": frames_per_step, "l2": "flushed between timed steps (256 MiB memset)",
-                       "precision_path": "fp64 DMMA"},
+                       "precision_path": ("tcgen05 split-TF32 candidate pass + fp64 re-check of near-ties (labels identical "
+                                          "to the fp64 path)") if path == _lib.ASSIGN_TF32X3 else "fp64 DMMA"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks.summary(),
             "gpu_launches": LAUNCHES_PER_STEP_STATIC(cfg) * args.steps,
         }
@@ -398,7 +401,7 @@ def LAUNCHES_PER_STEP_STATIC(cfg):
     M = cfg.n_clusters + 2
     bits = int(np.ceil(np.log2(M * M + 1)))
     passes = (bits + 7) // 8
-    return 1 + 5 + (1 + 3 * passes + 1 + 3 + 1 + 1) + 1
+    return 1 + 5 + 3 + (1 + 2 * passes + 1 + 3 + 1 + 1) + 1   # +3: centre preparation of the tcgen05 path
 
 
 def run_e2e(cfg, rank, world, dev, steps):

@@ -33,10 +33,12 @@ static constexpr int TC_KC = 32;                           // TF32 elements per 
 static constexpr int TC_LBO = 144;                         // bytes between K-adjacent core matrices (128 + 16 pad)
 static constexpr int TC_SBO = 8 * TC_LBO;                  // bytes between 8-row groups (8 core matrices / chunk)
 static constexpr int TC_A_BYTES = (TC_TP / 8) * TC_SBO;    // one hi or lo point tile
-static constexpr int TC_LOADER_WARPS = 8;
-static constexpr int TC_EPI_WARP0 = 4;                     // epilogue warps 4..7 (warp % 4 == TMEM lane quarter)
-static constexpr int TC_LOAD_WARP0 = 8;
-static constexpr int TC_THREADS = 16 * 32;
+static constexpr int TC_LOADER_WARPS = 16;
+static constexpr int TC_EPI_WARP0 = 0;                     // epilogue warps 0..3 (warp % 4 == TMEM lane quarter)
+static constexpr int TC_MMA_WARP = 4;
+static constexpr int TC_CENTRE_WARP = 5;
+static constexpr int TC_LOAD_WARP0 = 6;
+static constexpr int TC_THREADS = (TC_LOAD_WARP0 + TC_LOADER_WARPS) * 32;
 static constexpr int TC_MAX_STAGES = 6;
 static constexpr size_t TC_SMEM_BUDGET = 222 * 1024;
 
@@ -45,7 +47,7 @@ struct TcParams {
     const unsigned char* bprep;   // [bin][cb][kc] -> hi block, lo block (canonical layout, TC_SBO per 8 rows)
     const double* mean;           // [bin][d_pad]   bin mean centre (zero padded)
     const float* csqf;            // [bin][ncb * n_pad]  centred ||c'||^2 (+inf for padding columns)
-    const float* cmaxf;           // [bin][2]  upper bounds of max ||c'||^2 (centred) and max ||c||^2 (raw)
+    const float* cmaxf;           // [bin][3]  upper bounds: max ||c'||^2 (centred), max ||c||^2 (raw), ||mean||
     int n_pad;                    // UMMA N: centres per block, multiple of 16, <= 256
     int d_pad;                    // nch * TC_KC
     int nstages;
@@ -138,11 +140,22 @@ __global__ void __launch_bounds__(256)
         out = (float)s;
         if (lane == 0) {
             // positive floats order like their bit patterns
-            atomicMax(reinterpret_cast<int*>(cmaxf + 2 * b), __float_as_int(__double2float_ru(s)));
-            atomicMax(reinterpret_cast<int*>(cmaxf + 2 * b + 1), __float_as_int(__double2float_ru(csq_raw[c0 + c])));
+            atomicMax(reinterpret_cast<int*>(cmaxf + 3 * b), __float_as_int(__double2float_ru(s)));
+            atomicMax(reinterpret_cast<int*>(cmaxf + 3 * b + 1), __float_as_int(__double2float_ru(csq_raw[c0 + c])));
         }
     }
     if (lane == 0) csqf[(size_t)b * ncols + c] = out;
+    if (c == 0) {
+        // ||mean|| of the bin (upper bound), used for ||x|| <= ||x'|| + ||mean||
+        double s = 0.0;
+        for (int k = lane; k < D; k += 32) {
+            const double v = mean[(size_t)b * d_pad + k];
+            s = fma(v, v, s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) cmaxf[3 * b + 2] = __double2float_ru(sqrt(s)) * 1.000001f;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -194,7 +207,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
     __shared__ uint64_t empty_bar[TC_MAX_STAGES];
     __shared__ uint64_t tmem_full[2], tmem_empty[2], xn_full[2], xn_empty[2];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float s_xn[2][2][TC_TP];   // [buffer][0: centred ||x'||^2, 1: raw ||x||^2][row]
+    __shared__ float s_xn[2][TC_TP];      // [buffer][row]: centred ||x'||^2 (upper bound)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -229,7 +242,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
         }
         tt = TileTables{s_tp, s_bs, s_bo, p.nbins};
     }
-    if (warp == 0) {
+    if (warp == TC_MMA_WARP) {
         // TMEM allocation (whole warp), address lands in shared memory
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
                      "r"(q.tmem_cols)
@@ -245,7 +258,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
     const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int ncb = p.ncb, nch = p.nch;
 
-    if (warp == 0) {
+    if (warp == TC_MMA_WARP) {
         // =========================== MMA issuer (one lane) ===========================
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(q.n_pad >> 3) << 17) | ((uint32_t)(TC_TP >> 4) << 24);
@@ -281,7 +294,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
                     }
                 }
         }
-    } else if (warp == 1) {
+    } else if (warp == TC_CENTRE_WARP) {
         // =========================== centre-block producer (one lane) ===========================
         if (lane == 0) {
             TileWalk<TC_TP> w{0, 0, 0, 0, 0, 0, 0, 0};
@@ -346,16 +359,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
             const int xb = ti & 1;
             mbar_wait(&xn_full[xb], xphase[xb]);
             xphase[xb] ^= 1u;
-            const float xn2c = s_xn[xb][0][row], xn2r = s_xn[xb][1][row];
+            const float xn2c = s_xn[xb][row];
             __syncwarp();
             if (lane == 0) mbar_arrive(&xn_empty[xb]);
             if (pt >= 0) {
                 p.label_out[pt] = w.coff + bi;
                 if (p.local_out) p.local_out[pt] = bi;
-                const float cmc = sqrtf(q.cmaxf[2 * w.bin]) * 1.000001f;       // centred max ||c'||
-                const float cmr = sqrtf(q.cmaxf[2 * w.bin + 1]) * 1.000001f;   // raw max ||c||
-                const float err = q.err_coef * cmc * (2.0f * sqrtf(xn2c) * 1.000001f + cmc);   // tensor-core evaluation error
-                const float tol = (float)p.tie_scale * cmr * (2.0f * sqrtf(xn2r) * 1.000001f + cmr);   // fp64 tie band
+                const float cmc = sqrtf(q.cmaxf[3 * w.bin]) * 1.000001f;       // centred max ||c'||
+                const float cmr = sqrtf(q.cmaxf[3 * w.bin + 1]) * 1.000001f;   // raw max ||c||
+                const float xnc = sqrtf(xn2c) * 1.000001f;
+                const float xnr = xnc + q.cmaxf[3 * w.bin + 2];                  // ||x|| <= ||x'|| + ||mean||
+                const float err = q.err_coef * cmc * (2.0f * xnc + cmc);           // tensor-core evaluation error
+                const float tol = (float)p.tie_scale * cmr * (2.0f * xnr + cmr);   // fp64 tie band
                 // both scores may be off by err: the order is certain only beyond 2 err (+ the tie band)
                 if (!(m2 - m1 > 2.0f * err + 2.0f * tol)) p.recheck_list[atomicAdd(p.recheck_count, 1)] = pt;
             }
@@ -363,110 +378,126 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
         }
     } else if (warp >= TC_LOAD_WARP0) {
         // =========================== loaders: HBM fp64 rows -> TF32 hi/lo tiles ===========================
-        const int lt = threadIdx.x - TC_LOAD_WARP0 * 32;   // 0..255
+        // 8 lanes cover one 256-byte row chunk (4 elements = 2 x LDG.128 per lane), 16 warps cover 64 rows per
+        // pass, a thread owns rows rsub and rsub + 64.  The loads of step s+1 are issued before step s is
+        // converted (two register buffers): every loader keeps two chunks of HBM requests in flight.
+        // No masks in the math: a row past the tile end is read as zeros (garbage rows of the product are
+        // never used), the k-tail is read as zeros and the bin mean is zero-padded, so x' = 0 there.
+        const int lt = threadIdx.x - TC_LOAD_WARP0 * 32;   // 0..511
         const int slot = lt & 7;                           // 4-element k group inside the chunk
-        const int rbase = lt >> 3;                         // 0..31; this thread's rows: rbase + 32 * pass
-        TileWalk<TC_TP> w{0, 0, 0, 0, 0, 0, 0, 0};
-        w.load(tt, my_tiles);
-        TileWalk<TC_TP> nw = w;
-        int32_t pidx[4], pidx_next[4];
+        const int rsub = lt >> 3;                          // 0..63
+        constexpr int NP = TC_TP / 64;                     // rows per thread (2)
+        TileWalk<TC_TP> sw{0, 0, 0, 0, 0, 0, 0, 0};       // step being converted / stored
+        sw.load(tt, my_tiles);
+        TileWalk<TC_TP> lw = sw;                           // step whose loads are being issued
+        TileWalk<TC_TP> nw = sw;                           // tile whose point indices are being prefetched
+        const double* rowp[NP];                            // row base pointers of lw's tile (nullptr: no such row)
+        int32_t pidx_next[NP];
         auto fetch = [&](const TileWalk<TC_TP>& t, int32_t* out) {
 #pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
-                const int r = rbase + 32 * ps;
+            for (int ps = 0; ps < NP; ++ps) {
+                const int r = rsub + 64 * ps;
                 out[ps] = (r < t.pcount) ? p.perm[t.pstart + r] : -1;
             }
         };
-        fetch(w, pidx);
+        auto set_rows = [&]() {
+#pragma unroll
+            for (int ps = 0; ps < NP; ++ps)
+                rowp[ps] = pidx_next[ps] >= 0 ? p.X + (int64_t)pidx_next[ps] * p.ldx + 4 * slot : nullptr;
+        };
+        fetch(lw, pidx_next);
+        set_rows();
         nw.next_tile(tt, my_tiles);
         fetch(nw, pidx_next);
-        int stage = 0;
-        uint32_t phase = 0;
-        uint32_t xphase[2] = {0, 0};
-        for (int ti = 0; ti < my_tiles; ++ti) {
-            float xc[4] = {0.f, 0.f, 0.f, 0.f}, xr[4] = {0.f, 0.f, 0.f, 0.f};
-            const double* mean = q.mean + (size_t)w.bin * q.d_pad;
-            for (int cb = 0; cb < ncb; ++cb)
-                for (int kc = 0; kc < nch; ++kc) {
-                    const int k0 = kc * TC_KC + slot * 4;
-                    double mu[4];
+        const int64_t total_steps = (int64_t)my_tiles * ncb * nch;
+        const bool no_tail = (p.D % TC_KC) == 0;
+        double2 xa[NP][2], xb[NP][2];      // the two register buffers (4 elements per row)
+        auto issue = [&](double2 (*xv)[2]) {
+            const int k0 = lw.kc * TC_KC;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) mu[e] = mean[k0 + e];   // d_pad is a multiple of the chunk: in range
-                    double xv[4][4];
-#pragma unroll
-                    for (int ps = 0; ps < 4; ++ps) {
-                        if (pidx[ps] >= 0) {
-                            const double* src = p.X + (int64_t)pidx[ps] * p.ldx + k0;
-                            if (VEC == 2 && k0 + 4 <= p.D) {
-                                const double2 u0 = *reinterpret_cast<const double2*>(src);
-                                const double2 u1 = *reinterpret_cast<const double2*>(src + 2);
-                                xv[ps][0] = u0.x; xv[ps][1] = u0.y; xv[ps][2] = u1.x; xv[ps][3] = u1.y;
-                            } else {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) xv[ps][e] = (k0 + e < p.D) ? src[e] : 0.0;
-                            }
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) xv[ps][e] = 0.0;
-                        }
+            for (int ps = 0; ps < NP; ++ps) {
+                xv[ps][0] = xv[ps][1] = make_double2(0.0, 0.0);
+                if (rowp[ps]) {
+                    const double* src = rowp[ps] + k0;
+                    if (VEC == 2 && (no_tail || k0 + 4 * slot + 4 <= p.D)) {
+                        xv[ps][0] = *reinterpret_cast<const double2*>(src);
+                        xv[ps][1] = *reinterpret_cast<const double2*>(src + 2);
+                    } else {
+                        const int k = k0 + 4 * slot;
+                        if (k < p.D) xv[ps][0].x = src[0];
+                        if (k + 1 < p.D) xv[ps][0].y = src[1];
+                        if (k + 2 < p.D) xv[ps][1].x = src[2];
+                        if (k + 3 < p.D) xv[ps][1].y = src[3];
                     }
-                    mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    unsigned char* sa = smem_raw + (size_t)stage * stage_bytes;
-#pragma unroll
-                    for (int ps = 0; ps < 4; ++ps) {
-                        const int r = rbase + 32 * ps;
-                        float hi[4], lo[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const bool in = (k0 + e < p.D) && pidx[ps] >= 0;
-                            const float xf = in ? (float)(xv[ps][e] - mu[e]) : 0.f;
-                            hi[e] = tf32_rna(xf);
-                            lo[e] = xf - hi[e];
-                            if (cb == 0) {
-                                const float xraw = (float)xv[ps][e];
-                                xc[ps] = fmaf(xf, xf, xc[ps]);
-                                xr[ps] = fmaf(xraw, xraw, xr[ps]);
-                            }
-                        }
-                        const uint32_t off = (uint32_t)(r >> 3) * TC_SBO + (uint32_t)slot * TC_LBO + (uint32_t)(r & 7) * 16;
-                        *reinterpret_cast<float4*>(sa + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<float4*>(sa + TC_A_BYTES + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&full_bar[stage]);
-                    if (++stage == nstages) { stage = 0; phase ^= 1u; }
-                }
-            // ||x'||^2 and ||x||^2 of this tile's rows -> epilogue (slightly inflated: fp32 sums of fp32 roundings)
-            const int xb = ti & 1;
-            mbar_wait(&xn_empty[xb], xphase[xb] ^ 1u);
-            xphase[xb] ^= 1u;
-#pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
-                float a = xc[ps], b2 = xr[ps];
-#pragma unroll
-                for (int o = 1; o <= 4; o <<= 1) {
-                    a += __shfl_xor_sync(0xffffffffu, a, o);
-                    b2 += __shfl_xor_sync(0xffffffffu, b2, o);
-                }
-                if (slot == 0) {
-                    s_xn[xb][0][rbase + 32 * ps] = a * 1.0001f;
-                    s_xn[xb][1][rbase + 32 * ps] = b2 * 1.0001f;
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&xn_full[xb]);
-            w.next_tile(tt, my_tiles);
+            if (lw.advance(tt, ncb, nch, my_tiles)) {
+                set_rows();
+                nw.next_tile(tt, my_tiles);
+                fetch(nw, pidx_next);
+            }
+        };
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t xph0 = 0, xph1 = 0;
+        float xc[NP];
 #pragma unroll
-            for (int ps = 0; ps < 4; ++ps) pidx[ps] = pidx_next[ps];
-            nw.next_tile(tt, my_tiles);
-            fetch(nw, pidx_next);
+        for (int ps = 0; ps < NP; ++ps) xc[ps] = 0.f;
+        const uint32_t soff = (uint32_t)(rsub >> 3) * TC_SBO + (uint32_t)slot * TC_LBO + (uint32_t)(rsub & 7) * 16;
+        auto convert_store = [&](const double2 (*xv)[2]) {
+            const double* mp = q.mean + (size_t)sw.bin * q.d_pad + sw.kc * TC_KC + 4 * slot;   // zero padded past D
+            const double2 mu0 = *reinterpret_cast<const double2*>(mp);
+            const double2 mu1 = *reinterpret_cast<const double2*>(mp + 2);
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            unsigned char* sa = smem_raw + (size_t)stage * stage_bytes + soff;
+#pragma unroll
+            for (int ps = 0; ps < NP; ++ps) {
+                const float x0 = (float)(xv[ps][0].x - mu0.x), x1 = (float)(xv[ps][0].y - mu0.y);
+                const float x2 = (float)(xv[ps][1].x - mu1.x), x3 = (float)(xv[ps][1].y - mu1.y);
+                const float h0 = tf32_rna(x0), h1 = tf32_rna(x1), h2 = tf32_rna(x2), h3 = tf32_rna(x3);
+                xc[ps] = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, xc[ps]))));
+                *reinterpret_cast<float4*>(sa + ps * (8 * TC_SBO)) = make_float4(h0, h1, h2, h3);
+                *reinterpret_cast<float4*>(sa + ps * (8 * TC_SBO) + TC_A_BYTES) = make_float4(x0 - h0, x1 - h1, x2 - h2, x3 - h3);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[stage]);
+            if (++stage == nstages) { stage = 0; phase ^= 1u; }
+            if (sw.kc == nch - 1 && sw.cb == ncb - 1) {
+                // centred ||x'||^2 of this tile's rows -> epilogue.  (For blocks after the first the same rows
+                // are accumulated again; divide out below.)
+                const int xbuf = sw.ti & 1;
+                const uint32_t par = xbuf ? xph1 : xph0;
+                mbar_wait(&xn_empty[xbuf], par ^ 1u);
+                if (xbuf) xph1 ^= 1u; else xph0 ^= 1u;
+#pragma unroll
+                for (int ps = 0; ps < NP; ++ps) {
+                    float a = xc[ps];
+                    a += __shfl_xor_sync(0xffffffffu, a, 1);
+                    a += __shfl_xor_sync(0xffffffffu, a, 2);
+                    a += __shfl_xor_sync(0xffffffffu, a, 4);
+                    if (slot == 0) s_xn[xbuf][rsub + 64 * ps] = a * (1.0001f / (float)ncb);
+                    xc[ps] = 0.f;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&xn_full[xbuf]);
+            }
+            sw.advance(tt, ncb, nch, my_tiles);
+        };
+        if (total_steps > 0) issue(xa);
+        for (int64_t step = 0; step < total_steps; step += 2) {
+            if (step + 1 < total_steps) issue(xb);
+            convert_store(xa);
+            if (step + 1 < total_steps) {
+                if (step + 2 < total_steps) issue(xa);
+                convert_store(xb);
+            }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
+    if (warp == TC_MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(q.tmem_cols) : "memory");
     }
@@ -494,7 +525,7 @@ static TcLayout tc_layout(int32_t nbins, int D, int32_t max_k) {
     L.bprep_bytes = (size_t)nbins * L.ncb * L.nch * 2 * (L.n_pad / 8) * TC_SBO;
     L.mean_bytes = (size_t)nbins * L.d_pad * sizeof(double);
     L.csqf_bytes = (size_t)nbins * L.ncb * L.n_pad * sizeof(float);
-    L.cmax_bytes = (size_t)nbins * 2 * sizeof(float);
+    L.cmax_bytes = (size_t)nbins * 3 * sizeof(float);
     return L;
 }
 
@@ -516,7 +547,7 @@ int launch_assign_tc(const AssignParams& p_in, int32_t max_k, int64_t N, void* p
     unsigned char* bprep = cv.take<unsigned char>(L.bprep_bytes);
     double* mean = cv.take<double>((size_t)p_in.nbins * L.d_pad);
     float* csqf = cv.take<float>((size_t)p_in.nbins * L.ncb * L.n_pad);
-    float* cmaxf = cv.take<float>((size_t)p_in.nbins * 2);
+    float* cmaxf = cv.take<float>((size_t)p_in.nbins * 3);
 
     // ---- preparation (depends on the centres only) ----
     MWE_CHECK_CUDA(cudaMemsetAsync(cmaxf, 0, L.cmax_bytes, stream));
