@@ -194,6 +194,8 @@ MWE_API int mwe_hotpath_step_f64(const double* X2, int64_t ldx, int D, const dou
  * MWE_ASSIGN_TF32X3 calls fill with the scores the tensor cores produced (error-bound validation). */
 MWE_API int mwe_debug_set_tc_scores(float* buf);
 MWE_API int mwe_debug_tc_columns(int32_t max_k);
+/* tuning hook: device uint64[20] (or NULL) accumulating per-role wait cycles of the tcgen05 kernel */
+MWE_API int mwe_debug_set_tc_profile(unsigned long long* buf);
 
 /* ---- shared primitive, exported for tests ---------------------------------------------------
  * Stable LSD radix sort of (key, value) pairs on the low `key_bits` bits of the key.

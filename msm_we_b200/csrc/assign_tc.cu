@@ -24,6 +24,8 @@
 //   epilogue warps (4): tcgen05.ld their 32 TMEM lanes (one point per thread), scores = ||c'||^2 - 2 dot,
 //                       running best / runner-up, label store, near-tie list for the re-check
 // Two TMEM accumulators alternate so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <stdlib.h>
+
 #include "assign_common.cuh"
 
 namespace mwe {
@@ -33,12 +35,14 @@ static constexpr int TC_KC = 32;                           // TF32 elements per 
 static constexpr int TC_LBO = 144;                         // bytes between K-adjacent core matrices (128 + 16 pad)
 static constexpr int TC_SBO = 8 * TC_LBO;                  // bytes between 8-row groups (8 core matrices / chunk)
 static constexpr int TC_A_BYTES = (TC_TP / 8) * TC_SBO;    // one hi or lo point tile
-static constexpr int TC_LOADER_WARPS = 16;
 static constexpr int TC_EPI_WARP0 = 0;                     // epilogue warps 0..3 (warp % 4 == TMEM lane quarter)
 static constexpr int TC_MMA_WARP = 4;
 static constexpr int TC_CENTRE_WARP = 5;
-static constexpr int TC_LOAD_WARP0 = 6;
-static constexpr int TC_THREADS = (TC_LOAD_WARP0 + TC_LOADER_WARPS) * 32;
+static constexpr int TC_CONV_WARP0 = 6;                    // staging (cp.async) + fp64 -> TF32 conversion warps
+static constexpr int TC_CONV_WARPS = 8;
+static constexpr int TC_THREADS = (TC_CONV_WARP0 + TC_CONV_WARPS) * 32;
+static constexpr int TC_RAW_LD = TC_KC + 2;                // padded fp64 row (272 B): conflict-free 16-byte reads
+static constexpr int TC_RAW_BYTES = (TC_TP + 1) * TC_RAW_LD * 8;   // 128 rows + the bin-mean chunk
 static constexpr int TC_MAX_STAGES = 6;
 static constexpr size_t TC_SMEM_BUDGET = 222 * 1024;
 
@@ -50,9 +54,11 @@ struct TcParams {
     const float* cmaxf;           // [bin][3]  upper bounds: max ||c'||^2 (centred), max ||c||^2 (raw), ||mean||
     int n_pad;                    // UMMA N: centres per block, multiple of 16, <= 256
     int d_pad;                    // nch * TC_KC
-    int nstages;
+    int nstages;                  // TF32 operand ring depth
+    int nstages_raw;              // fp64 staging ring depth
     uint32_t tmem_cols;           // power of two >= 2 * n_pad
     float err_coef;               // bound of |score error| / (cmax' (2 ||x'|| + cmax'))
+    unsigned long long* dbg_prof; // tuning only: cycles spent waiting per role/barrier (16 slots) or nullptr
     float* dbg_scores;            // tests only: [N][ncb * n_pad] fp32 scores as the tensor cores produced them
 };
 
@@ -199,32 +205,48 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 // main kernel
 // ---------------------------------------------------------------------------------------------------------
 
+__device__ __forceinline__ void timed_wait(uint64_t* bar, uint32_t parity, long long& acc, bool on) {
+    if (on) {
+        const long long t0 = clock64();
+        mbar_wait(bar, parity);
+        acc += clock64() - t0;
+    } else {
+        mbar_wait(bar, parity);
+    }
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams q) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const AssignParams& p = q.a;
-    __shared__ uint64_t full_bar[TC_MAX_STAGES];
-    __shared__ uint64_t empty_bar[TC_MAX_STAGES];
+    __shared__ uint64_t raw_full[TC_MAX_STAGES], raw_empty[TC_MAX_STAGES];   // fp64 staging ring (cp.async)
+    __shared__ uint64_t tf_full[TC_MAX_STAGES], tf_empty[TC_MAX_STAGES];     // TF32 operand ring (UMMA)
     __shared__ uint64_t tmem_full[2], tmem_empty[2], xn_full[2], xn_empty[2];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float s_xn[2][TC_TP];      // [buffer][row]: centred ||x'||^2 (upper bound)
+    __shared__ float s_xn[2][TC_TP];                     // [buffer][row]: centred ||x'||^2 (upper bound)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int nstages = q.nstages;
+    const int n_raw = q.nstages_raw, n_tf = q.nstages;
     const int ng = q.n_pad / 8;
     const uint32_t b_bytes = (uint32_t)(2 * ng * TC_SBO);
-    const uint32_t stage_bytes = 2u * TC_A_BYTES + b_bytes;
+    const uint32_t tf_bytes = 2u * TC_A_BYTES + b_bytes;
+    unsigned char* tf_base = smem_raw;
+    unsigned char* raw_base = smem_raw + (size_t)n_tf * tf_bytes;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < nstages; ++s) {
-            mbar_init(&full_bar[s], TC_LOADER_WARPS + 1);   // 8 loader warps + the centre warp's expect_tx arrive
-            mbar_init(&empty_bar[s], 1);                    // tcgen05.commit
+        for (int s = 0; s < n_raw; ++s) {
+            mbar_init(&raw_full[s], TC_CONV_WARPS * 32);      // every staging thread: cp.async ... arrive.noinc
+            mbar_init(&raw_empty[s], TC_CONV_WARPS);          // one lane per converter warp
+        }
+        for (int s = 0; s < n_tf; ++s) {
+            mbar_init(&tf_full[s], TC_CONV_WARPS + 1);        // converter warps + the centre warp's expect_tx arrive
+            mbar_init(&tf_empty[s], 1);                       // tcgen05.commit
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);    // tcgen05.commit
             mbar_init(&tmem_empty[i], 4);   // one lane per epilogue warp
-            mbar_init(&xn_full[i], TC_LOADER_WARPS);
+            mbar_init(&xn_full[i], TC_CONV_WARPS);
             mbar_init(&xn_empty[i], 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -232,7 +254,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
     // bin tables -> shared memory
     TileTables tt{p.tile_prefix, p.bin_start, p.bin_offset, p.nbins};
     if (p.nbins <= AS_TABLE_BINS) {
-        int32_t* s_tp = reinterpret_cast<int32_t*>(smem_raw + (size_t)nstages * stage_bytes);
+        int32_t* s_tp = reinterpret_cast<int32_t*>(raw_base + (size_t)n_raw * TC_RAW_BYTES);
         int32_t* s_bs = s_tp + (p.nbins + 1);
         int64_t* s_bo = reinterpret_cast<int64_t*>(s_bs + (p.nbins + 1));
         for (int b = threadIdx.x; b <= p.nbins; b += TC_THREADS) {
@@ -257,6 +279,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
     const int32_t n_tiles = tt.tile_prefix[p.nbins];
     const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int ncb = p.ncb, nch = p.nch;
+    const bool prof = q.dbg_prof != nullptr;
+    long long w0 = 0, w1 = 0, w2 = 0;   // cycles waited on up to three barriers of this role
+    const long long t_begin = clock64();
 
     if (warp == TC_MMA_WARP) {
         // =========================== MMA issuer (one lane) ===========================
@@ -264,19 +289,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(q.n_pad >> 3) << 17) | ((uint32_t)(TC_TP >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
-            uint32_t tphase[2] = {0, 0};
+            uint32_t tph0 = 0, tph1 = 0;
             int unit = 0;
             for (int ti = 0; ti < my_tiles; ++ti)
                 for (int cb = 0; cb < ncb; ++cb, ++unit) {
                     const int ab = unit & 1;
-                    mbar_wait(&tmem_empty[ab], tphase[ab] ^ 1u);   // epilogue has drained this accumulator
-                    tphase[ab] ^= 1u;
+                    timed_wait(&tmem_empty[ab], (ab ? tph1 : tph0) ^ 1u, w0, prof);   // epilogue has drained this accumulator
+                    if (ab) tph1 ^= 1u; else tph0 ^= 1u;
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(ab * q.n_pad);
                     for (int kc = 0; kc < nch; ++kc) {
-                        mbar_wait(&full_bar[stage], phase);
+                        timed_wait(&tf_full[stage], phase, w1, prof);
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(smem_raw + (size_t)stage * stage_bytes);
+                        const uint32_t sa = smem_u32(tf_base + (size_t)stage * tf_bytes);
                         const uint32_t a_hi = sa, a_lo = sa + TC_A_BYTES;
                         const uint32_t b_hi = sa + 2 * TC_A_BYTES, b_lo = b_hi + (uint32_t)(ng * TC_SBO);
 #pragma unroll
@@ -288,9 +313,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
                             umma_tf32(d_tmem, dah, dbl, idesc, 1);              // hi.lo
                             umma_tf32(d_tmem, dal, dbh, idesc, 1);              // lo.hi
                         }
-                        umma_commit(&empty_bar[stage]);   // stage reusable once these MMAs have read it
+                        umma_commit(&tf_empty[stage]);   // stage reusable once these MMAs have read it
                         if (kc == nch - 1) umma_commit(&tmem_full[ab]);
-                        if (++stage == nstages) { stage = 0; phase ^= 1u; }
+                        if (++stage == n_tf) { stage = 0; phase ^= 1u; }
                     }
                 }
         }
@@ -304,12 +329,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
             for (int ti = 0; ti < my_tiles; ++ti) {
                 for (int cb = 0; cb < ncb; ++cb)
                     for (int kc = 0; kc < nch; ++kc) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1u);
-                        unsigned char* dst = smem_raw + (size_t)stage * stage_bytes + 2 * TC_A_BYTES;
+                        timed_wait(&tf_empty[stage], phase ^ 1u, w0, prof);
+                        unsigned char* dst = tf_base + (size_t)stage * tf_bytes + 2 * TC_A_BYTES;
                         const unsigned char* src = q.bprep + ((size_t)(w.bin * ncb + cb) * nch + kc) * b_bytes;
-                        mbar_expect_tx(&full_bar[stage], b_bytes);
-                        bulk_copy_g2s(dst, src, b_bytes, &full_bar[stage]);
-                        if (++stage == nstages) { stage = 0; phase ^= 1u; }
+                        mbar_expect_tx(&tf_full[stage], b_bytes);
+                        bulk_copy_g2s(dst, src, b_bytes, &tf_full[stage]);
+                        if (++stage == n_tf) { stage = 0; phase ^= 1u; }
                     }
                 w.next_tile(tt, my_tiles);
             }
@@ -321,8 +346,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
         const float finf = __int_as_float(0x7f800000);
         TileWalk<TC_TP> w{0, 0, 0, 0, 0, 0, 0, 0};
         w.load(tt, my_tiles);
-        uint32_t tphase[2] = {0, 0};
-        uint32_t xphase[2] = {0, 0};
+        uint32_t tph0 = 0, tph1 = 0, xph0 = 0, xph1 = 0;
         int unit = 0;
         const int ncols = ncb * q.n_pad;
         for (int ti = 0; ti < my_tiles; ++ti) {
@@ -332,8 +356,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
             int32_t bi = 0;
             for (int cb = 0; cb < ncb; ++cb, ++unit) {
                 const int ab = unit & 1;
-                mbar_wait(&tmem_full[ab], tphase[ab]);
-                tphase[ab] ^= 1u;
+                timed_wait(&tmem_full[ab], ab ? tph1 : tph0, w0, prof);
+                if (ab) tph1 ^= 1u; else tph0 ^= 1u;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(ab * q.n_pad);
                 for (int c0 = 0; c0 < q.n_pad; c0 += 16) {
@@ -355,10 +379,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[ab]);
             }
-            // norms of this tile's rows from the loader warps
+            // norms of this tile's rows from the converter warps
             const int xb = ti & 1;
-            mbar_wait(&xn_full[xb], xphase[xb]);
-            xphase[xb] ^= 1u;
+            timed_wait(&xn_full[xb], xb ? xph1 : xph0, w1, prof);
+            if (xb) xph1 ^= 1u; else xph0 ^= 1u;
             const float xn2c = s_xn[xb][row];
             __syncwarp();
             if (lane == 0) mbar_arrive(&xn_empty[xb]);
@@ -376,99 +400,117 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
             }
             w.next_tile(tt, my_tiles);
         }
-    } else if (warp >= TC_LOAD_WARP0) {
-        // =========================== loaders: HBM fp64 rows -> TF32 hi/lo tiles ===========================
-        // 8 lanes cover one 256-byte row chunk (4 elements = 2 x LDG.128 per lane), 16 warps cover 64 rows per
-        // pass, a thread owns rows rsub and rsub + 64.  The loads of step s+1 are issued before step s is
-        // converted (two register buffers): every loader keeps two chunks of HBM requests in flight.
-        // No masks in the math: a row past the tile end is read as zeros (garbage rows of the product are
-        // never used), the k-tail is read as zeros and the bin mean is zero-padded, so x' = 0 there.
-        const int lt = threadIdx.x - TC_LOAD_WARP0 * 32;   // 0..511
-        const int slot = lt & 7;                           // 4-element k group inside the chunk
-        const int rsub = lt >> 3;                          // 0..63
-        constexpr int NP = TC_TP / 64;                     // rows per thread (2)
-        TileWalk<TC_TP> sw{0, 0, 0, 0, 0, 0, 0, 0};       // step being converted / stored
-        sw.load(tt, my_tiles);
-        TileWalk<TC_TP> lw = sw;                           // step whose loads are being issued
-        TileWalk<TC_TP> nw = sw;                           // tile whose point indices are being prefetched
-        const double* rowp[NP];                            // row base pointers of lw's tile (nullptr: no such row)
-        int32_t pidx_next[NP];
-        auto fetch = [&](const TileWalk<TC_TP>& t, int32_t* out) {
+    } else if (warp >= TC_CONV_WARP0) {
+        // =========================== staging + conversion warps ===========================
+        // Each of the 8 warps (a) issues the cp.async (LDGSTS, zero-filling) copies of 16 point rows of the
+        // chunk n_raw-1 steps ahead into the fp64 staging ring -- fire-and-forget, completion lands on raw_full;
+        // spreading the issue over 8 warps matters: one warp sustains only ~16 copies in flight -- and
+        // (b) converts the current chunk: fp64 (shared) -> centred TF32 hi/lo tiles in the UMMA layout.
+        // Conversion mapping: 8 lanes cover one row chunk (4 elements each), 8 warps cover 32 rows per pass, a
+        // thread owns rows rsub + 32 * pass.  Rows past the tile end hold stale data: garbage rows of the
+        // product are never read.
+        const int cwp = warp - TC_CONV_WARP0;              // 0..7
+        const int lt = threadIdx.x - TC_CONV_WARP0 * 32;   // 0..255
+        const int slot = lt & 7;
+        const int rsub = lt >> 3;                          // 0..31
+        constexpr int NP = TC_TP / 32;
+        // copy geometry: SEGS lanes per row chunk, RPI rows per warp instruction, XQ instructions for 16 rows
+        constexpr int SEGS = TC_KC / VEC;
+        constexpr int RPI = 32 / SEGS;
+        constexpr int XQ = 16 / RPI;
+        const int seg = lane % SEGS, crs = lane / SEGS;
+        const int kcol0 = seg * VEC;
+        TileWalk<TC_TP> cw{0, 0, 0, 0, 0, 0, 0, 0};       // step being converted
+        cw.load(tt, my_tiles);
+        TileWalk<TC_TP> iw = cw;                           // step whose copies are being issued
+        TileWalk<TC_TP> nw = cw;                           // tile whose point indices are being prefetched
+        const double* xsrc[XQ];
+        int32_t pidx_next[XQ];
+        auto fetch = [&](const TileWalk<TC_TP>& t) {
 #pragma unroll
-            for (int ps = 0; ps < NP; ++ps) {
-                const int r = rsub + 64 * ps;
-                out[ps] = (r < t.pcount) ? p.perm[t.pstart + r] : -1;
+            for (int qq = 0; qq < XQ; ++qq) {
+                const int r = cwp * 16 + qq * RPI + crs;
+                pidx_next[qq] = (r < t.pcount) ? p.perm[t.pstart + r] : -1;
             }
         };
-        auto set_rows = [&]() {
+        auto set_xsrc = [&]() {
 #pragma unroll
-            for (int ps = 0; ps < NP; ++ps)
-                rowp[ps] = pidx_next[ps] >= 0 ? p.X + (int64_t)pidx_next[ps] * p.ldx + 4 * slot : nullptr;
+            for (int qq = 0; qq < XQ; ++qq)
+                xsrc[qq] = (pidx_next[qq] >= 0) ? p.X + (int64_t)pidx_next[qq] * p.ldx + kcol0 : nullptr;
         };
-        fetch(lw, pidx_next);
-        set_rows();
+        fetch(iw);
+        set_xsrc();
         nw.next_tile(tt, my_tiles);
-        fetch(nw, pidx_next);
+        fetch(nw);
         const int64_t total_steps = (int64_t)my_tiles * ncb * nch;
-        const bool no_tail = (p.D % TC_KC) == 0;
-        double2 xa[NP][2], xb[NP][2];      // the two register buffers (4 elements per row)
-        auto issue = [&](double2 (*xv)[2]) {
-            const int k0 = lw.kc * TC_KC;
+        int is = 0;
+        uint32_t iphase = 0;
+        int64_t issued = 0;
+        auto issue_one = [&]() {
+            timed_wait(&raw_empty[is], iphase ^ 1u, w2, prof);
+            double* st = reinterpret_cast<double*>(raw_base + (size_t)is * TC_RAW_BYTES);
+            const int k0 = iw.kc * TC_KC;
+            int vbytes = (p.D - k0 - kcol0) * 8;
+            vbytes = vbytes < 0 ? 0 : (vbytes > VEC * 8 ? VEC * 8 : vbytes);
+            double* dst = st + (cwp * 16 + crs) * TC_RAW_LD + kcol0;
 #pragma unroll
-            for (int ps = 0; ps < NP; ++ps) {
-                xv[ps][0] = xv[ps][1] = make_double2(0.0, 0.0);
-                if (rowp[ps]) {
-                    const double* src = rowp[ps] + k0;
-                    if (VEC == 2 && (no_tail || k0 + 4 * slot + 4 <= p.D)) {
-                        xv[ps][0] = *reinterpret_cast<const double2*>(src);
-                        xv[ps][1] = *reinterpret_cast<const double2*>(src + 2);
-                    } else {
-                        const int k = k0 + 4 * slot;
-                        if (k < p.D) xv[ps][0].x = src[0];
-                        if (k + 1 < p.D) xv[ps][0].y = src[1];
-                        if (k + 2 < p.D) xv[ps][1].x = src[2];
-                        if (k + 3 < p.D) xv[ps][1].y = src[3];
-                    }
-                }
-            }
-            if (lw.advance(tt, ncb, nch, my_tiles)) {
-                set_rows();
+            for (int qq = 0; qq < XQ; ++qq)   // (a zero-size copy still gets an in-range source address)
+                if (xsrc[qq]) cp_async_zfill<VEC>(dst + qq * RPI * TC_RAW_LD, vbytes ? xsrc[qq] + k0 : p.X, vbytes);
+            if (cwp == 0 && lane < 16)   // the bin-mean chunk rides along (zero padded past D: always 16 x 16 B)
+                cp_async_zfill<2>(st + TC_TP * TC_RAW_LD + 2 * lane, q.mean + (size_t)iw.bin * q.d_pad + k0 + 2 * lane, 16);
+            cp_async_arrive_noinc(&raw_full[is]);
+            if (++is == n_raw) { is = 0; iphase ^= 1u; }
+            ++issued;
+            if (iw.advance(tt, ncb, nch, my_tiles)) {
+                set_xsrc();
                 nw.next_tile(tt, my_tiles);
-                fetch(nw, pidx_next);
+                fetch(nw);
             }
         };
-        int stage = 0;
-        uint32_t phase = 0;
-        uint32_t xph0 = 0, xph1 = 0;
+        while (issued < total_steps && issued < n_raw - 1) issue_one();
+
+        int rs = 0, ts = 0;
+        uint32_t rphase = 0, tphase = 0, xph0 = 0, xph1 = 0;
+        const uint32_t soff = (uint32_t)(rsub >> 3) * TC_SBO + (uint32_t)slot * TC_LBO + (uint32_t)(rsub & 7) * 16;
         float xc[NP];
 #pragma unroll
         for (int ps = 0; ps < NP; ++ps) xc[ps] = 0.f;
-        const uint32_t soff = (uint32_t)(rsub >> 3) * TC_SBO + (uint32_t)slot * TC_LBO + (uint32_t)(rsub & 7) * 16;
-        auto convert_store = [&](const double2 (*xv)[2]) {
-            const double* mp = q.mean + (size_t)sw.bin * q.d_pad + sw.kc * TC_KC + 4 * slot;   // zero padded past D
-            const double2 mu0 = *reinterpret_cast<const double2*>(mp);
-            const double2 mu1 = *reinterpret_cast<const double2*>(mp + 2);
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
-            unsigned char* sa = smem_raw + (size_t)stage * stage_bytes + soff;
+        for (int64_t step = 0; step < total_steps; ++step) {
+            if (issued < total_steps) issue_one();
+            timed_wait(&raw_full[rs], rphase, w0, prof);
+            const double* st = reinterpret_cast<const double*>(raw_base + (size_t)rs * TC_RAW_BYTES);
+            const double2 mu0 = *reinterpret_cast<const double2*>(st + TC_TP * TC_RAW_LD + 4 * slot);
+            const double2 mu1 = *reinterpret_cast<const double2*>(st + TC_TP * TC_RAW_LD + 4 * slot + 2);
+            double2 xv[NP][2];
+#pragma unroll
+            for (int ps = 0; ps < NP; ++ps) {
+                const double* src = st + (rsub + 32 * ps) * TC_RAW_LD + 4 * slot;
+                xv[ps][0] = *reinterpret_cast<const double2*>(src);
+                xv[ps][1] = *reinterpret_cast<const double2*>(src + 2);
+            }
+            timed_wait(&tf_empty[ts], tphase ^ 1u, w1, prof);
+            unsigned char* sa = tf_base + (size_t)ts * tf_bytes + soff;
 #pragma unroll
             for (int ps = 0; ps < NP; ++ps) {
                 const float x0 = (float)(xv[ps][0].x - mu0.x), x1 = (float)(xv[ps][0].y - mu0.y);
                 const float x2 = (float)(xv[ps][1].x - mu1.x), x3 = (float)(xv[ps][1].y - mu1.y);
                 const float h0 = tf32_rna(x0), h1 = tf32_rna(x1), h2 = tf32_rna(x2), h3 = tf32_rna(x3);
-                xc[ps] = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, xc[ps]))));
-                *reinterpret_cast<float4*>(sa + ps * (8 * TC_SBO)) = make_float4(h0, h1, h2, h3);
-                *reinterpret_cast<float4*>(sa + ps * (8 * TC_SBO) + TC_A_BYTES) = make_float4(x0 - h0, x1 - h1, x2 - h2, x3 - h3);
+                if (cw.cb == 0) xc[ps] = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, xc[ps]))));
+                *reinterpret_cast<float4*>(sa + ps * (4 * TC_SBO)) = make_float4(h0, h1, h2, h3);
+                *reinterpret_cast<float4*>(sa + ps * (4 * TC_SBO) + TC_A_BYTES) = make_float4(x0 - h0, x1 - h1, x2 - h2, x3 - h3);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
             __syncwarp();
-            if (lane == 0) mbar_arrive(&full_bar[stage]);
-            if (++stage == nstages) { stage = 0; phase ^= 1u; }
-            if (sw.kc == nch - 1 && sw.cb == ncb - 1) {
-                // centred ||x'||^2 of this tile's rows -> epilogue.  (For blocks after the first the same rows
-                // are accumulated again; divide out below.)
-                const int xbuf = sw.ti & 1;
-                const uint32_t par = xbuf ? xph1 : xph0;
-                mbar_wait(&xn_empty[xbuf], par ^ 1u);
+            if (lane == 0) {
+                mbar_arrive(&tf_full[ts]);
+                mbar_arrive(&raw_empty[rs]);
+            }
+            if (++rs == n_raw) { rs = 0; rphase ^= 1u; }
+            if (++ts == n_tf) { ts = 0; tphase ^= 1u; }
+            if (cw.kc == nch - 1 && cw.cb == ncb - 1) {
+                // centred ||x'||^2 of this tile's rows -> epilogue (fp32 sums of fp32 roundings, inflated a little)
+                const int xbuf = cw.ti & 1;
+                mbar_wait(&xn_empty[xbuf], (xbuf ? xph1 : xph0) ^ 1u);
                 if (xbuf) xph1 ^= 1u; else xph0 ^= 1u;
 #pragma unroll
                 for (int ps = 0; ps < NP; ++ps) {
@@ -476,25 +518,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
                     a += __shfl_xor_sync(0xffffffffu, a, 1);
                     a += __shfl_xor_sync(0xffffffffu, a, 2);
                     a += __shfl_xor_sync(0xffffffffu, a, 4);
-                    if (slot == 0) s_xn[xbuf][rsub + 64 * ps] = a * (1.0001f / (float)ncb);
+                    if (slot == 0) s_xn[xbuf][rsub + 32 * ps] = a * 1.0001f;
                     xc[ps] = 0.f;
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&xn_full[xbuf]);
             }
-            sw.advance(tt, ncb, nch, my_tiles);
-        };
-        if (total_steps > 0) issue(xa);
-        for (int64_t step = 0; step < total_steps; step += 2) {
-            if (step + 1 < total_steps) issue(xb);
-            convert_store(xa);
-            if (step + 1 < total_steps) {
-                if (step + 2 < total_steps) issue(xa);
-                convert_store(xb);
-            }
+            cw.advance(tt, ncb, nch, my_tiles);
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
     }
 
+    if (prof && lane == 0 && (warp == TC_MMA_WARP || warp == TC_CENTRE_WARP || warp == TC_EPI_WARP0 || warp == TC_CONV_WARP0)) {
+        // slots: role * 4 + {total cycles, wait 0, wait 1, wait 2}; roles: 0 MMA, 1 centre, 2 epilogue, 3 raw, 4 converter
+        const int role = warp == TC_MMA_WARP ? 0 : warp == TC_CENTRE_WARP ? 1 : warp == TC_EPI_WARP0 ? 2 : 4;
+        atomicAdd(q.dbg_prof + role * 4 + 0, (unsigned long long)(clock64() - t_begin));
+        atomicAdd(q.dbg_prof + role * 4 + 1, (unsigned long long)w0);
+        atomicAdd(q.dbg_prof + role * 4 + 2, (unsigned long long)w1);
+        atomicAdd(q.dbg_prof + role * 4 + 3, (unsigned long long)w2);
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == TC_MMA_WARP) {
@@ -535,6 +577,7 @@ size_t assign_tc_prep_bytes(int32_t nbins, int D, int32_t max_k) {
            align_up(L.cmax_bytes, 256) + 1024;
 }
 
+static unsigned long long* g_dbg_prof = nullptr;
 static float* g_dbg_scores = nullptr;   // set through mwe_debug_set_tc_scores (tests only)
 
 int launch_assign_tc(const AssignParams& p_in, int32_t max_k, int64_t N, void* prep, size_t prep_bytes, cudaStream_t stream) {
@@ -583,16 +626,22 @@ int launch_assign_tc(const AssignParams& p_in, int32_t max_k, int64_t N, void* p
     //   fp32 score arithmetic (csq rounding, the fma)                            -> 2^-21
     q.err_coef = (float)(1.0 / 1048576.0 + (3.0 * ((p_in.D + 7) / 8) + 10.0) / 4194304.0);
     q.dbg_scores = g_dbg_scores;
-    const size_t stage_bytes = 2 * (size_t)TC_A_BYTES + (size_t)2 * (L.n_pad / 8) * TC_SBO;
+    q.dbg_prof = g_dbg_prof;
+    const size_t tf_bytes = 2 * (size_t)TC_A_BYTES + (size_t)2 * (L.n_pad / 8) * TC_SBO;
     const size_t table_bytes = (p_in.nbins <= AS_TABLE_BINS) ? (size_t)(p_in.nbins + 2) * 16 + 16 : 0;
-    int nstages = (int)((TC_SMEM_BUDGET - table_bytes) / stage_bytes);
-    if (nstages > TC_MAX_STAGES) nstages = TC_MAX_STAGES;
-    if (nstages < 2) {
-        set_last_error("assign(tc): a pipeline stage does not fit in shared memory");
+    // two TF32 stages when they fit next to two fp64 stages, the rest of the budget goes to the fp64 ring
+    // (that ring is what keeps HBM requests in flight)
+    int n_tf = (2 * tf_bytes + 2 * (size_t)TC_RAW_BYTES + table_bytes <= TC_SMEM_BUDGET) ? 2 : 1;
+    if (const char* e = getenv("MWE_TC_TF_STAGES")) n_tf = atoi(e);
+    if ((size_t)n_tf * tf_bytes + 2 * (size_t)TC_RAW_BYTES + table_bytes > TC_SMEM_BUDGET) {
+        set_last_error("assign(tc): pipeline stages do not fit in shared memory");
         return MWE_E_UNSUPPORTED;
     }
-    q.nstages = nstages;
-    const size_t smem = stage_bytes * nstages + table_bytes;
+    int n_raw = (int)((TC_SMEM_BUDGET - table_bytes - (size_t)n_tf * tf_bytes) / TC_RAW_BYTES);
+    if (n_raw > TC_MAX_STAGES) n_raw = TC_MAX_STAGES;
+    q.nstages = n_tf;
+    q.nstages_raw = n_raw;
+    const size_t smem = tf_bytes * n_tf + (size_t)TC_RAW_BYTES * n_raw + table_bytes;
     const bool vec2 = (p_in.D % 2 == 0) && (p_in.ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(p_in.X) & 15) == 0);
     const int64_t max_tiles = (N + TC_TP - 1) / TC_TP + p_in.nbins;
     int64_t grid = sm_count();
@@ -627,6 +676,10 @@ int launch_assign_tc(const AssignParams& p_in, int32_t max_k, int64_t N, void* p
 // tests only: device buffer [N][ncb * n_pad] that receives the fp32 scores of the next tcgen05 assignment calls
 extern "C" int mwe_debug_set_tc_scores(float* buf) {
     mwe::g_dbg_scores = buf;
+    return MWE_OK;
+}
+extern "C" int mwe_debug_set_tc_profile(unsigned long long* buf) {
+    mwe::g_dbg_prof = buf;
     return MWE_OK;
 }
 extern "C" int mwe_debug_tc_columns(int32_t max_k) {
