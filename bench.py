@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample-iters", type=int, default=0, help="iterations of the workload timed on the CPU (0 = auto)")
-    ap.add_argument("--precision-path", default="tf32x3", choices=["fp64", "tf32x3"],
+    ap.add_argument("--precision-path", default="auto", choices=["auto", "fp64", "tf32x3"],
                     help="K1 evaluation: fp64 DMMA, or tcgen05 split-TF32 candidates + fp64 re-check (same labels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -302,7 +302,9 @@ def main():
     labels = torch.empty(2 * N, dtype=torch.int64, device=dev)
     l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     n_iters_total = cfg.n_iters * world
-    path = _lib.ASSIGN_TF32X3 if args.precision_path == "tf32x3" else _lib.ASSIGN_FP64
+    path = {"auto": _lib.ASSIGN_AUTO, "tf32x3": _lib.ASSIGN_TF32X3, "fp64": _lib.ASSIGN_FP64}[args.precision_path]
+    if path == _lib.ASSIGN_AUTO:   # same rule as the library (csrc/assign.cu, resolve_assign_path)
+        path = _lib.ASSIGN_TF32X3 if cfg.k_per_bin * cfg.dim >= 2048 else _lib.ASSIGN_FP64
 
     def step(ev=None):
         if ev is not None:

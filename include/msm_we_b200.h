@@ -56,6 +56,7 @@ extern "C" {
 /* precision paths of the assignment kernel */
 #define MWE_ASSIGN_FP64 0      /* fp64 tensor (DMMA) distances, the parity path                    */
 #define MWE_ASSIGN_TF32X3 1    /* tcgen05 split-TF32 candidate pass + fp64 re-check of near-ties   */
+#define MWE_ASSIGN_AUTO 2      /* the faster of the two for the shape (labels are identical)        */
 
 MWE_API int mwe_abi_version(void);
 MWE_API const char* mwe_last_error(void);

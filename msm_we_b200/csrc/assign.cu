@@ -587,11 +587,19 @@ static int dispatch_nt(int nt, const AssignParams& p, int64_t max_tiles, cudaStr
     }
 }
 
+// MWE_ASSIGN_AUTO: the fp64 DMMA kernel needs 2 K D fp64 FLOPs per point (37 TFLOP/s measured), the tcgen05
+// kernel streams at ~2.9 TB/s whatever K is (measured, tools/assign_bench.py): cross-over near K*D ~ 2000.
+int resolve_assign_path(int precision_path, int D, int32_t max_k) {
+    if (precision_path != MWE_ASSIGN_AUTO) return precision_path;
+    return ((int64_t)max_k * D >= 2048) ? MWE_ASSIGN_TF32X3 : MWE_ASSIGN_FP64;
+}
+
 }  // namespace mwe
 
 extern "C" size_t mwe_assign_workspace_bytes(int64_t N, int32_t nbins) { return mwe::assign_ws_bytes(N, nbins); }
 
 extern "C" size_t mwe_assign_workspace_bytes_ex(int64_t N, int32_t nbins, int D, int32_t max_k, int precision_path) {
+    precision_path = mwe::resolve_assign_path(precision_path, D, max_k);
     size_t b = mwe::assign_ws_bytes(N, nbins);
     if (precision_path == MWE_ASSIGN_TF32X3) b += mwe::assign_tc_prep_bytes(nbins, D, max_k) + 256;
     return b;
@@ -617,6 +625,7 @@ extern "C" int mwe_assign_stratified_f64(const double* X, int64_t N, int D, int6
     MWE_REQUIRE(D >= 1 && ldx >= D, "assign: bad D / ldx");
     MWE_REQUIRE(nbins >= 1 && max_k >= 1, "assign: bad nbins / max_k");
     MWE_REQUIRE(bin && centers && csq && bin_offset && label_out && err_count, "assign: null pointer");
+    precision_path = mwe::resolve_assign_path(precision_path, D, max_k);
     if (precision_path != MWE_ASSIGN_FP64 && precision_path != MWE_ASSIGN_TF32X3) {
         set_last_error("assign: unknown precision path %d", precision_path);
         return MWE_E_UNSUPPORTED;

@@ -125,6 +125,7 @@ struct TileWalk {
 
 
 // tcgen05 path (assign_tc.cu).  prep_bytes: workspace for the pre-split centres.
+int resolve_assign_path(int precision_path, int D, int32_t max_k);
 size_t assign_tc_prep_bytes(int32_t nbins, int D, int32_t max_k);
 int launch_assign_tc(const AssignParams& p, int32_t max_k, int64_t N, void* prep, size_t prep_bytes, cudaStream_t stream);
 

@@ -79,10 +79,11 @@ __global__ void __launch_bounds__(128)
     mean[(size_t)b * d_pad + k] = (c1 > c0 && k < D) ? s / (double)(c1 - c0) : 0.0;
 }
 
+// round an fp32 value to TF32 (10 explicit mantissa bits), nearest with ties away from zero: add half a TF32
+// ulp to the magnitude bits and clear the 13 low bits.  Two integer ops (cvt.rna.tf32.f32 is emulated with
+// a longer sequence on sm_100a); the carry into the exponent is the correct rounding up to the next binade.
 __device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 // one thread per (bin, centre block, row of the block, 4-element k group)
@@ -402,22 +403,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
         }
     } else if (warp >= TC_CONV_WARP0) {
         // =========================== staging + conversion warps ===========================
-        // Each of the 8 warps (a) issues the cp.async (LDGSTS, zero-filling) copies of 16 point rows of the
+        // Each of the 16 warps (a) issues the cp.async (LDGSTS, zero-filling) copies of 8 point rows of the
         // chunk n_raw-1 steps ahead into the fp64 staging ring -- fire-and-forget, completion lands on raw_full;
-        // spreading the issue over 8 warps matters: one warp sustains only ~16 copies in flight -- and
+        // spreading the issue over all warps matters: one warp sustains only ~16 copies in flight -- and
         // (b) converts the current chunk: fp64 (shared) -> centred TF32 hi/lo tiles in the UMMA layout.
-        // Conversion mapping: 8 lanes cover one row chunk (4 elements each), 8 warps cover 32 rows per pass, a
-        // thread owns rows rsub + 32 * pass.  Rows past the tile end hold stale data: garbage rows of the
+        // Conversion mapping: 8 lanes cover one row chunk (4 elements each), 16 warps cover 64 rows per pass, a
+        // thread owns rows rsub and rsub + 64.  Rows past the tile end hold stale data: garbage rows of the
         // product are never read.
-        const int cwp = warp - TC_CONV_WARP0;              // 0..7
-        const int lt = threadIdx.x - TC_CONV_WARP0 * 32;   // 0..255
+        const int cwp = warp - TC_CONV_WARP0;              // 0..15
+        const int lt = threadIdx.x - TC_CONV_WARP0 * 32;   // 0..511
         const int slot = lt & 7;
-        const int rsub = lt >> 3;                          // 0..31
-        constexpr int NP = TC_TP / 32;
+        const int rsub = lt >> 3;                          // 0..63
+        constexpr int RPP = TC_CONV_WARPS * 4;             // rows per conversion pass (64)
+        constexpr int NP = TC_TP / RPP;
+        constexpr int CR = TC_TP / TC_CONV_WARPS;          // rows each warp copies (8)
         // copy geometry: SEGS lanes per row chunk, RPI rows per warp instruction, XQ instructions for 16 rows
         constexpr int SEGS = TC_KC / VEC;
         constexpr int RPI = 32 / SEGS;
-        constexpr int XQ = 16 / RPI;
+        constexpr int XQ = CR / RPI;
         const int seg = lane % SEGS, crs = lane / SEGS;
         const int kcol0 = seg * VEC;
         TileWalk<TC_TP> cw{0, 0, 0, 0, 0, 0, 0, 0};       // step being converted
@@ -429,7 +432,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
         auto fetch = [&](const TileWalk<TC_TP>& t) {
 #pragma unroll
             for (int qq = 0; qq < XQ; ++qq) {
-                const int r = cwp * 16 + qq * RPI + crs;
+                const int r = cwp * CR + qq * RPI + crs;
                 pidx_next[qq] = (r < t.pcount) ? p.perm[t.pstart + r] : -1;
             }
         };
@@ -452,7 +455,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
             const int k0 = iw.kc * TC_KC;
             int vbytes = (p.D - k0 - kcol0) * 8;
             vbytes = vbytes < 0 ? 0 : (vbytes > VEC * 8 ? VEC * 8 : vbytes);
-            double* dst = st + (cwp * 16 + crs) * TC_RAW_LD + kcol0;
+            double* dst = st + (cwp * CR + crs) * TC_RAW_LD + kcol0;
 #pragma unroll
             for (int qq = 0; qq < XQ; ++qq)   // (a zero-size copy still gets an in-range source address)
                 if (xsrc[qq]) cp_async_zfill<VEC>(dst + qq * RPI * TC_RAW_LD, vbytes ? xsrc[qq] + k0 : p.X, vbytes);
@@ -484,7 +487,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
             double2 xv[NP][2];
 #pragma unroll
             for (int ps = 0; ps < NP; ++ps) {
-                const double* src = st + (rsub + 32 * ps) * TC_RAW_LD + 4 * slot;
+                const double* src = st + (rsub + RPP * ps) * TC_RAW_LD + 4 * slot;
                 xv[ps][0] = *reinterpret_cast<const double2*>(src);
                 xv[ps][1] = *reinterpret_cast<const double2*>(src + 2);
             }
@@ -496,8 +499,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
                 const float x2 = (float)(xv[ps][1].x - mu1.x), x3 = (float)(xv[ps][1].y - mu1.y);
                 const float h0 = tf32_rna(x0), h1 = tf32_rna(x1), h2 = tf32_rna(x2), h3 = tf32_rna(x3);
                 if (cw.cb == 0) xc[ps] = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, xc[ps]))));
-                *reinterpret_cast<float4*>(sa + ps * (4 * TC_SBO)) = make_float4(h0, h1, h2, h3);
-                *reinterpret_cast<float4*>(sa + ps * (4 * TC_SBO) + TC_A_BYTES) = make_float4(x0 - h0, x1 - h1, x2 - h2, x3 - h3);
+                *reinterpret_cast<float4*>(sa + ps * ((RPP / 8) * TC_SBO)) = make_float4(h0, h1, h2, h3);
+                *reinterpret_cast<float4*>(sa + ps * ((RPP / 8) * TC_SBO) + TC_A_BYTES) = make_float4(x0 - h0, x1 - h1, x2 - h2, x3 - h3);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
             __syncwarp();
@@ -518,7 +521,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
                     a += __shfl_xor_sync(0xffffffffu, a, 1);
                     a += __shfl_xor_sync(0xffffffffu, a, 2);
                     a += __shfl_xor_sync(0xffffffffu, a, 4);
-                    if (slot == 0) s_xn[xbuf][rsub + 32 * ps] = a * 1.0001f;
+                    if (slot == 0) s_xn[xbuf][rsub + RPP * ps] = a * 1.0001f;
                     xc[ps] = 0.f;
                 }
                 __syncwarp();

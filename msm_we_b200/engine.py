@@ -75,7 +75,7 @@ class DeviceClusters:
                              errors=self.errors, bin_out=bin_out)
 
     # -- K0 + K1 -------------------------------------------------------------------------------
-    def predict(self, X_dev, pcoord_dev, pcoord_host=None, path=_lib.ASSIGN_FP64):
+    def predict(self, X_dev, pcoord_dev, pcoord_host=None, path=_lib.ASSIGN_AUTO):
         """Labels in the ``StratifiedClusters.predict`` convention (basis -> T, target -> T+1)."""
         if X_dev.shape[1] != self.D:
             raise ValueError(f"coordinates have {X_dev.shape[1]} features, cluster centers have {self.D}")
@@ -91,7 +91,7 @@ class DeviceClusters:
 
     # -- K0 + K1 + K3 in one C call -----------------------------------------------------------
     def hotpath_step(self, X2, pcoord2, weights, n_clusters, iter_offsets=None, dense=None, divisor=0.0,
-                     labels_out=None, path=_lib.ASSIGN_FP64):
+                     labels_out=None, path=_lib.ASSIGN_AUTO):
         """Stacked batch (parents then children): labels of both halves and, when ``dense`` is given,
         the batch's transitions added into it (then divided by ``divisor`` if it is neither 0 nor 1)."""
         if self.mapper.kind == _lib.MAPPER_PRECOMPUTED:
