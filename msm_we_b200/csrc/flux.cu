@@ -96,6 +96,103 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Pass 1 + group numbering in ONE launch: the flags of pass 1 and their exclusive prefix sum (= the index of
+// the group every element belongs to), single pass with decoupled look-back across tiles (each tile publishes
+// its aggregate, then its inclusive prefix, in one 64-bit word: top 2 bits = status, rest = value).  Tiles take
+// their number from an atomic ticket, so a tile only ever waits for tiles that are already running.
+static constexpr int FM_THREADS = 256;
+static constexpr int FM_ITEMS = 8;
+static constexpr int FM_TILE = FM_THREADS * FM_ITEMS;
+
+__global__ void __launch_bounds__(FM_THREADS)
+    flux_mark_scan_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t N,
+                          uint64_t sentinel, const double* __restrict__ w, const int64_t* __restrict__ iter_offsets,
+                          int64_t n_iters, double* __restrict__ wv, int32_t* __restrict__ sub_head,
+                          int32_t* __restrict__ cell_head, int32_t* __restrict__ sub_pos,
+                          unsigned long long* __restrict__ tile_state, unsigned int* __restrict__ ticket,
+                          int64_t* __restrict__ total_out, int32_t* __restrict__ err_count) {
+    __shared__ int scratch[9];
+    __shared__ unsigned int s_tile;
+    __shared__ long long s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned int tile = s_tile;
+    const int64_t base = (int64_t)tile * FM_TILE + (int64_t)threadIdx.x * FM_ITEMS;   // blocked: 8 consecutive items
+    int sh[FM_ITEMS], ch[FM_ITEMS];
+    int tsum = 0;
+#pragma unroll
+    for (int j = 0; j < FM_ITEMS; ++j) {
+        const int64_t q = base + j;
+        sh[j] = ch[j] = 0;
+        if (q < N) {
+            const uint64_t k = keys[q];
+            if (k != sentinel) {
+                const uint32_t idx = vals[q];
+                if (w) wv[q] = w[idx];
+                ch[j] = (q == 0 || keys[q - 1] != k) ? 1 : 0;
+                sh[j] = ch[j];
+                if (!ch[j] && iter_offsets) {
+                    const int64_t it = find_iter(iter_offsets, n_iters, (int64_t)idx);
+                    sh[j] = ((int64_t)vals[q - 1] < iter_offsets[it]) ? 1 : 0;
+                }
+            }
+            sub_head[q] = sh[j];
+            cell_head[q] = ch[j];
+            tsum += sh[j];
+        }
+    }
+    int blk_total;
+    const int excl = block_excl_scan_256(tsum, scratch, &blk_total);
+    // ---- decoupled look-back (warp 0: 32 predecessors per round) ----
+    if (threadIdx.x < 32) {
+        const unsigned long long AGG = 1ull << 62, PRE = 2ull << 62, MASK = (1ull << 62) - 1;
+        const int lane = threadIdx.x;
+        long long prefix = 0;
+        if (tile == 0) {
+            if (lane == 0) atomicExch(tile_state + 0, PRE | (unsigned long long)blk_total);
+        } else {
+            if (lane == 0) atomicExch(tile_state + tile, AGG | (unsigned long long)blk_total);
+            long long hi = (long long)tile - 1;   // nearest predecessor not yet accounted for
+            bool done = false;
+            int spins = 0;
+            while (!done) {
+                const long long t = hi - lane;
+                unsigned long long st = PRE;      // lanes before tile 0 behave like a finished prefix of 0
+                if (t >= 0) {
+                    while (((st = *reinterpret_cast<volatile unsigned long long*>(tile_state + t)) >> 62) == 0) {
+                        if (++spins > (1 << 22)) {   // never hang the GPU on a protocol bug
+                            atomicAdd(&err_count[MWE_ERR_INTERNAL], 1);
+                            st = PRE;
+                            break;
+                        }
+                    }
+                }
+                const uint32_t pre_mask = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+                const int stop = pre_mask ? (__ffs(pre_mask) - 1) : 32;   // first lane (nearest tile) with an inclusive prefix
+                long long contrib = (lane <= stop && t >= 0) ? (long long)(st & MASK) : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+                prefix += contrib;
+                done = pre_mask != 0;
+                hi -= 32;
+            }
+            if (lane == 0) atomicExch(tile_state + tile, PRE | (unsigned long long)(prefix + blk_total));
+        }
+        if (lane == 0) {
+            s_prefix = prefix;
+            if ((int64_t)(tile + 1) * FM_TILE >= N && total_out) *total_out = prefix + blk_total;
+        }
+    }
+    __syncthreads();
+    long long run = s_prefix + excl;
+#pragma unroll
+    for (int j = 0; j < FM_ITEMS; ++j) {
+        const int64_t q = base + j;
+        if (q < N) sub_pos[q] = (int32_t)run;
+        run += sh[j];
+    }
+}
+
 // Pass 2 (one thread per sub head): sum the weights of one (cell, iteration) group in segment order --
 // what scipy's coo_matrix -> dense does for that iteration's matrix.  Unit weights: the count, exactly.
 __global__ void __launch_bounds__(256)
@@ -137,50 +234,87 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// Pass 3 (one thread per cell): add the cell's per-iteration groups in iteration order onto the running
-// value of the dense matrix (the reference's `fluxMatrix = fluxMatrix + fluxMatrixI`), single write.
+// Pass 3: add every cell's per-iteration groups in iteration order onto the running value of the dense matrix
+// (the reference's `fluxMatrix = fluxMatrix + fluxMatrixI`), single writer per cell.
+// A warp owns a window of 32 consecutive groups (coalesced loads).  Cells that end inside the window are summed
+// lane-parallel: round u adds the value u places to the right to every head lane whose run is longer than u, so
+// each cell still sees its addends strictly in order.  Only the last cell of a window can continue past it; the
+// warp then walks the following windows together (one coalesced load per 32 groups, next window prefetched)
+// while the owner lane keeps adding in order.  Hot cells (basis -> basis, one group per WE iteration) therefore
+// cost one memory latency per 32 groups instead of one per group.
 __global__ void __launch_bounds__(256)
     flux_cell_sum_kernel(const double* __restrict__ group_sum, const uint8_t* __restrict__ group_is_cell_head,
                          const uint64_t* __restrict__ group_key, const int64_t* __restrict__ n_groups_p, uint64_t CM,
                          double* __restrict__ dense, const int32_t* __restrict__ cell_pos, int64_t* __restrict__ coo_row,
                          int64_t* __restrict__ coo_col, double* __restrict__ coo_val) {
     const int64_t n_groups = *n_groups_p;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < n_groups; gi += stride) {
-        if (!group_is_cell_head[gi]) continue;
-        const uint64_t k = group_key[gi];
-        double total = dense ? dense[k] : 0.0;
-        double fresh = 0.0;
-        // the adds stay strictly sequential (iteration order); the loads are issued 8 at a time
-        int64_t e = gi;
-        bool done = false;
-        bool first = true;
-        while (!done) {
-            double v[8];
-            uint8_t h[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int64_t q = (e + u < n_groups) ? e + u : n_groups - 1;
-                v[u] = group_sum[q];
-                h[u] = group_is_cell_head[q];
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (done) break;
-                if (e + u >= n_groups || (h[u] && !(first && u == 0))) { done = true; break; }
-                total = __dadd_rn(total, v[u]);
-                fresh = (first && u == 0) ? v[u] : __dadd_rn(fresh, v[u]);
-            }
-            first = false;
-            e += 8;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base = warp_global * 32; base < n_groups; base += n_warps * 32) {
+        const int64_t gi = base + lane;
+        const bool in = gi < n_groups;
+        const double v = in ? group_sum[gi] : 0.0;
+        const bool head = in && group_is_cell_head[gi];
+        const uint32_t heads = __ballot_sync(0xffffffffu, head);
+        const uint32_t valid = __ballot_sync(0xffffffffu, in);
+        // run length inside the window: distance to the next head (or to the end of the window / data)
+        const uint32_t after = heads & ~((2u << lane) - 1u);          // heads strictly to the right of this lane
+        const int nvalid = __popc(valid);
+        const int next = after ? (__ffs(after) - 1) : nvalid;
+        const int len = head ? next - lane : 0;
+        const bool open_end = head && !after && base + 32 < n_groups;  // the cell may continue in the next window
+        uint64_t k = 0;
+        double total = 0.0, fresh = 0.0;
+        if (head) {
+            k = group_key[gi];
+            total = dense ? dense[k] : 0.0;
         }
-        if (dense) dense[k] = total;
-        if (coo_val) {
-            const int32_t pos = cell_pos[gi];
-            const uint64_t r = k / CM;
-            coo_row[pos] = (int64_t)r;
-            coo_col[pos] = (int64_t)(k - r * CM);
-            coo_val[pos] = fresh;
+        const int maxlen = __reduce_max_sync(0xffffffffu, len);
+        for (int u = 0; u < maxlen; ++u) {
+            const double vu = __shfl_down_sync(0xffffffffu, v, u);
+            if (u < len) {
+                total = __dadd_rn(total, vu);
+                fresh = (u == 0) ? vu : __dadd_rn(fresh, vu);
+            }
+        }
+        // continuation of the window's last cell
+        const uint32_t open_mask = __ballot_sync(0xffffffffu, open_end);
+        if (open_mask) {
+            const int owner = __ffs(open_mask) - 1;
+            int64_t wb = base + 32;
+            bool more = true;
+            double nv = (wb + lane < n_groups) ? group_sum[wb + lane] : 0.0;
+            bool nh = (wb + lane < n_groups) ? group_is_cell_head[wb + lane] != 0 : true;   // past the end acts as a head
+            while (more) {
+                const double cv = nv;
+                const uint32_t ch = __ballot_sync(0xffffffffu, nh);
+                const int take = ch ? (__ffs(ch) - 1) : 32;
+                more = take == 32 && wb + 32 < n_groups;
+                if (more) {   // prefetch the next window before the ordered adds of this one
+                    const int64_t q = wb + 32 + lane;
+                    nv = (q < n_groups) ? group_sum[q] : 0.0;
+                    nh = (q < n_groups) ? group_is_cell_head[q] != 0 : true;
+                }
+                for (int u = 0; u < take; ++u) {
+                    const double vu = __shfl_sync(0xffffffffu, cv, u);
+                    if (lane == owner) {
+                        total = __dadd_rn(total, vu);
+                        fresh = __dadd_rn(fresh, vu);
+                    }
+                }
+                wb += 32;
+            }
+        }
+        if (head) {
+            if (dense) dense[k] = total;
+            if (coo_val) {
+                const int32_t pos = cell_pos[gi];
+                const uint64_t r = k / CM;
+                coo_row[pos] = (int64_t)r;
+                coo_col[pos] = (int64_t)(k - r * CM);
+                coo_val[pos] = fresh;
+            }
         }
     }
 }
@@ -204,6 +338,7 @@ static size_t flux_ws_bytes(int64_t N) {
     b += 2 * align_up((size_t)N * sizeof(double), 256);    // gathered weights, group sums
     b += align_up((size_t)N * sizeof(uint64_t), 256);      // group keys
     b += align_up((size_t)N, 256) + 256;                   // group flags, group counter
+    b += align_up((size_t)(N / 2048 + 4) * sizeof(unsigned long long), 256);   // look-back tile states + ticket
     b += sort_workspace_bytes(N);
     b += scan_workspace_bytes(N);
     return b + 1024;
@@ -249,6 +384,7 @@ extern "C" int mwe_flux_accumulate_f64(const int64_t* start, const int64_t* end,
     uint64_t* group_key = cv.take<uint64_t>((size_t)N);
     uint8_t* group_flag = cv.take<uint8_t>((size_t)N);
     int64_t* n_groups = cv.take<int64_t>(1);
+    unsigned long long* tile_state = cv.take<unsigned long long>((size_t)((N + FM_TILE - 1) / FM_TILE) + 2);
     const size_t sort_bytes = sort_workspace_bytes(N);
     void* sort_ws = cv.take<char>(sort_bytes);
     const size_t scan_bytes = scan_workspace_bytes(N);
@@ -266,10 +402,14 @@ extern "C" int mwe_flux_accumulate_f64(const int64_t* start, const int64_t* end,
     uint32_t* vs;
     int rc = sort_pairs(keys, vals, N, key_bits, sort_ws, sort_bytes, s, &ks, &vs);
     if (rc != MWE_OK) return rc;
-    flux_mark_kernel<<<(unsigned)blocks, 256, 0, s>>>(ks, vs, N, sentinel, w, iter_offsets, n_iters, wv, sub_head, cell_head);
-    MWE_CHECK_LAUNCH();
-    rc = exclusive_scan_i32(sub_head, pos, N, n_groups, scan_ws, scan_bytes, s);
-    if (rc != MWE_OK) return rc;
+    {
+        const int64_t ntiles = (N + FM_TILE - 1) / FM_TILE;
+        MWE_CHECK_CUDA(cudaMemsetAsync(tile_state, 0, (size_t)(ntiles + 1) * sizeof(unsigned long long), s));
+        unsigned int* ticket = reinterpret_cast<unsigned int*>(tile_state + ntiles);
+        flux_mark_scan_kernel<<<(unsigned)ntiles, FM_THREADS, 0, s>>>(ks, vs, N, sentinel, w, iter_offsets, n_iters, wv, sub_head,
+                                                                      cell_head, pos, tile_state, ticket, n_groups, err_count);
+        MWE_CHECK_LAUNCH();
+    }
     flux_group_sum_kernel<<<(unsigned)blocks, 256, 0, s>>>(ks, N, sentinel, wv, w != nullptr, sub_head, pos, cell_head,
                                                           group_sum, group_flag, group_key);
     MWE_CHECK_LAUNCH();
