@@ -17,6 +17,7 @@ import numpy as np
 from .._logging import log, ProgressBar
 
 DEFAULT_FLUX_CHUNK = 1 << 26  # transitions per launch sequence
+_FLUX_STAGE = {"host": None, "pending": None}   # pinned staging rows, reused across calls
 
 
 class _RemoteShim:
@@ -126,51 +127,67 @@ class FluxMatrixMixin:
         errors = ops.DeviceErrors(dev)
         mapper = ops.MapperSpec.precomputed(1)
         chunk = int(getattr(self, "flux_chunk_transitions", DEFAULT_FLUX_CHUNK))
-        pairs, pc0, pc1, ws, lens = [], [], [], [], []
+        W = 2 * P + 3                       # staged row: parent pcoord | child pcoord | weight | parent label | child label
+        stagebuf = _FLUX_STAGE          # module-level: a model stays picklable / deep-copyable
+        lens = []
+        n = 0
+
+        def rows(need):
+            """numpy view of the pinned staging rows, grown (contents kept) to hold ``need`` rows."""
+            if stagebuf["pending"] is not None:
+                stagebuf["pending"].synchronize()    # the H2D that last read the buffer has finished
+                stagebuf["pending"] = None
+            host = stagebuf["host"]
+            if host is None or host.shape[1] != W or host.shape[0] < need:
+                cap = max(need, 1 << 14, 2 * (host.shape[0] if host is not None and host.shape[1] == W else 0))
+                grown = torch.empty((cap, W), dtype=torch.float64, pin_memory=True)
+                if host is not None and host.shape[1] == W and n > 0:
+                    grown[:n] = host[:n]
+                stagebuf["host"] = host = grown
+            return host.numpy()
 
         def flush():
+            nonlocal n
             if not lens:
                 return
-            n = int(sum(lens))
             if n > 0:
-                idx = np.concatenate(pairs, axis=0).astype(np.int64, copy=False)
-                if idx.ndim != 2 or idx.shape[1] != 2:
-                    raise ValueError("pair_dtrajs entries must be [S, 2]")
-                host = torch.empty((n, 2 * P + 3), dtype=torch.float64, pin_memory=True)
-                h = host.numpy()
-                np.concatenate(pc0, axis=0, out=h[:, :P])
-                np.concatenate(pc1, axis=0, out=h[:, P:2 * P])
-                np.concatenate(ws, axis=0, out=h[:, 2 * P])
-                h[:, 2 * P + 1:] = idx          # labels < 2^53 are exact in fp64; one H2D instead of two
-                d = host.to(dev, non_blocking=True)
+                d = stagebuf["host"][:n].to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+                stagebuf["pending"] = ev
                 offs = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)).to(dev)
                 zeros = torch.zeros(n, dtype=torch.int32, device=dev)
                 _, f0 = ops.bin_flags(d[:, :P].contiguous(), mapper, self.basis_pcoord_bounds, self.target_pcoord_bounds,
                                       errors=errors, bin_out=zeros)
                 _, f1 = ops.bin_flags(d[:, P:2 * P].contiguous(), mapper, self.basis_pcoord_bounds,
                                       self.target_pcoord_bounds, errors=errors, bin_out=zeros)
-                start = d[:, 2 * P + 1].to(torch.int64)
+                start = d[:, 2 * P + 1].to(torch.int64)      # labels < 2^53 are exact in fp64; one H2D, not two
                 end = d[:, 2 * P + 2].to(torch.int64)
                 ops.flux_accumulate(start, end, d[:, 2 * P].contiguous(), int(self.n_clusters), flag0=f0, flag1=f1,
                                     iter_offsets=offs, dense=dense, errors=errors)
-            pairs.clear(); pc0.clear(); pc1.clear(); ws.clear(); lens.clear()
+            lens.clear()
+            n = 0
 
-        staged = 0
         for iS in iters:
             index_pairs, p0, p1, w = self._gather_flux_inputs(iS)
             s = w.shape[0]
             if s > 0:
+                index_pairs = np.asarray(index_pairs)
                 if index_pairs.shape[0] != s:
                     raise ValueError("row, column, and data array must all be the same length")
-                pairs.append(index_pairs.reshape(s, 2)); pc0.append(p0.reshape(s, P)); pc1.append(p1.reshape(s, P))
-                ws.append(w)
+                if index_pairs.ndim != 2 or index_pairs.shape[1] != 2:
+                    raise ValueError("pair_dtrajs entries must be [S, 2]")
+                h = rows(n + s)
+                h[n:n + s, :P] = p0.reshape(s, P)
+                h[n:n + s, P:2 * P] = p1.reshape(s, P)
+                h[n:n + s, 2 * P] = w
+                h[n:n + s, 2 * P + 1:] = index_pairs
+                n += s
             lens.append(s)
-            staged += s
             if progress is not None:
                 progress.update(task, advance=1)
-            if staged >= chunk:
+            if n >= chunk:
                 flush()
-                staged = 0
         flush()
         errors.check()
         return dense
