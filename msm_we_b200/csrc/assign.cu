@@ -111,10 +111,28 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     assign_scatter_kernel(const int32_t* __restrict__ bin, const uint8_t* __restrict__ flag, int64_t N, int32_t nbins,
                           const int64_t* __restrict__ bin_offset, int32_t* __restrict__ bin_cursor,
-                          int32_t* __restrict__ perm, int64_t* __restrict__ label_out, int32_t* __restrict__ local_out) {
+                          int32_t* __restrict__ perm, int64_t* __restrict__ label_out, int32_t* __restrict__ local_out,
+                          const int32_t* __restrict__ bin_start, const int32_t* __restrict__ tile_prefix, int tile_points,
+                          int4* __restrict__ tile_desc) {
     __shared__ int32_t s_cnt[AS_SMEM_BINS];
     const bool use_smem = nbins <= AS_SMEM_BINS;
     const int64_t T = bin_offset[nbins];
+    if (tile_desc) {
+        // tile records for the resident-centre kernel: the bin of a tile by binary search over the tile prefix
+        const int32_t n_tiles = tile_prefix[nbins];
+        for (int32_t tile = blockIdx.x * 256 + threadIdx.x; tile < n_tiles; tile += gridDim.x * 256) {
+            int lo = 0, hi = nbins - 1;          // last bin with tile_prefix[bin] <= tile
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (tile_prefix[mid] <= tile) lo = mid; else hi = mid - 1;
+            }
+            const int32_t in_bin = (tile - tile_prefix[lo]) * tile_points;
+            const int32_t left = (bin_start[lo + 1] - bin_start[lo]) - in_bin;
+            const int64_t coff = bin_offset[lo];
+            tile_desc[tile] = make_int4(bin_start[lo] + in_bin, left < tile_points ? left : tile_points, (int32_t)coff,
+                                        (int32_t)(bin_offset[lo + 1] - coff));
+        }
+    }
     if (use_smem) {
         for (int b = threadIdx.x; b < nbins; b += 256) s_cnt[b] = 0;
         __syncthreads();
@@ -301,7 +319,7 @@ __global__ void __launch_bounds__(CW * 32, (CW == 4 ? (NT <= 4 ? 4 : 2) : 1)) as
     float m1f[2] = {finf, finf};
     float m2f[2] = {finf, finf};
     int32_t besti[2] = {0, 0};
-    double xx[2] = {0.0, 0.0};        // partial ||x||^2 of rows g and g+8 (this thread's k positions)
+    uint32_t xhi[2] = {0u, 0u};       // largest |x_k| high word of rows g / g+8 (this thread's k positions)
     float cmaxf = 0.f;                // upper bound of the largest ||c||^2 among this thread's columns
     int32_t out_pt[2] = {-1, -1};     // point index of rows g / g+8 of the tile being computed (lanes t == 0)
     double acc[2][NT][2];
@@ -332,8 +350,8 @@ __global__ void __launch_bounds__(CW * 32, (CW == 4 ? (NT <= 4 ? 4 : 2) : 1)) as
             for (int ks = 0; ks < AS_DC / 4; ++ks) {
                 const double a0 = xa0[ks * 4];
                 const double a1 = xa1[ks * 4];
-                xx[0] = fma(a0, a0, xx[0]);   // ||x||^2, once per tile (only feeds the tie tolerance)
-                xx[1] = fma(a1, a1, xx[1]);
+                xhi[0] = max(xhi[0], (uint32_t)__double2hiint(a0) & 0x7fffffffu);   // bound of |x_k| (feeds the tie tolerance)
+                xhi[1] = max(xhi[1], (uint32_t)__double2hiint(a1) & 0x7fffffffu);
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     const double bv = cb0[nt * 8 * AS_LD + ks * 4];
@@ -390,13 +408,13 @@ __global__ void __launch_bounds__(CW * 32, (CW == 4 ? (NT <= 4 ? 4 : 2) : 1)) as
             for (int mt = 0; mt < 2; ++mt) {
                 float bs = m1f[mt], ru = m2f[mt];
                 int32_t bi = besti[mt];
-                float xs = __double2float_ru(xx[mt]);
+                uint32_t xh = xhi[mt];
 #pragma unroll
                 for (int o = 1; o <= 2; o <<= 1) {
                     const float os = __shfl_xor_sync(0xffffffffu, bs, o);
                     const float o2 = __shfl_xor_sync(0xffffffffu, ru, o);
                     const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                    xs += __shfl_xor_sync(0xffffffffu, xs, o);
+                    xh = max(xh, __shfl_xor_sync(0xffffffffu, xh, o));
                     // runner-up of the union = min(both runner-ups, the larger of the two bests)
                     ru = fminf(fminf(ru, o2), fmaxf(bs, os));
                     if (os < bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
@@ -407,13 +425,15 @@ __global__ void __launch_bounds__(CW * 32, (CW == 4 ? (NT <= 4 ? 4 : 2) : 1)) as
                     if (p.local_out) p.local_out[pt] = bi;
                     // true gap > (ru - bs) - ulp32(bs); flag unless that clears the (over-estimated) tolerance
                     const float cmax = sqrtf(cmaxf) * 1.000001f;
-                    const float tolf = 2.0f * (float)p.tie_scale * cmax * (2.0f * sqrtf(xs) * 1.000001f + cmax);
+                    // ||x|| <= sqrt(D) max|x_k|, max|x_k| < the double whose high word is xh + 1 (inf/NaN -> inf)
+                    const float xnorm = __double2float_ru(__hiloint2double((int)(min(xh, 0x7ff00000u) + 1u), 0)) * p.sqrt_d;
+                    const float tolf = 2.0f * (float)p.tie_scale * cmax * (2.0f * xnorm + cmax);
                     const double gap_lb = ((double)ru - (double)bs) - 1.2e-7 * fabs((double)bs);
                     if (!(gap_lb > (double)tolf)) p.recheck_list[atomicAdd(p.recheck_count, 1)] = pt;
                 }
                 m1f[mt] = m2f[mt] = finf;
                 besti[mt] = 0;
-                xx[mt] = 0.0;
+                xhi[mt] = 0u;
             }
             cmaxf = 0.f;
         }
@@ -504,6 +524,7 @@ __global__ void __launch_bounds__(256) centers_sqnorm_kernel(const double* __res
 
 
 struct AssignWs {
+    int4* tile_desc;
     int32_t* recheck_list;
     int32_t* recheck_count;
     int32_t* perm;
@@ -517,6 +538,7 @@ static size_t assign_ws_bytes(int64_t N, int32_t nbins) {
     size_t b = 0;
     b += 2 * align_up((size_t)(N > 0 ? N : 1) * sizeof(int32_t), 256);
     b += 5 * align_up((size_t)(nbins + 1) * sizeof(int32_t), 256);
+    b += align_up(((size_t)(N > 0 ? N : 1) / 128 + (size_t)nbins + 2) * sizeof(int4), 256);   // tile records
     return b + 1024;
 }
 
@@ -646,34 +668,41 @@ extern "C" int mwe_assign_stratified_f64(const double* X, int64_t N, int D, int6
     ws.bin_cursor = cv.take<int32_t>((size_t)nbins + 1);
     ws.bin_start = cv.take<int32_t>((size_t)nbins + 1);
     ws.tile_prefix = cv.take<int32_t>((size_t)nbins + 1);
+    ws.tile_desc = cv.take<int4>((size_t)N / 128 + (size_t)nbins + 2);
 
     const int nt = pick_nt(max_k);
-    const int tile_points = use_tc ? 128 : tile_points_for(nt);
+    const bool vec2 = (D % 2 == 0) && (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(centers) & 15) == 0);
+    const int res_points = (use_tc || (int64_t)nbins * max_k >= ((int64_t)1 << 31) || ldx >= ((int64_t)1 << 28)) ? 0 : assign_resident_tile_points(D, max_k, vec2);
+    const bool use_res = res_points > 0;
+    const int tile_points = use_tc ? 128 : use_res ? res_points : tile_points_for(nt);
     MWE_CHECK_CUDA(cudaMemsetAsync(ws.bin_count, 0, (size_t)(nbins + 2) * sizeof(int32_t), s));
     const int64_t blocks = (N + 256 * AS_BK_ITEMS - 1) / (256 * AS_BK_ITEMS);
     if (!bin_count_in) assign_count_kernel<<<(unsigned)blocks, 256, 0, s>>>(bin, flag, N, nbins, ws.bin_count);
     assign_scan_kernel<<<1, 256, 0, s>>>(bin_count_in ? bin_count_in : ws.bin_count, bin_offset, nbins, ws.bin_start, ws.bin_cursor, ws.tile_prefix, err_count,
                                          tile_points);
     assign_scatter_kernel<<<(unsigned)blocks, 256, 0, s>>>(bin, flag, N, nbins, bin_offset, ws.bin_cursor, ws.perm, label_out,
-                                                          local_out);
+                                                          local_out, ws.bin_start, ws.tile_prefix, tile_points,
+                                                          use_res ? ws.tile_desc : nullptr);
     MWE_CHECK_LAUNCH();
 
     AssignParams p;
     p.X = X; p.ldx = ldx; p.D = D; p.centers = centers; p.csq = csq; p.bin_offset = bin_offset; p.nbins = nbins;
-    p.perm = ws.perm; p.bin_start = ws.bin_start; p.tile_prefix = ws.tile_prefix;
+    p.perm = ws.perm; p.bin_start = ws.bin_start; p.tile_prefix = ws.tile_prefix; p.tile_desc = ws.tile_desc;
     p.label_out = label_out; p.local_out = local_out;
     p.recheck_list = ws.recheck_list; p.recheck_count = ws.recheck_count;
     p.tie_scale = AS_TIE_C * (double)(D + 8) * 1.1102230246251565e-16;
+    p.sqrt_d = (float)(sqrt((double)D) * 1.000001);
     p.ncb = (max_k + nt * 8 - 1) / (nt * 8);
     p.nch = (D + AS_DC - 1) / AS_DC;
     const int64_t max_tiles = (N + tile_points - 1) / tile_points + nbins;
-    const bool vec2 = (D % 2 == 0) && (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(centers) & 15) == 0);
     int rc;
     if (use_tc) {
         const size_t prep_bytes = assign_tc_prep_bytes(nbins, D, max_k);
         void* prep = cv.take<char>(prep_bytes);
         rc = launch_assign_tc(p, max_k, N, prep, prep_bytes, s);
+    } else if (use_res) {
+        rc = launch_assign_resident(p, max_k, vec2, max_tiles, s);
     } else {
         rc = vec2 ? dispatch_nt<2>(nt, p, max_tiles, s) : dispatch_nt<1>(nt, p, max_tiles, s);
     }

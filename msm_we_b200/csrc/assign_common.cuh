@@ -5,7 +5,7 @@
 namespace mwe {
 
 static constexpr int AS_TABLE_BINS = 1024;     // bins whose tile tables are cached in shared memory
-static constexpr int AS_SPIN_LIMIT = 1 << 26;
+static constexpr int AS_SPIN_LIMIT = 1 << 22;     // a protocol bug traps after a few seconds instead of hanging the GPU
 static constexpr double AS_TIE_C = 4.0;        // tie band = AS_TIE_C (D+8) 2^-53 cmax (2||x|| + cmax)
 
 // ---- PTX helpers -----------------------------------------------------------------------------
@@ -71,11 +71,13 @@ struct AssignParams {
     const int32_t* perm;
     const int32_t* bin_start;
     const int32_t* tile_prefix;
+    const int4* tile_desc;   // per tile {first bucket slot, points, first centre row, centres} (resident kernel)
     int64_t* label_out;
     int32_t* local_out;
     int32_t* recheck_list;   // points whose best two scores are within rounding noise
     int32_t* recheck_count;
     double tie_scale;        // TIE_C * (D + 8) * 2^-53
+    float sqrt_d;            // sqrt(D), rounded up
     int ncb;      // centre blocks of NT*8 per tile
     int nch;      // k-chunks of AS_DC per centre block
     int nstages;  // depth of the shared-memory ring
@@ -123,6 +125,10 @@ struct TileWalk {
     }
 };
 
+
+// fp64 path with the bin's centres resident in shared memory (assign_res.cu)
+int assign_resident_tile_points(int D, int32_t max_k, bool vec2);   // 0 = shape outside the kernel's envelope
+int launch_assign_resident(AssignParams p, int32_t max_k, bool vec2, int64_t max_tiles, cudaStream_t stream);
 
 // tcgen05 path (assign_tc.cu).  prep_bytes: workspace for the pre-split centres.
 int resolve_assign_path(int precision_path, int D, int32_t max_k);

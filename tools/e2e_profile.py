@@ -18,6 +18,8 @@ model.get_iterations(); model.dimReduce()
 clusters = StratifiedClusters(RectilinearBinMapper(synthetic.boundaries(cfg)), model, cfg.k_per_bin, [])
 for b in range(cfg.n_bins):
     clusters.cluster_models[b].cluster_centers_ = centers[b]
+import os
+if os.environ.get('CHUNK_MB'): clusters.cluster_args['gpu_chunk_bytes'] = int(os.environ['CHUNK_MB']) << 20
 model.clusters = clusters; model.n_clusters = cfg.n_clusters; model.pre_discretization_model = model
 
 def once():
