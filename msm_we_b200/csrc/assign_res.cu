@@ -46,12 +46,11 @@ struct ResShared {
 //   NT : 8-column centre sub-tiles (K_pad = NT*8 >= every bin's centre count)
 //   NW : consumer warps
 template <int NT, int NW>
-__global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_kernel(const AssignParams p, int nbufs, int xld) {
+__global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_kernel(const AssignParams p, int nbufs, int xld, int nks) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int KP = NT * 8;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int nks = (xld - 4) / 4;                       // k4 steps over the zero-padded row
     const uint32_t row_bytes = (uint32_t)p.D * 8u;
     double* sC = reinterpret_cast<double*>(smem_raw);            // [2][KP][xld]
     double* sQ = sC + (size_t)2 * KP * xld;                       // [2][KP]
@@ -63,9 +62,18 @@ __global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_ker
     const int count = (int)(((int64_t)n_tiles * (blockIdx.x + 1)) / gridDim.x) - first;
     const int4* __restrict__ desc = p.tile_desc + first;         // {pstart, pcount, coff, kb}
 
-    // zero everything once: pad columns of rows and centres stay zero for the whole kernel (copies only ever
-    // write the first D doubles of a row), never-copied rows hold finite values
-    for (size_t e = threadIdx.x; e < (size_t)(2 * KP * xld + 2 * KP) + (size_t)nbufs * AR_GROUP * xld; e += blockDim.x) sC[e] = 0.0;
+    // Columns [D, 8*ceil(D/8)) of every point and centre row are read by the k loop but never written by a copy:
+    // zero them once.  Nothing else needs initialising: rows of a short group / centre rows past the bin's count
+    // only feed accumulator rows / columns that are never read (rows and columns of the product are independent).
+    if (p.D != xld - 4) {
+        const int npad = xld - 4 - p.D;
+        const int nrows_all = 2 * KP + nbufs * AR_GROUP;          // sC rows, then (after sQ) the buffer rows
+        for (int e = threadIdx.x; e < nrows_all * npad; e += blockDim.x) {
+            const int r = e / npad, c = p.D + (e - r * npad);
+            double* row = (r < 2 * KP) ? sC + (size_t)r * xld : bufs + (size_t)(r - 2 * KP) * xld;
+            row[c] = 0.0;
+        }
+    }
     if (threadIdx.x == 0) {
         for (int b = 0; b < nbufs; ++b) { mbar_init(&sh->full[b], 33); mbar_init(&sh->empty[b], 1); }
         mbar_init(&sh->cbar[0], 1);
@@ -81,8 +89,6 @@ __global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_ker
         for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
         if (lane == 0) sh->total_groups = tot;
     }
-    // make the generic-proxy zero fill visible to the async proxy (bulk copies write the same rows later)
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
     if (warp >= NW) {
@@ -135,9 +141,9 @@ __global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_ker
                     double* cdst = sC + (size_t)nb * KP * xld;
                     if (lane == 0) mbar_expect_tx(&sh->cbar[nb], (uint32_t)kb * row_bytes);
                     __syncwarp();
-                    for (int r = lane; r < kb; r += 32) {
-                        bulk_copy_g2s(cdst + (size_t)r * xld, p.centers + ((int64_t)d_cur.z + r) * p.D, row_bytes, &sh->cbar[nb]);
-                        sQ[nb * KP + r] = p.csq[d_cur.z + r];
+                    for (int r = lane; r < KP; r += 32) {
+                        if (r < kb) bulk_copy_g2s(cdst + (size_t)r * xld, p.centers + ((int64_t)d_cur.z + r) * p.D, row_bytes, &sh->cbar[nb]);
+                        sQ[nb * KP + r] = (r < kb) ? -0.5 * p.csq[d_cur.z + r] : 0.0;     // accumulator seed: acc = x.c - ||c||^2/2
                     }
                     mbar_wait(&sh->cbar[nb], cuse[nb] & 1u);
                 }
@@ -225,12 +231,15 @@ __global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_ker
         const int g = lane >> 2, t = lane & 3;
         const float finf = __int_as_float(0x7f800000);
         const int32_t total = sh->total_groups;
+        const uint32_t nbufs_magic = (uint32_t)((((uint64_t)1 << 32) + (uint32_t)nbufs - 1) / (uint32_t)nbufs);
+        int32_t q_next = 0;
+        if (lane == 0) q_next = atomicAdd(&sh->ticket, 1);
         while (true) {
-            int32_t q = 0;
-            if (lane == 0) q = atomicAdd(&sh->ticket, 1);
-            q = __shfl_sync(0xffffffffu, q, 0);
+            const int32_t q = __shfl_sync(0xffffffffu, q_next, 0);
             if (q >= total) break;
-            const int b = q % nbufs;
+            if (lane == 0) q_next = atomicAdd(&sh->ticket, 1);   // next ticket: its latency hides under this group's math
+            const uint32_t use = __umulhi((uint32_t)q, nbufs_magic);     // q / nbufs (exact for q < 2^32 / nbufs)
+            const int b = q - (int32_t)use * nbufs;
             // Tickets can run ahead of the fills by more than nbufs groups (other consumers keep finishing groups
             // while one waits), and an mbarrier parity cannot tell phase u from phase u-2.  So first wait until
             // the producer has claimed the buffer for THIS group (then full[b] is in phase u or u+1), then wait
@@ -239,11 +248,11 @@ __global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_ker
                 const volatile int32_t* tag = &sh->meta[b][20];
                 int spins = 0;
                 while (*tag != q) {
-                    __nanosleep(200);      // do not take issue slots from the producer warps while waiting
+                    __nanosleep(20);       // do not take issue slots from the producer warps while waiting
                     if (++spins > AS_SPIN_LIMIT) __trap();
                 }
             }
-            mbar_wait(&sh->full[b], (uint32_t)(q / nbufs) & 1u);
+            mbar_wait(&sh->full[b], use & 1u);
             const int32_t* meta = sh->meta[b];
             const int32_t coff = meta[16], kb = meta[17], cbuf = meta[18], nrows = meta[19];
             int32_t out_pt[2];
@@ -252,11 +261,23 @@ __global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_ker
             const double* xa0 = bufs + ((size_t)b * AR_GROUP + g) * xld + t;
             const double* xa1 = xa0 + 8 * xld;
             const double* cb0 = sC + ((size_t)cbuf * KP + g) * xld + t;
+            // Accumulators start at -||c_j||^2/2, so after the k loop acc = x.c_j - ||c_j||^2/2 = -score_j/2 and the
+            // fold needs no fp64 arithmetic.  This is NOT the reference's evaluation order (dot product from 0, then
+            // one fma with ||c||^2): the two differ by < D u cmax (cmax + 2||x||), a quarter of the tie band, and the
+            // filter below only trusts gaps of two tie bands, so everything it accepts has the reference's argmin;
+            // everything else is re-evaluated in the reference's order by assign_recheck_kernel.
             double acc[2][NT][2];
+            float cmaxf = 0.f;
+            {
+                const double* sq = sQ + cbuf * KP;
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+                for (int nt = 0; nt < NT; ++nt) {
+                    const double2 h = *reinterpret_cast<const double2*>(sq + nt * 8 + 2 * t);
+                    acc[0][nt][0] = acc[1][nt][0] = h.x;
+                    acc[0][nt][1] = acc[1][nt][1] = h.y;
+                    cmaxf = fmaxf(cmaxf, fmaxf(__double2float_rd(h.x) * -2.0f, __double2float_rd(h.y) * -2.0f));   // >= ||c||^2
+                }
+            }
             uint32_t xhi[2] = {0u, 0u};
 #pragma unroll 4
             for (int ks = 0; ks < nks; ++ks) {
@@ -272,23 +293,24 @@ __global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_ker
                 }
             }
 
-            // fp32 round-down candidates (smallest, its column, second smallest): see assign.cu for the contract
+            // rows and metadata are in registers and the centre buffers were read for the last time: the buffer goes
+            // back ("groups in flight <= buffers" therefore also bounds who can still be reading a centre buffer,
+            // which the producer relies on when it reuses one)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh->empty[b]);
+
+            // fp32 candidates: sf = round-down(score) = -2 * round-up(acc); smallest, its column, second smallest
             float m1f[2] = {finf, finf}, m2f[2] = {finf, finf};
             int32_t besti[2] = {0, 0};
-            float cmaxf = 0.f;
-            const double* sq = sQ + cbuf * KP;
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-                const double2 cs2 = *reinterpret_cast<const double2*>(sq + nt * 8 + 2 * t);
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const int c = nt * 8 + 2 * t + j;
                     if (c < kb) {
-                        const double cs = j ? cs2.y : cs2.x;
-                        cmaxf = fmaxf(cmaxf, __double2float_ru(cs));
 #pragma unroll
                         for (int mt = 0; mt < 2; ++mt) {
-                            const float sf = __double2float_rd(fma(-2.0, acc[mt][nt][j], cs));
+                            const float sf = -2.0f * __double2float_ru(acc[mt][nt][j]);
                             const bool lt = sf < m1f[mt];          // strict: the first of equal roundings stays
                             m2f[mt] = lt ? m1f[mt] : fminf(m2f[mt], sf);
                             besti[mt] = lt ? c : besti[mt];
@@ -297,10 +319,6 @@ __global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_ker
                     }
                 }
             }
-            // rows, metadata and ||c||^2 are in registers now: hand the buffer back.  (Released only after the last
-            // read of the centre buffers, so "groups in flight <= buffers" also bounds who can still read them.)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sh->empty[b]);
             cmaxf = fmaxf(cmaxf, __shfl_xor_sync(0xffffffffu, cmaxf, 1));
             cmaxf = fmaxf(cmaxf, __shfl_xor_sync(0xffffffffu, cmaxf, 2));
             const float cmax = sqrtf(cmaxf) * 1.000001f;
@@ -345,6 +363,7 @@ static bool resident_plan(int D, int32_t max_k, bool vec2, ResidentPlan* pl) {
     if (!vec2 || max_k > 64) return false;   // 16-byte copies need aligned rows; K_pad <= 64 accumulator columns
     pl->nt = max_k <= 16 ? 2 : max_k <= 24 ? 3 : max_k <= 32 ? 4 : max_k <= 48 ? 6 : 8;
     pl->nw = pl->nt <= 3 ? 16 : pl->nt == 4 ? 14 : 12;
+    if (const char* e = getenv("MWE_ASSIGN_NW")) { if (pl->nt == 3 && (atoi(e) == 18 || atoi(e) == 20)) pl->nw = atoi(e); }   // tuning knob
     pl->xld = ((D + 7) / 8) * 8 + 4;
     const size_t kp = (size_t)pl->nt * 8;
     const size_t fixed = (2 * kp * pl->xld + 2 * kp) * sizeof(double) + sizeof(ResShared) + 128;
@@ -375,7 +394,7 @@ static int launch_resident(const AssignParams& p, const ResidentPlan& pl, int64_
     cudaEvent_t ev0, ev1;
     timing_events(&ev0, &ev1);
     if (ev0) MWE_CHECK_CUDA(cudaEventRecord(ev0, stream));
-    assign_dmma_resident_kernel<NT, NW><<<(unsigned)grid, (NW + AR_NP) * 32, pl.smem, stream>>>(p, pl.nbufs, pl.xld);
+    assign_dmma_resident_kernel<NT, NW><<<(unsigned)grid, (NW + AR_NP) * 32, pl.smem, stream>>>(p, pl.nbufs, pl.xld, (pl.xld - 4) / 4);
     MWE_CHECK_LAUNCH();
     if (ev1) MWE_CHECK_CUDA(cudaEventRecord(ev1, stream));
     return MWE_OK;
@@ -392,7 +411,9 @@ int launch_assign_resident(AssignParams p, int32_t max_k, bool vec2, int64_t max
     if (!resident_plan(p.D, max_k, vec2, &pl)) return MWE_E_UNSUPPORTED;
     switch (pl.nt) {
         case 2: return launch_resident<2, 16>(p, pl, max_tiles, stream);
-        case 3: return launch_resident<3, 16>(p, pl, max_tiles, stream);
+        case 3: return pl.nw == 20 ? launch_resident<3, 20>(p, pl, max_tiles, stream)
+                     : pl.nw == 18 ? launch_resident<3, 18>(p, pl, max_tiles, stream)
+                                   : launch_resident<3, 16>(p, pl, max_tiles, stream);
         case 4: return launch_resident<4, 14>(p, pl, max_tiles, stream);
         case 6: return launch_resident<6, 12>(p, pl, max_tiles, stream);
         default: return launch_resident<8, 12>(p, pl, max_tiles, stream);

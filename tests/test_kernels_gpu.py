@@ -204,6 +204,36 @@ def test_assign_tcgen05_scores_within_error_bound():
     assert worst < 1.0, worst          # measured ratio is reported in profiles/; the bound must never be exceeded
 
 
+@pytest.mark.parametrize("N,D,nbins,K,ragged", [
+    (300000, 64, 30, 20, False),    # BASELINE cfg2 shape, several tiles per CTA
+    (4000, 6, 3, 9, True),          # D not a multiple of 8: zero-padded k steps
+    (4000, 2, 7, 64, True),         # smallest even D, widest accumulator block
+    (3000, 66, 4, 16, False),       # rows of 528 bytes: general copy loop
+    (5000, 130, 5, 8, True),        # long rows, few buffers
+    (6000, 32, 400, 5, True),       # hundreds of tiny bins: centre buffers recycled with groups still in flight
+    (257, 64, 2, 1, False),         # one centre per bin
+])
+def test_assign_resident_kernel_matches_streaming_kernel_and_oracle(N, D, nbins, K, ragged, monkeypatch):
+    """The resident-centre producer/consumer kernel (assign_res.cu) is what the fp64 path runs for K <= 64 and
+    16-byte aligned rows; the streaming kernel (assign.cu) is its fallback.  Same labels from both, and from
+    the oracle."""
+    ops = _ops()
+    rng = np.random.default_rng(N + 31 * D)
+    X, bins, flags, centers, offs, ks = _strat_case(rng, N, D, nbins, K, ragged)
+    c = t(centers)
+    args = (t(X), t(bins), t(flags), c, ops.centers_sqnorm(c), t(offs), int(ks.max()))
+    from msm_we_b200 import _lib
+    monkeypatch.delenv("MWE_ASSIGN_RESIDENT", raising=False)
+    lab_res = ops.assign_stratified(*args, path=_lib.ASSIGN_FP64).cpu().numpy()
+    monkeypatch.setenv("MWE_ASSIGN_RESIDENT", "0")
+    lab_str = ops.assign_stratified(*args, path=_lib.ASSIGN_FP64).cpu().numpy()
+    assert np.array_equal(lab_res, lab_str)
+    if N <= 6000:
+        ref, margins = _ref_labels(X, bins, flags, centers, offs)
+        safe = margins > 1e-11
+        assert np.array_equal(lab_res[safe], ref[safe])
+
+
 def test_assign_ties_pick_lowest_index():
     ops = _ops()
     rng = np.random.default_rng(5)
