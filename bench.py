@@ -184,7 +184,16 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
                                           "--format=csv,noheader,nounits", "-lms", "10", "-f", self.path],
                                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-            time.sleep(0.15)   # let it take its first samples
+            # nvidia-smi needs up to a second to start on a fresh box: wait for its first sample, else a short
+            # timed region ends before anything was written
+            t_end = time.time() + 5.0
+            while time.time() < t_end:
+                try:
+                    if os.path.getsize(self.path) > 0:
+                        break
+                except OSError:
+                    pass
+                time.sleep(0.02)
         except Exception:
             self.proc = None
         return self
@@ -197,7 +206,7 @@ class ClockSampler:
 
     def __exit__(self, *exc):
         if self.proc is not None:
-            time.sleep(0.05)
+            time.sleep(0.03)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=5)
@@ -358,7 +367,8 @@ def main():
     peak, peak_src = load_peaks()
     alg_bytes = 2 * N * (cfg.dim * 8 + 4 + 8)
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "assign_tc_kernel" if path == _lib.ASSIGN_TF32X3 else "assign_dmma_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "assign_tc_kernel" if path == _lib.ASSIGN_TF32X3 else
+                ("assign_dmma_resident_kernel" if (cfg.k_per_bin <= 64 and cfg.dim % 2 == 0) else "assign_dmma_kernel"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "fp64_tflops": 2 * N * 2.0 * cfg.k_per_bin * cfg.dim / (kernel_ms * 1e-3) / 1e12}

@@ -26,12 +26,22 @@
 
 namespace mwe {
 
+// iteration that owns transition idx: largest it with offsets[it] <= idx
+__device__ __forceinline__ int64_t find_iter(const int64_t* __restrict__ offsets, int64_t n_iters, int64_t idx) {
+    int64_t lo = 0, hi = n_iters;  // answer in [lo, hi)
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= idx) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
 __global__ void __launch_bounds__(256)
     flux_keys_kernel(const int64_t* __restrict__ start, const int64_t* __restrict__ end,
                      const uint8_t* __restrict__ flag0, const uint8_t* __restrict__ flag1,
                      const uint8_t* __restrict__ col0, const uint8_t* __restrict__ col1, int64_t N, int64_t n_clusters,
-                     int C, uint64_t sentinel, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                     int32_t* __restrict__ err_count) {
+                     int C, uint64_t sentinel, const int64_t* __restrict__ iter_offsets, int64_t n_iters, int iter_shift,
+                     uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int32_t* __restrict__ err_count) {
     const int64_t M = n_clusters + 2;
     const uint64_t CM = (uint64_t)C * (uint64_t)M;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -52,47 +62,12 @@ __global__ void __launch_bounds__(256)
             if (c0 >= (uint64_t)C || c1 >= (uint64_t)C) atomicAdd(&err_count[MWE_ERR_LABEL_RANGE], 1);
             else key = ((uint64_t)C * (uint64_t)s + c0) * CM + ((uint64_t)C * (uint64_t)e + c1);
         }
+        // The WE iteration of the transition rides in the key bits ABOVE the cell (the sort only looks at the
+        // cell bits, the rest is carried along), so the passes after the sort find (cell, iteration) group
+        // boundaries by comparing neighbouring keys instead of searching iter_offsets per element.
+        if (iter_shift && key != sentinel) key |= (uint64_t)find_iter(iter_offsets, n_iters, i) << iter_shift;
         keys[i] = key;
         vals[i] = (uint32_t)i;
-    }
-}
-
-// iteration that owns transition idx: largest it with offsets[it] <= idx
-__device__ __forceinline__ int64_t find_iter(const int64_t* __restrict__ offsets, int64_t n_iters, int64_t idx) {
-    int64_t lo = 0, hi = n_iters;  // answer in [lo, hi)
-    while (hi - lo > 1) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (offsets[mid] <= idx) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-
-// Pass 1 (one thread per sorted position): gather the weight, mark where a new matrix cell starts
-// (cell head) and where a new (cell, iteration) group starts (sub head).
-//   flags[q] bit0 = sub head, bit1 = cell head.  Sentinel (dropped) transitions carry no flags.
-__global__ void __launch_bounds__(256)
-    flux_mark_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t N,
-                     uint64_t sentinel, const double* __restrict__ w, const int64_t* __restrict__ iter_offsets,
-                     int64_t n_iters, double* __restrict__ wv, int32_t* __restrict__ sub_head,
-                     int32_t* __restrict__ cell_head) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += stride) {
-        const uint64_t k = keys[q];
-        int sh = 0, ch = 0;
-        if (k != sentinel) {
-            const uint32_t idx = vals[q];
-            if (w) wv[q] = w[idx];
-            ch = (q == 0 || keys[q - 1] != k) ? 1 : 0;
-            sh = ch;
-            if (!ch && iter_offsets) {
-                // same cell as the previous element (which has a smaller transition index): a new group
-                // starts when the previous element belongs to an earlier iteration
-                const int64_t it = find_iter(iter_offsets, n_iters, (int64_t)idx);
-                sh = ((int64_t)vals[q - 1] < iter_offsets[it]) ? 1 : 0;
-            }
-        }
-        sub_head[q] = sh;
-        cell_head[q] = ch;
     }
 }
 
@@ -106,8 +81,9 @@ static constexpr int FM_TILE = FM_THREADS * FM_ITEMS;
 
 __global__ void __launch_bounds__(FM_THREADS)
     flux_mark_scan_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t N,
-                          uint64_t sentinel, const double* __restrict__ w, const int64_t* __restrict__ iter_offsets,
-                          int64_t n_iters, double* __restrict__ wv, int32_t* __restrict__ sub_head,
+                          uint64_t sentinel, uint64_t cell_mask, bool iter_in_key, const double* __restrict__ w,
+                          const int64_t* __restrict__ iter_offsets, int64_t n_iters, double* __restrict__ wv,
+                          int32_t* __restrict__ sub_head,
                           int32_t* __restrict__ cell_head, int32_t* __restrict__ sub_pos,
                           unsigned long long* __restrict__ tile_state, unsigned int* __restrict__ ticket,
                           int64_t* __restrict__ total_out, int32_t* __restrict__ err_count) {
@@ -126,12 +102,17 @@ __global__ void __launch_bounds__(FM_THREADS)
         sh[j] = ch[j] = 0;
         if (q < N) {
             const uint64_t k = keys[q];
-            if (k != sentinel) {
+            if ((k & cell_mask) != sentinel) {
                 const uint32_t idx = vals[q];
                 if (w) wv[q] = w[idx];
-                ch[j] = (q == 0 || keys[q - 1] != k) ? 1 : 0;
+                const uint64_t kp = q ? keys[q - 1] : ~k;
+                ch[j] = ((kp ^ k) & cell_mask) ? 1 : 0;
                 sh[j] = ch[j];
-                if (!ch[j] && iter_offsets) {
+                if (iter_in_key) {
+                    sh[j] = (kp != k) ? 1 : 0;          // cell or iteration differs
+                } else if (!ch[j] && iter_offsets) {
+                    // same cell as the previous element (which has a smaller transition index): a new group
+                    // starts when the previous element belongs to an earlier iteration
                     const int64_t it = find_iter(iter_offsets, n_iters, (int64_t)idx);
                     sh[j] = ((int64_t)vals[q - 1] < iter_offsets[it]) ? 1 : 0;
                 }
@@ -196,7 +177,8 @@ __global__ void __launch_bounds__(FM_THREADS)
 // Pass 2 (one thread per sub head): sum the weights of one (cell, iteration) group in segment order --
 // what scipy's coo_matrix -> dense does for that iteration's matrix.  Unit weights: the count, exactly.
 __global__ void __launch_bounds__(256)
-    flux_group_sum_kernel(const uint64_t* __restrict__ keys, int64_t N, uint64_t sentinel, const double* __restrict__ wv,
+    flux_group_sum_kernel(const uint64_t* __restrict__ keys, int64_t N, uint64_t sentinel, uint64_t cell_mask,
+                          const double* __restrict__ wv,
                           bool have_w, const int32_t* __restrict__ sub_head, const int32_t* __restrict__ sub_pos,
                           const int32_t* __restrict__ cell_head, double* __restrict__ group_sum,
                           uint8_t* __restrict__ group_is_cell_head, uint64_t* __restrict__ group_key) {
@@ -211,7 +193,7 @@ __global__ void __launch_bounds__(256)
             e = q + 1;
             // 4 loads in flight; the adds stay strictly sequential
             while (e + 4 <= N && !(sub_head[e] | sub_head[e + 1] | sub_head[e + 2] | sub_head[e + 3]) &&
-                   keys[e + 3] != sentinel) {
+                   (keys[e + 3] & cell_mask) != sentinel) {
                 const double a = wv[e], b = wv[e + 1], c = wv[e + 2], d = wv[e + 3];
                 part = __dadd_rn(part, a);
                 part = __dadd_rn(part, b);
@@ -219,18 +201,18 @@ __global__ void __launch_bounds__(256)
                 part = __dadd_rn(part, d);
                 e += 4;
             }
-            while (e < N && !sub_head[e] && keys[e] != sentinel) {
+            while (e < N && !sub_head[e] && (keys[e] & cell_mask) != sentinel) {
                 part = __dadd_rn(part, wv[e]);
                 ++e;
             }
         } else {
             e = q + 1;
-            while (e < N && !sub_head[e] && keys[e] != sentinel) ++e;
+            while (e < N && !sub_head[e] && (keys[e] & cell_mask) != sentinel) ++e;
             part = (double)(e - q);
         }
         group_sum[gidx] = part;
         group_is_cell_head[gidx] = (uint8_t)cell_head[q];
-        group_key[gidx] = keys[q];
+        group_key[gidx] = keys[q] & cell_mask;
     }
 }
 
@@ -395,8 +377,14 @@ extern "C" int mwe_flux_accumulate_f64(const int64_t* start, const int64_t* end,
     int64_t blocks = (N + 255) / 256;
     const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
+    // iteration id above the cell bits when both fit in 64 bits (always, for any realistic matrix)
+    // (above the last radix digit, not just above the cell: the sort must not see iteration bits)
+    int iter_shift = 0;
+    const int sorted_bits = ((key_bits + 7) / 8) * 8;
+    if (iter_offsets && sorted_bits + ceil_log2_u64((uint64_t)n_iters + 1) <= 63) iter_shift = sorted_bits;
+    const uint64_t cell_mask = iter_shift ? (((uint64_t)1 << iter_shift) - 1) : ~(uint64_t)0;
     flux_keys_kernel<<<(unsigned)blocks, 256, 0, s>>>(start, end, flag0, flag1, col0, col1, N, n_clusters, C, sentinel,
-                                                     keys, vals, err_count);
+                                                     iter_offsets, n_iters, iter_shift, keys, vals, err_count);
     MWE_CHECK_LAUNCH();
     uint64_t* ks;
     uint32_t* vs;
@@ -406,11 +394,12 @@ extern "C" int mwe_flux_accumulate_f64(const int64_t* start, const int64_t* end,
         const int64_t ntiles = (N + FM_TILE - 1) / FM_TILE;
         MWE_CHECK_CUDA(cudaMemsetAsync(tile_state, 0, (size_t)(ntiles + 1) * sizeof(unsigned long long), s));
         unsigned int* ticket = reinterpret_cast<unsigned int*>(tile_state + ntiles);
-        flux_mark_scan_kernel<<<(unsigned)ntiles, FM_THREADS, 0, s>>>(ks, vs, N, sentinel, w, iter_offsets, n_iters, wv, sub_head,
-                                                                      cell_head, pos, tile_state, ticket, n_groups, err_count);
+        flux_mark_scan_kernel<<<(unsigned)ntiles, FM_THREADS, 0, s>>>(ks, vs, N, sentinel, cell_mask, iter_shift != 0, w, iter_offsets,
+                                                                      n_iters, wv, sub_head, cell_head, pos, tile_state, ticket,
+                                                                      n_groups, err_count);
         MWE_CHECK_LAUNCH();
     }
-    flux_group_sum_kernel<<<(unsigned)blocks, 256, 0, s>>>(ks, N, sentinel, wv, w != nullptr, sub_head, pos, cell_head,
+    flux_group_sum_kernel<<<(unsigned)blocks, 256, 0, s>>>(ks, N, sentinel, cell_mask, wv, w != nullptr, sub_head, pos, cell_head,
                                                           group_sum, group_flag, group_key);
     MWE_CHECK_LAUNCH();
     if (coo_val) {
