@@ -373,6 +373,16 @@ def main():
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "fp64_tflops": 2 * N * 2.0 * cfg.k_per_bin * cfg.dim / (kernel_ms * 1e-3) / 1e12}
 
+    # DRAM bytes per launch of that kernel from the committed ncu capture of the same workload (None if none)
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "k1_dram_traffic.json")) as f:
+            entry = json.load(f).get(f"{cfg.name}/{roofline['kernel']}")
+        if entry:
+            roofline["traffic"] = entry["bytes"]
+            roofline["traffic_source"] = entry["source"]
+    except (OSError, ValueError):
+        pass
+
     # ---------------------------------------------------------------- e2e through the plugin API
     e2e = None
     if not args.no_e2e:

@@ -34,7 +34,7 @@ static constexpr size_t AS_SMEM_BUDGET_SMALL = 54 * 1024;   // four 4-warp CTAs 
 // ---- bucketing -----------------------------------------------------------------------------
 
 static constexpr int AS_SMEM_BINS = 2048;   // bins whose counters fit the shared-memory histogram
-static constexpr int AS_BK_ITEMS = 8;       // points per thread in the bucketing kernels
+static constexpr int AS_BK_ITEMS = 2;       // points per thread in the bucketing kernels (latency-bound: keep the grid wide)
 
 __global__ void __launch_bounds__(256)
     assign_count_kernel(const int32_t* __restrict__ bin, const uint8_t* __restrict__ flag, int64_t N, int32_t nbins,
@@ -117,22 +117,6 @@ __global__ void __launch_bounds__(256)
     __shared__ int32_t s_cnt[AS_SMEM_BINS];
     const bool use_smem = nbins <= AS_SMEM_BINS;
     const int64_t T = bin_offset[nbins];
-    if (tile_desc) {
-        // tile records for the resident-centre kernel: the bin of a tile by binary search over the tile prefix
-        const int32_t n_tiles = tile_prefix[nbins];
-        for (int32_t tile = blockIdx.x * 256 + threadIdx.x; tile < n_tiles; tile += gridDim.x * 256) {
-            int lo = 0, hi = nbins - 1;          // last bin with tile_prefix[bin] <= tile
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (tile_prefix[mid] <= tile) lo = mid; else hi = mid - 1;
-            }
-            const int32_t in_bin = (tile - tile_prefix[lo]) * tile_points;
-            const int32_t left = (bin_start[lo + 1] - bin_start[lo]) - in_bin;
-            const int64_t coff = bin_offset[lo];
-            tile_desc[tile] = make_int4(bin_start[lo] + in_bin, left < tile_points ? left : tile_points, (int32_t)coff,
-                                        (int32_t)(bin_offset[lo + 1] - coff));
-        }
-    }
     if (use_smem) {
         for (int b = threadIdx.x; b < nbins; b += 256) s_cnt[b] = 0;
         __syncthreads();
@@ -174,6 +158,22 @@ __global__ void __launch_bounds__(256)
         if (mybin[j] >= 0) {
             const int64_t i = base + j * 256 + threadIdx.x;
             perm[(use_smem ? s_cnt[mybin[j]] : 0) + rank[j]] = (int32_t)i;
+        }
+    }
+    if (tile_desc) {
+        // tile records for the resident-centre kernel: the bin of a tile by binary search over the tile prefix
+        const int32_t n_tiles = tile_prefix[nbins];
+        for (int32_t tile = blockIdx.x * 256 + threadIdx.x; tile < n_tiles; tile += gridDim.x * 256) {
+            int lo = 0, hi = nbins - 1;          // last bin with tile_prefix[bin] <= tile
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (tile_prefix[mid] <= tile) lo = mid; else hi = mid - 1;
+            }
+            const int32_t in_bin = (tile - tile_prefix[lo]) * tile_points;
+            const int32_t left = (bin_start[lo + 1] - bin_start[lo]) - in_bin;
+            const int64_t coff = bin_offset[lo];
+            tile_desc[tile] = make_int4(bin_start[lo] + in_bin, left < tile_points ? left : tile_points, (int32_t)coff,
+                                        (int32_t)(bin_offset[lo + 1] - coff));
         }
     }
 }

@@ -33,7 +33,12 @@ struct BinFlagParams {
     double target[BF_MAX_P][2];
 };
 
+// PP: compile-time pcoord_ndim for the common 1-D / 2-D progress coordinates (0 = read p.P at run time); the
+// generic body carries 8-way predicated loops that cost ~5x the instructions of the 1-D case.
+template <int PP>
 __global__ void __launch_bounds__(BF_THREADS) bin_flags_kernel(const BinFlagParams p) {
+    const int P = PP ? PP : p.P;
+    constexpr int MAXP = PP ? PP : BF_MAX_P;
     __shared__ int32_t s_count[BF_SMEM_BINS];
     __shared__ float s_bounds[BF_SMEM_BOUNDS];
     const bool use_smem = p.bin_count != nullptr && p.nbins <= BF_SMEM_BINS;
@@ -47,14 +52,14 @@ __global__ void __launch_bounds__(BF_THREADS) bin_flags_kernel(const BinFlagPara
     const float* bounds = smem_bounds ? s_bounds : p.mapper_data;
     const int64_t stride = (int64_t)gridDim.x * BF_THREADS;
     for (int64_t i = (int64_t)blockIdx.x * BF_THREADS + threadIdx.x; i < p.N; i += stride) {
-        double pc[BF_MAX_P];
+        double pc[MAXP];
 #pragma unroll
-        for (int d = 0; d < BF_MAX_P; ++d)
-            if (d < p.P) pc[d] = p.pcoord[i * p.P + d];
+        for (int d = 0; d < MAXP; ++d)
+            if (d < P) pc[d] = p.pcoord[i * P + d];
         bool in_basis = true, in_target = true;
 #pragma unroll
-        for (int d = 0; d < BF_MAX_P; ++d)
-            if (d < p.P) {
+        for (int d = 0; d < MAXP; ++d)
+            if (d < P) {
                 in_basis = in_basis && (pc[d] > p.basis[d][0]) && (pc[d] < p.basis[d][1]);
                 in_target = in_target && (pc[d] > p.target[d][0]) && (pc[d] < p.target[d][1]);
             }
@@ -63,8 +68,8 @@ __global__ void __launch_bounds__(BF_THREADS) bin_flags_kernel(const BinFlagPara
             int32_t index = 0;
             bool ok = true;
 #pragma unroll
-            for (int d = 0; d < BF_MAX_P; ++d)
-                if (d < p.P) {
+            for (int d = 0; d < MAXP; ++d)
+                if (d < P) {
                     const float x = (float)pc[d];  // westpa casts coordinates to float32
                     const float* b = bounds + p.starts[d];
                     const int nb = p.lens[d];
@@ -85,9 +90,9 @@ __global__ void __launch_bounds__(BF_THREADS) bin_flags_kernel(const BinFlagPara
             for (int32_t c = 0; c < p.nbins; ++c) {
                 float d2 = 0.f;
 #pragma unroll
-                for (int d = 0; d < BF_MAX_P; ++d)
-                    if (d < p.P) {
-                        const float diff = __fsub_rn((float)pc[d], p.mapper_data[(size_t)c * p.P + d]);
+                for (int d = 0; d < MAXP; ++d)
+                    if (d < P) {
+                        const float diff = __fsub_rn((float)pc[d], p.mapper_data[(size_t)c * P + d]);
                         d2 = __fadd_rn(d2, __fmul_rn(diff, diff));
                     }
                 if (c == 0 || d2 < best) { best = d2; besti = c; }
@@ -155,9 +160,13 @@ extern "C" int mwe_bin_flags_f64(const double* pcoord, int64_t N, int P, int map
     if (mapper_kind == MWE_MAPPER_RECTILINEAR) MWE_REQUIRE(prod == nbins, "bin_flags: nbins != product of per-dimension bins");
     if (mapper_kind != MWE_MAPPER_PRECOMPUTED) MWE_REQUIRE(mapper_data, "bin_flags: null mapper data");
     int64_t blocks = (N + BF_THREADS - 1) / BF_THREADS;
-    const int64_t cap = (int64_t)sm_count() * 8;
+    // latency-bound per point (one search per dimension): one point per thread until the grid is many waves deep
+    const int64_t cap = (int64_t)sm_count() * 32;
     if (blocks > cap) blocks = cap;
-    bin_flags_kernel<<<(unsigned)blocks, BF_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (P == 1) bin_flags_kernel<1><<<(unsigned)blocks, BF_THREADS, 0, st>>>(p);
+    else if (P == 2) bin_flags_kernel<2><<<(unsigned)blocks, BF_THREADS, 0, st>>>(p);
+    else bin_flags_kernel<0><<<(unsigned)blocks, BF_THREADS, 0, st>>>(p);
     MWE_CHECK_LAUNCH();
     return MWE_OK;
 }
