@@ -63,6 +63,13 @@ MWE_API const char* mwe_last_error(void);
 /* number of SMs of the current device (grid sizing is done inside the library) */
 MWE_API int mwe_device_sm_count(void);
 
+/* Page-lock / unlock a host range the caller owns (cudaHostRegister / cudaHostUnregister), so that the
+ * per-iteration coordinate arrays a model already holds (msm_we/_hamsm/_data.py:557-618 hands them out as numpy
+ * arrays) can be copied to the device asynchronously at link speed without a staging copy.  Returns MWE_OK, or
+ * MWE_E_CUDA when the range cannot be registered (already registered, overlapping, over the lock limit). */
+MWE_API int mwe_host_register(void* ptr, size_t bytes);
+MWE_API int mwe_host_unregister(void* ptr);
+
 /* Measurement hook: CUDA events (cudaEvent_t as void*, nullable) that the following calls on this
  * host thread record immediately before / after their dominant kernel (K1: the DMMA assignment
  * kernel), on the stream the kernel is launched on.  Pass NULL, NULL to switch it off. */

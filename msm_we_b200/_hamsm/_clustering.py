@@ -342,43 +342,62 @@ class ClusteringMixin:
         inflight = []   # (chunk, n, labels_host, bins_host, flags_host, done_event)
 
         def stage(ci, chunk):
+            from .._pinning import PINS
+
             n = sum(s for _, s in chunk)
             slot = slots[ci % 2]
             if slot["event"] is not None:
                 slot["event"].synchronize()          # the H2D that last read this buffer has finished
+            # pinned staging: pcoords always (small), feature rows only for iterations whose arrays cannot be
+            # page-locked in place
             need = 2 * n * (D + P)
             if slot["host"] is None or slot["host"].numel() < need:
                 slot["host"] = torch.empty(need, dtype=torch.float64, pin_memory=True)
             host = slot["host"]
-            hx = host[: 2 * n * D].view(2 * n, D).numpy()
-            hp = host[2 * n * D: need].view(2 * n, P).numpy()
+            hx_t = host[: 2 * n * D].view(2 * n, D)
+            hp_t = host[2 * n * D: need].view(2 * n, P)
+            hx, hp = hx_t.numpy(), hp_t.numpy()
+            X = torch.empty((2 * n, D), dtype=torch.float64, device=dev.device)
             pool = _staging_pool()
             featurise, transform = self.processCoordinates, self.coordinates.transform
 
-            def fill(it, s, pos):
-                # one iteration: featurise + transform parents and children straight into the pinned rows
+            def fill(dst, feat):
+                np.copyto(dst, feat)
+
+            pos, jobs, staged = 0, [], []
+            for it, s in chunk:
                 parent_coords, child_coords = self.iter_coordinate_pair(it)
                 rec = self._record(it)
-                np.copyto(hx[pos:pos + s], transform(featurise(parent_coords)))
-                np.copyto(hx[n + pos:n + pos + s], transform(featurise(child_coords)))
                 hp[pos:pos + s] = rec.pcoord0[:, :P]
                 hp[n + pos:n + pos + s] = rec.pcoord1[:, :P]
-
-            pos, jobs = 0, []
-            for it, s in chunk:
-                if pool is None:
-                    fill(it, s, pos)
-                else:
-                    jobs.append(pool.submit(fill, it, s, pos))
+                for off, coords in ((pos, parent_coords), (n + pos, child_coords)):
+                    feat = transform(featurise(coords))
+                    if isinstance(feat, np.ndarray) and feat.shape == (s, D) and PINS.ensure(feat):
+                        # the model's own array is page-locked: straight to the device at link speed
+                        X[off:off + s].copy_(torch.from_numpy(feat), non_blocking=True)
+                    else:
+                        # featurised / projected on the fly (or not lockable): stage through the pinned rows
+                        if pool is None:
+                            fill(hx[off:off + s], feat)
+                        else:
+                            jobs.append(pool.submit(fill, hx[off:off + s], feat))
+                        staged.append((off, s))
                 pos += s
             for j in jobs:
                 j.result()
-            d = host[:need].to(dev.device, non_blocking=True)
+            staged.sort()
+            k = 0
+            while k < len(staged):                   # one copy per run of adjacent staged row ranges
+                lo, hi = staged[k][0], staged[k][0] + staged[k][1]
+                while k + 1 < len(staged) and staged[k + 1][0] == hi:
+                    k += 1
+                    hi = staged[k][0] + staged[k][1]
+                X[lo:hi].copy_(hx_t[lo:hi], non_blocking=True)
+                k += 1
+            Pc = hp_t.to(dev.device, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(stream)
             slot["event"] = ev
-            X = d[: 2 * n * D].view(2 * n, D)
-            Pc = d[2 * n * D:].view(2 * n, P)
             labels, bins, flags = dev.predict(X, Pc, pcoord_host=hp)
             lh = torch.empty(2 * n, dtype=torch.int64, pin_memory=True)
             bh = torch.empty(2 * n, dtype=torch.int32, pin_memory=True)

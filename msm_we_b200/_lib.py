@@ -31,6 +31,8 @@ SIGNATURES = {
     "mwe_abi_version": (_int, []),
     "mwe_last_error": (C.c_char_p, []),
     "mwe_device_sm_count": (_int, []),
+    "mwe_host_register": (_int, [_p, _sz]),
+    "mwe_host_unregister": (_int, [_p]),
     "mwe_set_timing_events": (_int, [_p, _p]),
     "mwe_bin_flags_f64": (_int, [_p, _i64, _int, _int, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "mwe_assign_workspace_bytes": (_sz, [_i64, _i32]),

@@ -5,8 +5,8 @@
 // order-deterministic: inside one key the values stay in input order, so the segmented fp64 sums
 // that follow always add in the same sequence.
 //
-// Per pass, three launches over a FIXED grid of G CTAs, each owning a contiguous span of tiles:
-//   hist    : per-CTA digit histogram                  (reads keys)
+// Launches over a FIXED grid of G CTAs, each owning a contiguous span of tiles:
+//   hist    : per-CTA digit histogram (first pass only; every scatter counts the next pass's digits)
 //   scan    : exclusive scan over [digit][cta]         (one CTA, G*256 counters)
 //   scatter : per tile, warp-level match ranking -> tile-local reorder in shared memory ->
 //             coalesced run-wise stores                 (reads + writes keys and values)
@@ -24,10 +24,15 @@ static constexpr int RS_RADIX = 256;
 static constexpr int RS_WARPS = RS_THREADS / 32;
 static constexpr int RS_FUSED_SCAN_MAX_G = 160;   // up to here the scatter kernel scans the histograms itself
 
+// Only the first pass runs this kernel: every scatter pass counts the NEXT pass's per-CTA digits while it stores
+// (it knows where each element lands), so later passes need no histogram launch.  The later histograms are zeroed
+// here, each CTA its own rows.
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t* __restrict__ keys, int64_t N, int shift,
-                                                            int tiles_per_cta, uint32_t* __restrict__ hist) {
+                                                            int tiles_per_cta, uint32_t* __restrict__ hist, int later_passes,
+                                                            size_t hist_stride) {
     __shared__ uint32_t s_hist[RS_RADIX];
     s_hist[threadIdx.x] = 0;
+    for (int q = 1; q <= later_passes; ++q) hist[q * hist_stride + (size_t)blockIdx.x * RS_RADIX + threadIdx.x] = 0;
     __syncthreads();
     const int64_t begin = (int64_t)blockIdx.x * tiles_per_cta * RS_TILE;
     int64_t end = begin + (int64_t)tiles_per_cta * RS_TILE;
@@ -58,7 +63,8 @@ __global__ void __launch_bounds__(RS_RADIX) rs_scan_kernel(uint32_t* __restrict_
 __global__ void __launch_bounds__(RS_THREADS)
     rs_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                       uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t N, int shift,
-                      int tiles_per_cta, const uint32_t* __restrict__ offsets, int fused_scan) {
+                      int tiles_per_cta, const uint32_t* __restrict__ offsets, int fused_scan,
+                      uint32_t* __restrict__ next_hist) {
     __shared__ uint32_t s_base[RS_RADIX];
     __shared__ uint32_t s_warp_cnt[RS_WARPS][RS_RADIX];
     __shared__ uint32_t s_tile_excl[RS_RADIX];
@@ -74,10 +80,16 @@ __global__ void __launch_bounds__(RS_THREADS)
         // (offsets[c][d] = count) instead of waiting for a separate one-CTA scan kernel
         uint32_t below = 0, total = 0;
         const int G = (int)gridDim.x;
-        for (int c = 0; c < G; ++c) {
-            const uint32_t v = offsets[(size_t)c * RS_RADIX + tid];
-            if (c < (int)blockIdx.x) below += v;
-            total += v;
+        // 32 independent loads in flight per thread: the loop is pure L2 latency otherwise
+        for (int c0 = 0; c0 < G; c0 += 32) {
+            uint32_t v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = (c0 + i < G) ? offsets[(size_t)(c0 + i) * RS_RADIX + tid] : 0u;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (c0 + i < (int)blockIdx.x) below += v[i];
+                total += v[i];
+            }
         }
         int blk_total;
         const uint32_t digit_base = (uint32_t)block_excl_scan_256((int)total, scratch, &blk_total);
@@ -86,7 +98,8 @@ __global__ void __launch_bounds__(RS_THREADS)
         s_base[tid] = offsets[(size_t)blockIdx.x * RS_RADIX + tid];
     }
 
-    const int64_t span_begin = (int64_t)blockIdx.x * tiles_per_cta * RS_TILE;
+    const uint32_t span = (uint32_t)tiles_per_cta * RS_TILE;
+    const int64_t span_begin = (int64_t)blockIdx.x * span;
     for (int t = 0; t < tiles_per_cta; ++t) {
         const int64_t tile_base = span_begin + (int64_t)t * RS_TILE;
         if (tile_base >= N) break;
@@ -159,6 +172,8 @@ __global__ void __launch_bounds__(RS_THREADS)
                 const uint32_t g = s_base[d] + ((uint32_t)p - s_tile_excl[d]);
                 keys_out[g] = kk;
                 vals_out[g] = s_vals[p];
+                // per-CTA digit histogram of the next pass: element g belongs to CTA g / span there
+                if (next_hist) atomicAdd(&next_hist[(size_t)(g / span) * RS_RADIX + ((uint32_t)(kk >> (shift + 8)) & 0xffu)], 1u);
             }
         }
         __syncthreads();
@@ -182,7 +197,7 @@ size_t sort_workspace_bytes(int64_t N) {
     size_t b = 0;
     b += align_up((size_t)N * sizeof(uint64_t), 256);
     b += align_up((size_t)N * sizeof(uint32_t), 256);
-    b += align_up((size_t)sm_count() * 4 * RS_RADIX * sizeof(uint32_t), 256);
+    b += 8 * align_up((size_t)sm_count() * 4 * RS_RADIX * sizeof(uint32_t), 256);   // one histogram per pass
     return b + 1024;
 }
 
@@ -200,7 +215,8 @@ int sort_pairs(uint64_t* keys, uint32_t* vals, int64_t N, int key_bits, void* ws
     Carver cv(ws, ws_bytes);
     uint64_t* keys_alt = cv.take<uint64_t>((size_t)N);
     uint32_t* vals_alt = cv.take<uint32_t>((size_t)N);
-    uint32_t* hist = cv.take<uint32_t>((size_t)sm_count() * 4 * RS_RADIX);
+    const size_t hist_stride = align_up((size_t)sm_count() * 4 * RS_RADIX * sizeof(uint32_t), 256) / sizeof(uint32_t);
+    uint32_t* hist = cv.take<uint32_t>(8 * hist_stride);
     int G, tpc;
     plan(N, &G, &tpc);
     uint64_t* kin = keys;
@@ -208,12 +224,14 @@ int sort_pairs(uint64_t* keys, uint32_t* vals, int64_t N, int key_bits, void* ws
     uint64_t* kout = keys_alt;
     uint32_t* vout = vals_alt;
     const int passes = (key_bits + 7) / 8;
+    const int fused = G <= RS_FUSED_SCAN_MAX_G;
+    rs_hist_kernel<<<G, RS_THREADS, 0, stream>>>(kin, N, 0, tpc, hist, passes - 1, hist_stride);
     for (int p = 0; p < passes; ++p) {
         const int shift = p * 8;
-        const int fused = G <= RS_FUSED_SCAN_MAX_G;
-        rs_hist_kernel<<<G, RS_THREADS, 0, stream>>>(kin, N, shift, tpc, hist);
-        if (!fused) rs_scan_kernel<<<1, RS_RADIX, 0, stream>>>(hist, G);
-        rs_scatter_kernel<<<G, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, N, shift, tpc, hist, fused);
+        uint32_t* hp = hist + (size_t)p * hist_stride;
+        if (!fused) rs_scan_kernel<<<1, RS_RADIX, 0, stream>>>(hp, G);
+        rs_scatter_kernel<<<G, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, N, shift, tpc, hp, fused,
+                                                        p + 1 < passes ? hp + hist_stride : nullptr);
         MWE_CHECK_LAUNCH();
         uint64_t* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;

@@ -57,6 +57,28 @@ extern "C" int mwe_abi_version(void) { return MWE_ABI_VERSION; }
 extern "C" const char* mwe_last_error(void) { return mwe::g_last_error; }
 extern "C" int mwe_device_sm_count(void) { return mwe::sm_count(); }
 
+extern "C" int mwe_host_register(void* ptr, size_t bytes) {
+    MWE_REQUIRE(ptr != nullptr && bytes > 0, "host_register: empty range");
+    const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();   // not sticky, but it must not surface at the next launch check
+        mwe::set_last_error("host_register: %s", cudaGetErrorString(e));
+        return MWE_E_CUDA;
+    }
+    return MWE_OK;
+}
+
+extern "C" int mwe_host_unregister(void* ptr) {
+    MWE_REQUIRE(ptr != nullptr, "host_unregister: null pointer");
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        mwe::set_last_error("host_unregister: %s", cudaGetErrorString(e));
+        return MWE_E_CUDA;
+    }
+    return MWE_OK;
+}
+
 extern "C" int mwe_divide_f64(double* buf, int64_t count, double divisor, void* stream) {
     MWE_REQUIRE(count >= 0, "divide: negative count");
     if (count == 0) return MWE_OK;
