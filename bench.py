@@ -307,7 +307,13 @@ def main():
     n_clusters = cfg.n_clusters
     M = n_clusters + 2
     X, pc, w, offs = data["X"], data["pcoord"], data["weights"], data["iter_offsets"]
-    dense = torch.zeros((M, M), dtype=torch.float64, device=dev)
+    # N > 1: the per-rank matrix lives in a buffer every rank can map; one kernel per rank does the all-reduce and
+    # the "/ nI" over NVLink peer memory (NCCL all-reduce + divide when the ranks cannot map each other)
+    reducer = None
+    if world > 1:
+        from msm_we_b200.distributed import PeerFluxAllreduce
+        reducer = PeerFluxAllreduce.create((M, M), dev)
+    dense = reducer.partial if reducer is not None else torch.zeros((M, M), dtype=torch.float64, device=dev)
     labels = torch.empty(2 * N, dtype=torch.int64, device=dev)
     l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     n_iters_total = cfg.n_iters * world
@@ -324,7 +330,9 @@ def main():
                             divisor=float(n_iters_total) if world == 1 else 0.0, labels_out=labels, path=path)
         if ev is not None:
             _lib.set_timing_events(None, None)
-        if world > 1:
+        if reducer is not None:
+            reducer.reduce(float(n_iters_total))
+        elif world > 1:
             dist.all_reduce(dense)
             ops.divide_(dense, float(n_iters_total))
 
@@ -359,6 +367,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     engine.check_errors()
+    if reducer is not None:
+        reducer.errors.check()
     frames_per_step = N * world
     value = frames_per_step * args.steps / (total_ms * 1e-3)
 
@@ -406,6 +416,8 @@ def main():
                                    f"{cfg.n_bins} bins x {cfg.k_per_bin} clusters/bin, fp64 (per GPU; iteration-range "
                                    f"sharded, flux all-reduced)",
                        "frames_per_step": frames_per_step, "l2": "flushed between timed steps (256 MiB memset)",
+                       "exchange": ("none (1 GPU)" if world == 1 else "one peer-memory kernel per rank (rank-order sum + / nI over NVLink)"
+                                    if reducer is not None else "NCCL all-reduce + divide"),
                        "precision_path": ("tcgen05 split-TF32 candidate pass + fp64 re-check of near-ties (labels identical "
                                           "to the fp64 path)") if path == _lib.ASSIGN_TF32X3 else "fp64 DMMA"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks.summary(),
@@ -413,6 +425,9 @@ def main():
         }
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
+        if reducer is not None:
+            reducer.close()
         dist.destroy_process_group()
     return 0
 

@@ -212,6 +212,24 @@ MWE_API size_t mwe_sort_workspace_bytes(int64_t N);
 MWE_API int mwe_sort_pairs_u64_u32(uint64_t* keys, uint32_t* vals, int64_t N, int key_bits, void* workspace,
                            size_t workspace_bytes, void* stream);
 
+/* ---- multi-GPU exchange step of the flux path, over NVLink peer memory -------------------------
+ * Replaces the driver-side sum of the per-worker iteration matrices and the final "/ nI"
+ * (msm_we/_hamsm/_fluxmatrix.py:311-327, :342) when WE iterations are sharded over one process per GPU.
+ * Setup (once): every rank allocates its partial-sum buffer, result buffer ([count] f64 each) and flag words
+ * ([2*world] u32, zero) with mwe_device_malloc, exports them (mwe_ipc_export -> 64-byte handle), sends the handles
+ * to the other ranks by any transport, and opens theirs (mwe_ipc_open).  Per call: all ranks call
+ * mwe_flux_peer_allreduce_f64 with the same `epoch` (1, 2, 3, ...), host arrays of the `world` device pointers
+ * (own buffers at index `rank`), and a zeroed u32 `cta_counter`.  On return (stream order) outs[rank] holds
+ * (partial_0 + partial_1 + ...) / divisor, summed in rank order, on every rank. */
+MWE_API int mwe_device_malloc(size_t bytes, void** out);
+MWE_API int mwe_device_free(void* ptr);
+MWE_API int mwe_ipc_export(void* device_ptr, unsigned char* handle64);
+MWE_API int mwe_ipc_open(const unsigned char* handle64, void** out);
+MWE_API int mwe_ipc_close(void* ptr);
+MWE_API int mwe_flux_peer_allreduce_f64(const void* const* partials, void* const* outs, void* const* flags, int rank,
+                                        int world, int64_t count, double divisor, uint32_t epoch, void* cta_counter,
+                                        int32_t* err_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

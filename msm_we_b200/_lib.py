@@ -31,6 +31,12 @@ SIGNATURES = {
     "mwe_abi_version": (_int, []),
     "mwe_last_error": (C.c_char_p, []),
     "mwe_device_sm_count": (_int, []),
+    "mwe_device_malloc": (_int, [_sz, _p]),
+    "mwe_device_free": (_int, [_p]),
+    "mwe_ipc_export": (_int, [_p, _p]),
+    "mwe_ipc_open": (_int, [_p, _p]),
+    "mwe_ipc_close": (_int, [_p]),
+    "mwe_flux_peer_allreduce_f64": (_int, [_p, _p, _p, _int, _int, _i64, C.c_double, C.c_uint32, _p, _p, _p]),
     "mwe_host_register": (_int, [_p, _sz]),
     "mwe_host_unregister": (_int, [_p]),
     "mwe_set_timing_events": (_int, [_p, _p]),

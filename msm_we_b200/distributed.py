@@ -33,11 +33,31 @@ def partition_iterations(iters, seg_counts, world_size):
     return [iters[bounds[r]:bounds[r + 1]] for r in range(world_size)]
 
 
+_PEER_REDUCERS = {}
+
+
+def peer_reducer(shape, device, group=None):
+    """Cached ``PeerFluxAllreduce`` for this matrix shape (None when the ranks cannot map each other's memory)."""
+    key = (tuple(shape), str(device), id(group))
+    if key not in _PEER_REDUCERS:
+        _PEER_REDUCERS[key] = PeerFluxAllreduce.create(shape, device, group)
+    return _PEER_REDUCERS[key]
+
+
 def allreduce_flux(local_sum, n_iters_total, group=None):
     """all-reduce(sum) of the per-rank un-normalised flux matrix, then the reference's ``/ nI``
-    (_fluxmatrix.py:342).  ``local_sum`` is a torch tensor (CUDA -> NCCL, CPU -> gloo), reduced in place."""
+    (_fluxmatrix.py:342).  CUDA tensors of ranks that can map each other's memory go through the one-kernel
+    peer-memory exchange (rank-order sum); otherwise NCCL (CUDA) / gloo (CPU) all-reduce in place."""
     import torch.distributed as dist
 
+    if local_sum.is_cuda and n_iters_total != 0 and dist.is_available() and dist.is_initialized() \
+            and dist.get_world_size(group) > 1:
+        red = peer_reducer(local_sum.shape, local_sum.device, group)
+        if red is not None:
+            red.partial.copy_(local_sum)
+            out = red.reduce(float(n_iters_total))
+            red.errors.check()
+            return out.clone()
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(local_sum, op=dist.ReduceOp.SUM, group=group)
     if n_iters_total == 0:
@@ -75,3 +95,122 @@ def get_fluxMatrix_sharded(model, n_lag=0, first_iter=1, last_iter=None, iters_t
     out = allreduce_flux(local, len(iters_to_use), group)
     model.fluxMatrixRaw = out.cpu().numpy()
     return model.fluxMatrixRaw
+
+
+class _RawDeviceBuffer:
+    """cudaMalloc'd memory (so that its CUDA IPC handle maps exactly this buffer) viewed as a torch tensor."""
+
+    def __init__(self, nbytes, typestr, shape):
+        import ctypes as C
+
+        from . import _lib
+
+        p = C.c_void_p()
+        _lib.check(_lib.lib.mwe_device_malloc(int(nbytes), C.byref(p)), "mwe_device_malloc")
+        self.ptr = p.value
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (self.ptr, False), "version": 2}
+
+    def free(self):
+        from . import _lib
+
+        if self.ptr:
+            _lib.lib.mwe_device_free(self.ptr)
+            self.ptr = None
+
+
+class PeerFluxAllreduce:
+    """The exchange step of the sharded flux path as ONE kernel per rank over NVLink peer memory
+    (csrc/peer_reduce.cu): ``out = (partial_0 + partial_1 + ...) / divisor`` on every rank, summed in rank order
+    (= iteration order, ranks hold contiguous iteration blocks), instead of NCCL all-reduce + a divide launch.
+
+    ``partial`` is the tensor the local K3 launches accumulate into (zero it, run the step, call ``reduce``);
+    ``out`` holds the result afterwards.  Needs one process per GPU on one node with peer access between all of
+    them; ``PeerFluxAllreduce.create`` returns None when that is not available and the caller keeps the NCCL path.
+    Handles travel once, through ``torch.distributed`` object collectives."""
+
+    def __init__(self, shape, rank, world, device, group=None):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+
+        self.rank, self.world, self.device, self.shape = rank, world, device, tuple(shape)
+        self.count = int(np.prod(self.shape))
+        self.epoch = 0
+        self._bufs = [_RawDeviceBuffer(self.count * 8, "<f8", self.shape), _RawDeviceBuffer(self.count * 8, "<f8", self.shape),
+                      _RawDeviceBuffer(2 * world * 4 + 4, "<u4", (2 * world + 1,))]
+        self.partial = torch.as_tensor(self._bufs[0], device=device)
+        self.out = torch.as_tensor(self._bufs[1], device=device)
+        self._flags = self._bufs[2]
+        handles = []
+        for b in self._bufs:
+            h = (C.c_ubyte * 64)()
+            _lib.check(_lib.lib.mwe_ipc_export(b.ptr, h), "mwe_ipc_export")
+            handles.append(bytes(h))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, handles, group=group)
+        self._opened = []
+        ptrs = [[0] * world for _ in range(3)]
+        for r in range(world):
+            for k in range(3):
+                if r == rank:
+                    ptrs[k][r] = self._bufs[k].ptr
+                else:
+                    p = C.c_void_p()
+                    hb = (C.c_ubyte * 64).from_buffer_copy(gathered[r][k])
+                    _lib.check(_lib.lib.mwe_ipc_open(hb, C.byref(p)), "mwe_ipc_open")
+                    self._opened.append(p.value)
+                    ptrs[k][r] = p.value
+        arr = C.c_void_p * world
+        self._partials, self._outs, self._flagps = arr(*ptrs[0]), arr(*ptrs[1]), arr(*ptrs[2])
+        self._counter = self._bufs[2].ptr + 2 * world * 4      # the spare u32 behind the flags
+        from . import ops
+
+        self.errors = ops.DeviceErrors(device)
+
+    @classmethod
+    def create(cls, shape, device, group=None):
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()):
+            return None
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world < 2 or world > 16:
+            return None
+        ok = True
+        try:
+            obj = cls(shape, rank, world, device, group)
+        except Exception:          # no peer access / IPC between these processes: NCCL path
+            obj, ok = None, False
+        flags = [None] * world
+        dist.all_gather_object(flags, ok, group=group)
+        if not all(flags):
+            if obj is not None:
+                obj.close()
+            return None
+        return obj
+
+    def reduce(self, divisor=0.0):
+        """All ranks must call this the same number of times.  Stream-ordered; returns ``self.out``."""
+        import torch
+
+        from . import _lib
+
+        self.epoch += 1
+        _lib.check(_lib.lib.mwe_flux_peer_allreduce_f64(self._partials, self._outs, self._flagps, self.rank, self.world,
+                                                        self.count, float(divisor), self.epoch, self._counter,
+                                                        self.errors.counts.data_ptr(),
+                                                        torch.cuda.current_stream().cuda_stream),
+                   "mwe_flux_peer_allreduce_f64")
+        return self.out
+
+    def close(self):
+        from . import _lib
+
+        for p in self._opened:
+            _lib.lib.mwe_ipc_close(p)
+        self._opened = []
+        for b in self._bufs:
+            b.free()

@@ -281,3 +281,25 @@ def test_hotpath_step_matches_separate_kernels_and_oracle():
     assert np.array_equal(lab[n:], np.concatenate(model.dtrajs))
     assert np.array_equal(lab[:n], np.concatenate([np.asarray(p)[:, 0] for p in model.pair_dtrajs]))
     assert np.array_equal(dense.cpu().numpy(), model.fluxMatrixRaw)
+
+
+@pytest.mark.gpu
+def test_peer_memory_flux_allreduce_two_gpus():
+    """The one-kernel exchange step (csrc/peer_reduce.cu) on 2 GPUs of one node: every rank ends with exactly the
+    rank-order sum divided by nI (numpy on the gathered partials), and agrees with NCCL to rounding.  Skipped on
+    single-GPU boxes; `gpurun --gpus 2 -- python -m pytest tests -m gpu -k peer` runs it."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "peer_reduce_test.py")],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "peer path available: True" in out.stdout
+    assert "values identical on all ranks: True" in out.stdout
