@@ -65,8 +65,8 @@ __global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_ker
     // Columns [D, 8*ceil(D/8)) of every point and centre row are read by the k loop but never written by a copy:
     // zero them once.  Nothing else needs initialising: rows of a short group / centre rows past the bin's count
     // only feed accumulator rows / columns that are never read (rows and columns of the product are independent).
-    if (p.D != xld - 4) {
-        const int npad = xld - 4 - p.D;
+    if (p.D != xld - 8) {
+        const int npad = xld - 8 - p.D;
         const int nrows_all = 2 * KP + nbufs * AR_GROUP;          // sC rows, then (after sQ) the buffer rows
         for (int e = threadIdx.x; e < nrows_all * npad; e += blockDim.x) {
             const int r = e / npad, c = p.D + (e - r * npad);
@@ -258,12 +258,18 @@ __global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_ker
             int32_t out_pt[2];
             out_pt[0] = (g < nrows) ? meta[g] : -1;
             out_pt[1] = (g + 8 < nrows) ? meta[g + 8] : -1;
-            const double* xa0 = bufs + ((size_t)b * AR_GROUP + g) * xld + t;
+            // Fragment addressing: lane (g, t) reads the 16-byte pair of columns {8p + 2t, 8p + 2t + 1} of its rows
+            // with ONE LDS.128 and feeds the first to k-step 2p and the second to k-step 2p + 1 -- the dot product
+            // is summed in a permuted column order (the same permutation for points and centres), which the
+            // candidate pass may do (see the note on evaluation order below); row stride = 8 mod 16 doubles keeps
+            // the quarter-warp phases of LDS.128 conflict-free.
+            const double* xa0 = bufs + ((size_t)b * AR_GROUP + g) * xld + 2 * t;
             const double* xa1 = xa0 + 8 * xld;
-            const double* cb0 = sC + ((size_t)cbuf * KP + g) * xld + t;
+            const double* cb0 = sC + ((size_t)cbuf * KP + g) * xld + 2 * t;
             // Accumulators start at -||c_j||^2/2, so after the k loop acc = x.c_j - ||c_j||^2/2 = -score_j/2 and the
-            // fold needs no fp64 arithmetic.  This is NOT the reference's evaluation order (dot product from 0, then
-            // one fma with ||c||^2): the two differ by < D u cmax (cmax + 2||x||), a quarter of the tie band, and the
+            // fold needs no fp64 arithmetic.  This is NOT the reference's evaluation order (dot product from 0 in
+            // column order, then one fma with ||c||^2; here also columns 0,2,4,6 before 1,3,5,7 inside every block
+            // of 8): any two orders differ by < D u cmax (cmax + 2||x||), a quarter of the tie band, and the
             // filter below only trusts gaps of two tie bands, so everything it accepts has the reference's argmin;
             // everything else is re-evaluated in the reference's order by assign_recheck_kernel.
             double acc[2][NT][2];
@@ -279,17 +285,25 @@ __global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_ker
                 }
             }
             uint32_t xhi[2] = {0u, 0u};
-#pragma unroll 4
-            for (int ks = 0; ks < nks; ++ks) {
-                const double a0 = xa0[ks * 4];
-                const double a1 = xa1[ks * 4];
-                xhi[0] = max(xhi[0], (uint32_t)__double2hiint(a0) & 0x7fffffffu);   // bound of |x_k| (feeds the tie tolerance)
-                xhi[1] = max(xhi[1], (uint32_t)__double2hiint(a1) & 0x7fffffffu);
+#pragma unroll 2
+            for (int kp = 0; kp < (nks >> 1); ++kp) {
+                const double2 a0 = *reinterpret_cast<const double2*>(xa0 + kp * 8);
+                const double2 a1 = *reinterpret_cast<const double2*>(xa1 + kp * 8);
+                // bound of |x_k| (feeds the tie tolerance)
+                xhi[0] = max(xhi[0], max((uint32_t)__double2hiint(a0.x) & 0x7fffffffu, (uint32_t)__double2hiint(a0.y) & 0x7fffffffu));
+                xhi[1] = max(xhi[1], max((uint32_t)__double2hiint(a1.x) & 0x7fffffffu, (uint32_t)__double2hiint(a1.y) & 0x7fffffffu));
+                double2 bv[NT];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) bv[nt] = *reinterpret_cast<const double2*>(cb0 + (size_t)nt * 8 * xld + kp * 8);
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
-                    const double bv = cb0[(size_t)nt * 8 * xld + ks * 4];
-                    dmma8x8x4(acc[0][nt][0], acc[0][nt][1], a0, bv);
-                    dmma8x8x4(acc[1][nt][0], acc[1][nt][1], a1, bv);
+                    dmma8x8x4(acc[0][nt][0], acc[0][nt][1], a0.x, bv[nt].x);
+                    dmma8x8x4(acc[1][nt][0], acc[1][nt][1], a1.x, bv[nt].x);
+                }
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    dmma8x8x4(acc[0][nt][0], acc[0][nt][1], a0.y, bv[nt].y);
+                    dmma8x8x4(acc[1][nt][0], acc[1][nt][1], a1.y, bv[nt].y);
                 }
             }
 
@@ -364,7 +378,7 @@ static bool resident_plan(int D, int32_t max_k, bool vec2, ResidentPlan* pl) {
     pl->nt = max_k <= 16 ? 2 : max_k <= 24 ? 3 : max_k <= 32 ? 4 : max_k <= 48 ? 6 : 8;
     pl->nw = pl->nt <= 3 ? 16 : pl->nt == 4 ? 14 : 12;
     if (const char* e = getenv("MWE_ASSIGN_NW")) { if (pl->nt == 3 && (atoi(e) == 18 || atoi(e) == 20)) pl->nw = atoi(e); }   // tuning knob
-    pl->xld = ((D + 7) / 8) * 8 + 4;
+    pl->xld = ((D + 7) / 8) * 8 + 8;      // 8 mod 16 doubles: conflict-free LDS.128 fragment loads
     const size_t kp = (size_t)pl->nt * 8;
     const size_t fixed = (2 * kp * pl->xld + 2 * kp) * sizeof(double) + sizeof(ResShared) + 128;
     const size_t buf_bytes = (size_t)AR_GROUP * pl->xld * sizeof(double);
@@ -394,7 +408,7 @@ static int launch_resident(const AssignParams& p, const ResidentPlan& pl, int64_
     cudaEvent_t ev0, ev1;
     timing_events(&ev0, &ev1);
     if (ev0) MWE_CHECK_CUDA(cudaEventRecord(ev0, stream));
-    assign_dmma_resident_kernel<NT, NW><<<(unsigned)grid, (NW + AR_NP) * 32, pl.smem, stream>>>(p, pl.nbufs, pl.xld, (pl.xld - 4) / 4);
+    assign_dmma_resident_kernel<NT, NW><<<(unsigned)grid, (NW + AR_NP) * 32, pl.smem, stream>>>(p, pl.nbufs, pl.xld, (pl.xld - 8) / 4);
     MWE_CHECK_LAUNCH();
     if (ev1) MWE_CHECK_CUDA(cudaEventRecord(ev1, stream));
     return MWE_OK;
