@@ -421,7 +421,7 @@ def main():
                        "precision_path": ("tcgen05 split-TF32 candidate pass + fp64 re-check of near-ties (labels identical "
                                           "to the fp64 path)") if path == _lib.ASSIGN_TF32X3 else "fp64 DMMA"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks.summary(),
-            "gpu_launches": LAUNCHES_PER_STEP_STATIC(cfg) * args.steps,
+            "gpu_launches": LAUNCHES_PER_STEP_STATIC(cfg, path == _lib.ASSIGN_TF32X3) * args.steps,
         }
         print(json.dumps(line))
     if world > 1:
@@ -432,13 +432,19 @@ def main():
     return 0
 
 
-def LAUNCHES_PER_STEP_STATIC(cfg):
-    """Kernels of ours per step, counted from the launch sequences in csrc/: K0 (1) + K1 (count, scan, scatter,
-    dmma, re-check = 5) + K3 (keys 1 + 3 per radix pass + mark 1 + scan 3 + group sum 1 + cell sum 1) + divide 1."""
+def LAUNCHES_PER_STEP_STATIC(cfg, tc_path=False):
+    """Kernels of ours per step, counted from the launch sequences in csrc/ (and confirmed by the ncu launch list
+    in profiles/): K0 bin_flags (1) + K1 scan, scatter, main kernel, re-check (4; +3 centre-preparation kernels on
+    the tcgen05 path) + K3 keys (1), radix sort = 1 histogram + one scatter per 8-bit pass (+ one scan per pass when
+    the grid is too large for the fused scan), mark+scan (1), group sum (1), cell sum (1) + the final divide or,
+    with N > 1, the peer-memory exchange kernel (1)."""
     M = cfg.n_clusters + 2
     bits = int(np.ceil(np.log2(M * M + 1)))
     passes = (bits + 7) // 8
-    return 1 + 5 + 3 + (1 + 2 * passes + 1 + 3 + 1 + 1) + 1   # +3: centre preparation of the tcgen05 path
+    n_trans = cfg.n_iters * cfg.n_segs
+    sort_ctas = min((n_trans + 2047) // 2048, 148 * 4)
+    scans = passes if sort_ctas > 160 else 0
+    return 1 + 4 + (3 if tc_path else 0) + 1 + (1 + passes + scans) + 3 + 1
 
 
 def run_e2e(cfg, rank, world, dev, steps):
