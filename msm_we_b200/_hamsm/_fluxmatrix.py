@@ -113,6 +113,26 @@ class FluxMatrixMixin:
         index_pairs = np.asarray(self.pair_dtrajs[n_iter - 1])
         return index_pairs, parent_pcoords, child_pcoords, transition_weights
 
+    def _gather_flux_inputs_lean(self, n_iter):
+        """Same four arrays as ``_gather_flux_inputs`` for an iteration that is not the last one of a pass: the
+        per-iteration model attributes (``n_iter``, ``weightList``, ``pcoord0List`` ...) are overwritten by the
+        next iteration anyway, so only ``seg_weights[n_iter]`` (which persists in the reference, _data.py:915)
+        is recorded.  Falls back to the full version for missing / empty iterations."""
+        src = self.iteration_source
+        if not src.has(n_iter):
+            return self._gather_flux_inputs(n_iter)
+        rec = src.get(n_iter)
+        if rec.weights.shape[0] == 0:
+            return self._gather_flux_inputs(n_iter)
+        self.seg_weights[n_iter] = rec.weights.copy()
+        w = rec.weights
+        bad = self.iter_nan_segments(n_iter)
+        if bad.shape[0] > 0:
+            w = w.copy()
+            w[bad] = 0.0
+        P = self.pcoord_ndim
+        return np.asarray(self.pair_dtrajs[n_iter - 1]), rec.pcoord0[:, :P], rec.pcoord1[:, :P], w
+
     def _flux_device(self, iters, progress=None, task=None):
         """Dense un-normalised sum over ``iters`` on the device, serial-order association."""
         import torch
@@ -168,8 +188,11 @@ class FluxMatrixMixin:
             lens.clear()
             n = 0
 
-        for iS in iters:
-            index_pairs, p0, p1, w = self._gather_flux_inputs(iS)
+        iters = list(iters)
+        for k, iS in enumerate(iters):
+            # the last iteration goes through the reference's full loader, so the model is left in the state the
+            # reference leaves it in
+            index_pairs, p0, p1, w = (self._gather_flux_inputs if k == len(iters) - 1 else self._gather_flux_inputs_lean)(iS)
             s = w.shape[0]
             if s > 0:
                 index_pairs = np.asarray(index_pairs)
