@@ -69,10 +69,13 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     assign_scan_kernel(const int32_t* __restrict__ bin_count, const int64_t* __restrict__ bin_offset, int32_t nbins,
                        int32_t* __restrict__ bin_start, int32_t* __restrict__ bin_cursor,
-                       int32_t* __restrict__ tile_prefix, int32_t* __restrict__ err_count, int tile_points) {
+                       int32_t* __restrict__ tile_prefix, int32_t* __restrict__ err_count, int tile_points,
+                       int32_t* __restrict__ recheck_count) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ int scratch[9];
     __shared__ int s_carry[2];
-    if (threadIdx.x == 0) { s_carry[0] = 0; s_carry[1] = 0; }
+    if (threadIdx.x == 0) { s_carry[0] = 0; s_carry[1] = 0; *recheck_count = 0; }   // (saves a memset node between kernels)
     __syncthreads();
     for (int base = 0; base < nbins; base += 256) {
         const int b = base + threadIdx.x;
@@ -114,6 +117,8 @@ __global__ void __launch_bounds__(256)
                           int32_t* __restrict__ perm, int64_t* __restrict__ label_out, int32_t* __restrict__ local_out,
                           const int32_t* __restrict__ bin_start, const int32_t* __restrict__ tile_prefix, int tile_points,
                           int4* __restrict__ tile_desc) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ int32_t s_cnt[AS_SMEM_BINS];
     const bool use_smem = nbins <= AS_SMEM_BINS;
     const int64_t T = bin_offset[nbins];
@@ -191,6 +196,8 @@ __global__ void __launch_bounds__(256)
 // lane through an ELECT loop, cost more issue slots than the vectorised LDGSTS below -- profiles/.)
 template <int NT, int VEC, int CW>
 __global__ void __launch_bounds__(CW * 32, (CW == 4 ? (NT <= 4 ? 4 : 2) : 1)) assign_dmma_kernel(const AssignParams p) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int TP = CW * 16;
     constexpr int THREADS = CW * 32;
@@ -455,6 +462,8 @@ __global__ void __launch_bounds__(128)
                           const int64_t* __restrict__ bin_offset, const int32_t* __restrict__ list,
                           const int32_t* __restrict__ count, double tie_scale, int64_t* __restrict__ label_out,
                           int32_t* __restrict__ local_out) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int n = *count;
     const int lane = threadIdx.x & 31;
     const int warps_total = gridDim.x * (blockDim.x >> 5);
@@ -568,8 +577,7 @@ static int launch_assign(AssignParams p, int64_t max_tiles, cudaStream_t stream)
     cudaEvent_t ev0, ev1;
     timing_events(&ev0, &ev1);
     if (ev0) MWE_CHECK_CUDA(cudaEventRecord(ev0, stream));
-    assign_dmma_kernel<NT, VEC, CW><<<(unsigned)grid, CW * 32, smem, stream>>>(p);
-    MWE_CHECK_LAUNCH();
+    MWE_CHECK_CUDA(launch_pdl(assign_dmma_kernel<NT, VEC, CW>, dim3((unsigned)grid), dim3(CW * 32), smem, stream, p));
     if (ev1) MWE_CHECK_CUDA(cudaEventRecord(ev1, stream));
     return MWE_OK;
 }
@@ -676,15 +684,16 @@ extern "C" int mwe_assign_stratified_f64(const double* X, int64_t N, int D, int6
     const int res_points = (use_tc || (int64_t)nbins * max_k >= ((int64_t)1 << 31) || ldx >= ((int64_t)1 << 28)) ? 0 : assign_resident_tile_points(D, max_k, vec2);
     const bool use_res = res_points > 0;
     const int tile_points = use_tc ? 128 : use_res ? res_points : tile_points_for(nt);
-    MWE_CHECK_CUDA(cudaMemsetAsync(ws.bin_count, 0, (size_t)(nbins + 2) * sizeof(int32_t), s));
     const int64_t blocks = (N + 256 * AS_BK_ITEMS - 1) / (256 * AS_BK_ITEMS);
-    if (!bin_count_in) assign_count_kernel<<<(unsigned)blocks, 256, 0, s>>>(bin, flag, N, nbins, ws.bin_count);
-    assign_scan_kernel<<<1, 256, 0, s>>>(bin_count_in ? bin_count_in : ws.bin_count, bin_offset, nbins, ws.bin_start, ws.bin_cursor, ws.tile_prefix, err_count,
-                                         tile_points);
-    assign_scatter_kernel<<<(unsigned)blocks, 256, 0, s>>>(bin, flag, N, nbins, bin_offset, ws.bin_cursor, ws.perm, label_out,
-                                                          local_out, ws.bin_start, ws.tile_prefix, tile_points,
-                                                          use_res ? ws.tile_desc : nullptr);
-    MWE_CHECK_LAUNCH();
+    if (!bin_count_in) {
+        MWE_CHECK_CUDA(cudaMemsetAsync(ws.bin_count, 0, (size_t)(nbins + 1) * sizeof(int32_t), s));
+        assign_count_kernel<<<(unsigned)blocks, 256, 0, s>>>(bin, flag, N, nbins, ws.bin_count);
+    }
+    MWE_CHECK_CUDA(launch_pdl(assign_scan_kernel, dim3(1), dim3(256), 0, s, bin_count_in ? bin_count_in : ws.bin_count, bin_offset,
+                              nbins, ws.bin_start, ws.bin_cursor, ws.tile_prefix, err_count, tile_points, ws.recheck_count));
+    MWE_CHECK_CUDA(launch_pdl(assign_scatter_kernel, dim3((unsigned)blocks), dim3(256), 0, s, bin, flag, N, nbins, bin_offset,
+                              ws.bin_cursor, ws.perm, label_out, local_out, ws.bin_start, ws.tile_prefix, tile_points,
+                              use_res ? ws.tile_desc : nullptr));
 
     AssignParams p;
     p.X = X; p.ldx = ldx; p.D = D; p.centers = centers; p.csq = csq; p.bin_offset = bin_offset; p.nbins = nbins;
@@ -707,8 +716,7 @@ extern "C" int mwe_assign_stratified_f64(const double* X, int64_t N, int D, int6
         rc = vec2 ? dispatch_nt<2>(nt, p, max_tiles, s) : dispatch_nt<1>(nt, p, max_tiles, s);
     }
     if (rc != MWE_OK) return rc;
-    assign_recheck_kernel<<<sm_count(), 128, 0, s>>>(X, ldx, D, bin, centers, csq, bin_offset, ws.recheck_list,
-                                                    ws.recheck_count, p.tie_scale, label_out, local_out);
-    MWE_CHECK_LAUNCH();
+    MWE_CHECK_CUDA(launch_pdl(assign_recheck_kernel, dim3(sm_count()), dim3(128), 0, s, X, ldx, D, bin, centers, csq, bin_offset,
+                              ws.recheck_list, ws.recheck_count, p.tie_scale, label_out, local_out));
     return MWE_OK;
 }

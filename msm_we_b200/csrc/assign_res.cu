@@ -47,6 +47,8 @@ struct ResShared {
 //   NW : consumer warps
 template <int NT, int NW>
 __global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_kernel(const AssignParams p, int nbufs, int xld, int nks) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int KP = NT * 8;
     const int warp = threadIdx.x >> 5;
@@ -408,8 +410,8 @@ static int launch_resident(const AssignParams& p, const ResidentPlan& pl, int64_
     cudaEvent_t ev0, ev1;
     timing_events(&ev0, &ev1);
     if (ev0) MWE_CHECK_CUDA(cudaEventRecord(ev0, stream));
-    assign_dmma_resident_kernel<NT, NW><<<(unsigned)grid, (NW + AR_NP) * 32, pl.smem, stream>>>(p, pl.nbufs, pl.xld, (pl.xld - 8) / 4);
-    MWE_CHECK_LAUNCH();
+    MWE_CHECK_CUDA(launch_pdl(assign_dmma_resident_kernel<NT, NW>, dim3((unsigned)grid), dim3((NW + AR_NP) * 32), pl.smem, stream, p,
+                              pl.nbufs, pl.xld, (pl.xld - 8) / 4));
     if (ev1) MWE_CHECK_CUDA(cudaEventRecord(ev1, stream));
     return MWE_OK;
 }

@@ -37,6 +37,8 @@ struct BinFlagParams {
 // generic body carries 8-way predicated loops that cost ~5x the instructions of the 1-D case.
 template <int PP>
 __global__ void __launch_bounds__(BF_THREADS) bin_flags_kernel(const BinFlagParams p) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int P = PP ? PP : p.P;
     constexpr int MAXP = PP ? PP : BF_MAX_P;
     __shared__ int32_t s_count[BF_SMEM_BINS];
@@ -164,9 +166,9 @@ extern "C" int mwe_bin_flags_f64(const double* pcoord, int64_t N, int P, int map
     const int64_t cap = (int64_t)sm_count() * 32;
     if (blocks > cap) blocks = cap;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (P == 1) bin_flags_kernel<1><<<(unsigned)blocks, BF_THREADS, 0, st>>>(p);
-    else if (P == 2) bin_flags_kernel<2><<<(unsigned)blocks, BF_THREADS, 0, st>>>(p);
-    else bin_flags_kernel<0><<<(unsigned)blocks, BF_THREADS, 0, st>>>(p);
-    MWE_CHECK_LAUNCH();
+    const dim3 g((unsigned)blocks), b(BF_THREADS);
+    if (P == 1) MWE_CHECK_CUDA(launch_pdl(bin_flags_kernel<1>, g, b, 0, st, p));
+    else if (P == 2) MWE_CHECK_CUDA(launch_pdl(bin_flags_kernel<2>, g, b, 0, st, p));
+    else MWE_CHECK_CUDA(launch_pdl(bin_flags_kernel<0>, g, b, 0, st, p));
     return MWE_OK;
 }

@@ -13,6 +13,29 @@ int sm_count();
 // optional CUDA events recorded around the dominant kernel of the next calls (bench roofline timing)
 void timing_events(cudaEvent_t* start, cudaEvent_t* stop);
 
+// Programmatic dependent launch: the kernels of the hot path are short (3-60 us) and run back to back on one
+// stream, so launch latency and CTA ramp-up are a visible share of the step.  Launched with launch_pdl(), a kernel
+// may become resident while its predecessor is still running; it must call pdl_wait() before it touches anything
+// the predecessor wrote (all of them do so first thing), and pdl_launch_dependents() lets ITS successor in.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args... args) {
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 #define MWE_CHECK_CUDA(expr)                                                                   \
     do {                                                                                       \
         cudaError_t _e = (expr);                                                               \

@@ -41,7 +41,13 @@ __global__ void __launch_bounds__(256)
                      const uint8_t* __restrict__ flag0, const uint8_t* __restrict__ flag1,
                      const uint8_t* __restrict__ col0, const uint8_t* __restrict__ col1, int64_t N, int64_t n_clusters,
                      int C, uint64_t sentinel, const int64_t* __restrict__ iter_offsets, int64_t n_iters, int iter_shift,
-                     uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int32_t* __restrict__ err_count) {
+                     uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int32_t* __restrict__ err_count,
+                     unsigned long long* __restrict__ tile_state, int64_t n_tile_state) {
+    pdl_wait();
+    pdl_launch_dependents();
+    // look-back state + ticket of the mark/scan pass that follows the sort (zeroed here: no memset between kernels)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_tile_state; i += (int64_t)gridDim.x * blockDim.x)
+        tile_state[i] = 0ull;
     const int64_t M = n_clusters + 2;
     const uint64_t CM = (uint64_t)C * (uint64_t)M;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -87,6 +93,8 @@ __global__ void __launch_bounds__(FM_THREADS)
                           int32_t* __restrict__ cell_head, int32_t* __restrict__ sub_pos,
                           unsigned long long* __restrict__ tile_state, unsigned int* __restrict__ ticket,
                           int64_t* __restrict__ total_out, int32_t* __restrict__ err_count) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ int scratch[9];
     __shared__ unsigned int s_tile;
     __shared__ long long s_prefix;
@@ -182,6 +190,8 @@ __global__ void __launch_bounds__(256)
                           bool have_w, const int32_t* __restrict__ sub_head, const int32_t* __restrict__ sub_pos,
                           const int32_t* __restrict__ cell_head, double* __restrict__ group_sum,
                           uint8_t* __restrict__ group_is_cell_head, uint64_t* __restrict__ group_key) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += stride) {
         if (!sub_head[q]) continue;
@@ -229,6 +239,8 @@ __global__ void __launch_bounds__(256)
                          const uint64_t* __restrict__ group_key, const int64_t* __restrict__ n_groups_p, uint64_t CM,
                          double* __restrict__ dense, const int32_t* __restrict__ cell_pos, int64_t* __restrict__ coo_row,
                          int64_t* __restrict__ coo_col, double* __restrict__ coo_val) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int64_t n_groups = *n_groups_p;
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -383,25 +395,22 @@ extern "C" int mwe_flux_accumulate_f64(const int64_t* start, const int64_t* end,
     const int sorted_bits = ((key_bits + 7) / 8) * 8;
     if (iter_offsets && sorted_bits + ceil_log2_u64((uint64_t)n_iters + 1) <= 63) iter_shift = sorted_bits;
     const uint64_t cell_mask = iter_shift ? (((uint64_t)1 << iter_shift) - 1) : ~(uint64_t)0;
-    flux_keys_kernel<<<(unsigned)blocks, 256, 0, s>>>(start, end, flag0, flag1, col0, col1, N, n_clusters, C, sentinel,
-                                                     iter_offsets, n_iters, iter_shift, keys, vals, err_count);
-    MWE_CHECK_LAUNCH();
+    MWE_CHECK_CUDA(launch_pdl(flux_keys_kernel, dim3((unsigned)blocks), dim3(256), 0, s, start, end, flag0, flag1, col0, col1, N, n_clusters,
+                              C, sentinel, iter_offsets, n_iters, iter_shift, keys, vals, err_count, tile_state,
+                              (N + FM_TILE - 1) / FM_TILE + 1));
     uint64_t* ks;
     uint32_t* vs;
     int rc = sort_pairs(keys, vals, N, key_bits, sort_ws, sort_bytes, s, &ks, &vs);
     if (rc != MWE_OK) return rc;
     {
         const int64_t ntiles = (N + FM_TILE - 1) / FM_TILE;
-        MWE_CHECK_CUDA(cudaMemsetAsync(tile_state, 0, (size_t)(ntiles + 1) * sizeof(unsigned long long), s));
         unsigned int* ticket = reinterpret_cast<unsigned int*>(tile_state + ntiles);
-        flux_mark_scan_kernel<<<(unsigned)ntiles, FM_THREADS, 0, s>>>(ks, vs, N, sentinel, cell_mask, iter_shift != 0, w, iter_offsets,
-                                                                      n_iters, wv, sub_head, cell_head, pos, tile_state, ticket,
-                                                                      n_groups, err_count);
-        MWE_CHECK_LAUNCH();
+        MWE_CHECK_CUDA(launch_pdl(flux_mark_scan_kernel, dim3((unsigned)ntiles), dim3(FM_THREADS), 0, s, ks, vs, N, sentinel, cell_mask,
+                                  iter_shift != 0, w, iter_offsets, n_iters, wv, sub_head, cell_head, pos, tile_state, ticket,
+                                  n_groups, err_count));
     }
-    flux_group_sum_kernel<<<(unsigned)blocks, 256, 0, s>>>(ks, N, sentinel, cell_mask, wv, w != nullptr, sub_head, pos, cell_head,
-                                                          group_sum, group_flag, group_key);
-    MWE_CHECK_LAUNCH();
+    MWE_CHECK_CUDA(launch_pdl(flux_group_sum_kernel, dim3((unsigned)blocks), dim3(256), 0, s, ks, N, sentinel, cell_mask, wv, w != nullptr,
+                              sub_head, pos, cell_head, group_sum, group_flag, group_key));
     if (coo_val) {
         // COO slot of every cell = rank of its head group among the cell heads
         flux_cellflag_kernel<<<(unsigned)blocks, 256, 0, s>>>(group_flag, n_groups, N, pos);
@@ -409,8 +418,7 @@ extern "C" int mwe_flux_accumulate_f64(const int64_t* start, const int64_t* end,
         rc = exclusive_scan_i32(pos, pos, N, nnz_out, scan_ws, scan_bytes, s);
         if (rc != MWE_OK) return rc;
     }
-    flux_cell_sum_kernel<<<(unsigned)blocks, 256, 0, s>>>(group_sum, group_flag, group_key, n_groups, CM, dense_inout, pos,
-                                                         coo_row, coo_col, coo_val);
-    MWE_CHECK_LAUNCH();
+    MWE_CHECK_CUDA(launch_pdl(flux_cell_sum_kernel, dim3((unsigned)blocks), dim3(256), 0, s, group_sum, group_flag, group_key, n_groups, CM,
+                              dense_inout, pos, coo_row, coo_col, coo_val));
     return MWE_OK;
 }

@@ -30,6 +30,8 @@ static constexpr int RS_FUSED_SCAN_MAX_G = 160;   // up to here the scatter kern
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t* __restrict__ keys, int64_t N, int shift,
                                                             int tiles_per_cta, uint32_t* __restrict__ hist, int later_passes,
                                                             size_t hist_stride) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ uint32_t s_hist[RS_RADIX];
     s_hist[threadIdx.x] = 0;
     for (int q = 1; q <= later_passes; ++q) hist[q * hist_stride + (size_t)blockIdx.x * RS_RADIX + threadIdx.x] = 0;
@@ -47,6 +49,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t* __r
 
 // hist layout [G][256]; afterwards hist[c][d] = global start offset of digit d for CTA c.
 __global__ void __launch_bounds__(RS_RADIX) rs_scan_kernel(uint32_t* __restrict__ hist, int G) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ int scratch[9];
     const int d = threadIdx.x;
     uint32_t total = 0;
@@ -65,6 +69,8 @@ __global__ void __launch_bounds__(RS_THREADS)
                       uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t N, int shift,
                       int tiles_per_cta, const uint32_t* __restrict__ offsets, int fused_scan,
                       uint32_t* __restrict__ next_hist) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ uint32_t s_base[RS_RADIX];
     __shared__ uint32_t s_warp_cnt[RS_WARPS][RS_RADIX];
     __shared__ uint32_t s_tile_excl[RS_RADIX];
@@ -225,14 +231,13 @@ int sort_pairs(uint64_t* keys, uint32_t* vals, int64_t N, int key_bits, void* ws
     uint32_t* vout = vals_alt;
     const int passes = (key_bits + 7) / 8;
     const int fused = G <= RS_FUSED_SCAN_MAX_G;
-    rs_hist_kernel<<<G, RS_THREADS, 0, stream>>>(kin, N, 0, tpc, hist, passes - 1, hist_stride);
+    MWE_CHECK_CUDA(launch_pdl(rs_hist_kernel, dim3(G), dim3(RS_THREADS), 0, stream, kin, N, 0, tpc, hist, passes - 1, hist_stride));
     for (int p = 0; p < passes; ++p) {
         const int shift = p * 8;
         uint32_t* hp = hist + (size_t)p * hist_stride;
-        if (!fused) rs_scan_kernel<<<1, RS_RADIX, 0, stream>>>(hp, G);
-        rs_scatter_kernel<<<G, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, N, shift, tpc, hp, fused,
-                                                        p + 1 < passes ? hp + hist_stride : nullptr);
-        MWE_CHECK_LAUNCH();
+        if (!fused) MWE_CHECK_CUDA(launch_pdl(rs_scan_kernel, dim3(1), dim3(RS_RADIX), 0, stream, hp, G));
+        MWE_CHECK_CUDA(launch_pdl(rs_scatter_kernel, dim3(G), dim3(RS_THREADS), 0, stream, kin, vin, kout, vout, N, shift, tpc, hp,
+                                  fused, p + 1 < passes ? hp + hist_stride : nullptr));
         uint64_t* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;
     }

@@ -1,6 +1,8 @@
 // Library-level plumbing: last-error text, device queries, small elementwise helpers.
 #include <stdarg.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mwe {
@@ -40,6 +42,8 @@ int sm_count() {
 }
 
 __global__ void divide_kernel(double* __restrict__ buf, int64_t n, double divisor) {
+    pdl_wait();
+    pdl_launch_dependents();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) buf[i] = buf[i] / divisor;
@@ -55,6 +59,13 @@ extern "C" int mwe_set_timing_events(void* start, void* stop) {
 
 extern "C" int mwe_abi_version(void) { return MWE_ABI_VERSION; }
 extern "C" const char* mwe_last_error(void) { return mwe::g_last_error; }
+namespace mwe {
+bool pdl_enabled() {
+    static const bool on = []() { const char* e = getenv("MWE_PDL"); return !(e && atoi(e) == 0); }();   // tuning knob
+    return on;
+}
+}  // namespace mwe
+
 extern "C" int mwe_device_sm_count(void) { return mwe::sm_count(); }
 
 extern "C" int mwe_host_register(void* ptr, size_t bytes) {
@@ -85,7 +96,6 @@ extern "C" int mwe_divide_f64(double* buf, int64_t count, double divisor, void* 
     int64_t blocks = (count + 255) / 256;
     int64_t cap = (int64_t)mwe::sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    mwe::divide_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(buf, count, divisor);
-    MWE_CHECK_LAUNCH();
+    MWE_CHECK_CUDA(mwe::launch_pdl(mwe::divide_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), buf, count, divisor));
     return MWE_OK;
 }
