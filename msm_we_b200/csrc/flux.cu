@@ -71,7 +71,16 @@ __global__ void __launch_bounds__(256)
         // The WE iteration of the transition rides in the key bits ABOVE the cell (the sort only looks at the
         // cell bits, the rest is carried along), so the passes after the sort find (cell, iteration) group
         // boundaries by comparing neighbouring keys instead of searching iter_offsets per element.
-        if (iter_shift && key != sentinel) key |= (uint64_t)find_iter(iter_offsets, n_iters, i) << iter_shift;
+        if (iter_shift && key != sentinel) {
+            // iterations of a WE run have similar sizes: start from the proportional guess, walk a few steps, and
+            // only fall back to the binary search (a chain of log2(n_iters) dependent loads) when that fails
+            int64_t it = (int64_t)(((unsigned long long)i * (unsigned long long)n_iters) / (unsigned long long)N);
+            int steps = 0;
+            while (it > 0 && iter_offsets[it] > i && steps < 4) { --it; ++steps; }
+            while (it + 1 < n_iters && iter_offsets[it + 1] <= i && steps < 4) { ++it; ++steps; }
+            if (iter_offsets[it] > i || (it + 1 < n_iters && iter_offsets[it + 1] <= i)) it = find_iter(iter_offsets, n_iters, i);
+            key |= (uint64_t)it << iter_shift;
+        }
         keys[i] = key;
         vals[i] = (uint32_t)i;
     }
