@@ -1,4 +1,4 @@
-// K1: stratified nearest-centre assignment, fp64 parity path (DMMA tensor pipe).
+// K1: stratified nearest-centre assignment -- bucketing, dispatch, the streaming fp64 kernel and the exact re-check.
 //
 // reference: StratifiedClusters.predict (msm_we/stratified_clustering.py:101-212) whose inner
 // call is MiniBatchKMeans.predict([coord]) -> sklearn/cluster/_k_means_lloyd.pyx:168-218:
@@ -6,15 +6,22 @@
 //
 // Design.  Points of one WE bin only ever meet that bin's K_b centres, so the points are first
 // bucketed by bin (count -> scan -> scatter of indices, order inside a bucket is irrelevant
-// because every point's label is computed independently).  A tile is 64 points of ONE bin; the
-// x.c products of a tile are a [64 x K_b x D] GEMM run on the fp64 tensor pipe
-// (mma.sync.m8n8k4.f64 -> SASS DMMA): warp w owns points [16w, 16w+16) x all centres of the block,
-// accumulators stay in registers, the argmin epilogue is fused (quad shuffles), and no distance
-// matrix ever reaches HBM.  One producer warp streams k-chunks of the gathered point rows and of
-// the bin's centre rows into a 3-stage shared-memory ring with cp.async (zero-filling tails) and
-// signals mbarriers; four consumer warps issue the DMMAs.  The grid is persistent
-// (multiple of the SM count) and the ring runs across tile boundaries, so short-D tiles
-// (D=64 is two chunks) do not drain the pipeline.
+// because every point's label is computed independently); then one of three main kernels labels the
+// buckets (mwe_assign_stratified_f64 picks):
+//   * assign_res.cu  fp64, all centres of the bin resident in shared memory, producer/consumer warps --
+//                    K <= 64 and 16-byte aligned rows (BASELINE cfg2);
+//   * this file      fp64, centres streamed with the points: every shape (assign_dmma_kernel below);
+//   * assign_tc.cu   tcgen05 split-TF32 candidate pass (precision path 1), large K*D.
+// All three keep fp32 candidates (best, its column, runner-up) and hand every point whose gap does not clear
+// the tie tolerance to assign_recheck_kernel, which evaluates the scores in the reference's order.
+//
+// assign_dmma_kernel: a tile is 64 (or 128) points of ONE bin; the x.c products of a tile are a
+// [TP x K_b x D] GEMM on the fp64 tensor pipe (mma.sync.m8n8k4.f64 -> SASS DMMA): warp w owns points
+// [16w, 16w+16) x all centres of the block, accumulators stay in registers, the argmin epilogue is fused
+// (quad shuffles), and no distance matrix ever reaches HBM.  Every warp copies its own point rows and a share of
+// the centre block into an mbarrier-guarded shared-memory ring with cp.async (zero-filling tails), nstages-1
+// steps ahead of the step it computes.  The grid is persistent (multiple of the SM count) and the ring runs
+// across tile boundaries, so short-D tiles (D=64 is two chunks) do not drain the pipeline.
 //
 // Algorithmic traffic per point: D*8 bytes of features (+4 B bucket index, +8 B label); centres
 // are re-read from L2.  FLOPs per point: 2*K_b*D.
