@@ -435,15 +435,12 @@ def main():
 def LAUNCHES_PER_STEP_STATIC(cfg, tc_path=False):
     """Kernels of ours per step, counted from the launch sequences in csrc/ (and confirmed by the ncu launch list
     in profiles/): K0 bin_flags (1) + K1 scan, scatter, main kernel, re-check (4; +3 centre-preparation kernels on
-    the tcgen05 path) + K3 keys (1), radix sort = 1 histogram + one scatter per 8-bit pass (+ one scan per pass when
-    the grid is too large for the fused scan), mark+scan (1), group sum (1), cell sum (1) + the final divide or,
+    the tcgen05 path) + K3 keys (1), radix sort = 1 histogram + one scatter per 8-bit pass, mark+scan (1), group sum (1), cell sum (1) + the final divide or,
     with N > 1, the peer-memory exchange kernel (1)."""
     M = cfg.n_clusters + 2
     bits = int(np.ceil(np.log2(M * M + 1)))
     passes = (bits + 7) // 8
-    n_trans = cfg.n_iters * cfg.n_segs
-    sort_ctas = min((n_trans + 2047) // 2048, 148 * 4)
-    scans = passes if sort_ctas > 160 else 0
+    scans = 0          # the scatter kernels scan the per-CTA histograms themselves for every grid the sort launches
     return 1 + 4 + (3 if tc_path else 0) + 1 + (1 + passes + scans) + 3 + 1
 
 

@@ -9,9 +9,9 @@
 //
 //   keys   : key = cluster label (points outside [0, sumK) get a sentinel and are ignored)
 //   sort   : stable radix sort by label (radix_sort.cu) -> each cluster's members contiguous, in
-//            input order; a histogram + scan gives every cluster's segment start
-//   sum    : one CTA per cluster; threads own feature columns (coalesced row reads), members are
-//            visited in order, 4 rows in flight per thread
+//            input order; segment starts are read off the sorted keys
+//   sum    : one CTA per cluster; member rows staged 32 at a time through a cp.async shared-memory ring,
+//            threads own feature columns and add the staged rows in member order
 // HBM-bound: D*8 + 8 + 8 bytes per point per pass, partial sums written once per cluster.
 #include "common.cuh"
 #include "sort.cuh"
@@ -20,61 +20,136 @@ namespace mwe {
 
 __global__ void __launch_bounds__(256)
     centroid_keys_kernel(const int64_t* __restrict__ label, int64_t N, int64_t sumK, uint64_t* __restrict__ keys,
-                         uint32_t* __restrict__ vals, int32_t* __restrict__ count) {
+                         uint32_t* __restrict__ vals) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
         const int64_t l = label[i];
-        const bool ok = l >= 0 && l < sumK;
-        keys[i] = ok ? (uint64_t)l : (uint64_t)sumK;
+        keys[i] = (l >= 0 && l < sumK) ? (uint64_t)l : (uint64_t)sumK;
         vals[i] = (uint32_t)i;
-        if (ok) atomicAdd(&count[l], 1);
+    }
+}
+
+// Segment starts straight from the sorted keys (no per-label atomics, no scan): wherever the key changes at
+// position q, every label in (previous key, key] starts at q; labels above the last key start at N.
+// seg_start has sumK + 2 entries; [sumK] is where the ignored points (sentinel key) begin.
+__global__ void __launch_bounds__(256)
+    centroid_bounds_kernel(const uint64_t* __restrict__ keys, int64_t N, int64_t sumK, int32_t* __restrict__ seg_start) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += stride) {
+        const int64_t k = (int64_t)keys[q];
+        const int64_t kp = q ? (int64_t)keys[q - 1] : -1;
+        for (int64_t l = kp + 1; l <= k; ++l) seg_start[l] = (int32_t)q;
+        if (q == N - 1)
+            for (int64_t l = k + 1; l <= sumK + 1; ++l) seg_start[l] = (int32_t)N;
     }
 }
 
 enum CentroidMode { CM_ACCUMULATE = 0, CM_MINIBATCH = 1 };
 
 static constexpr int CS_THREADS = 128;
+static constexpr int CS_ROWS = 32;    // member rows per staged chunk
+static constexpr int CS_FT = 64;      // feature columns per pass: thread f < CS_FT owns column ft*CS_FT + f
 
-template <int MODE>
+// One CTA per cluster.  The add chain of a (cluster, feature) pair is sequential by definition (sample order, product
+// and sum rounded separately), so the parallelism is clusters x features; what must not be serial is the MEMORY
+// side.  Member rows are therefore staged in chunks of 32 through a double-buffered shared-memory ring with cp.async
+// (all 128 threads copy, coalesced row segments), the member indices and weights of the chunk after next are
+// prefetched into registers, and the 64 feature threads only ever read shared memory.  One extra thread adds the
+// weights in member order while the others work (the first version made every thread walk the whole weight list
+// through two dependent global loads per member before it started: 416 us on the cfg2 shape, now HBM-bound).
+template <int MODE, int VEC>
 __global__ void __launch_bounds__(CS_THREADS)
     centroid_sum_kernel(const double* __restrict__ X, int64_t ldx, int D, const double* __restrict__ w,
                         const uint32_t* __restrict__ members, const int32_t* __restrict__ seg_start,
                         double* __restrict__ out_wx, double* __restrict__ out_w) {
+    pdl_wait();
+    pdl_launch_dependents();
+    __shared__ __align__(16) double s_x[2][CS_ROWS][CS_FT];
+    __shared__ double s_w[2][CS_ROWS];
+    __shared__ uint32_t s_idx[2][CS_ROWS];
+    __shared__ double s_wsum;
     const int64_t k = blockIdx.x;
     const int32_t s = seg_start[k], e = seg_start[k + 1];
-    // weight sum in member order (every thread computes the same value)
-    double wsum = 0.0;
-    for (int32_t q = s; q < e; ++q) wsum = __dadd_rn(wsum, w ? w[members[q]] : 1.0);
-    double count0 = 0.0;
-    if (MODE == CM_MINIBATCH) {
-        count0 = out_w[k];
-        __syncthreads();  // everyone has read the old count before thread 0 overwrites it
-        if (!(wsum > 0.0)) return;  // centre untouched (_k_means_minibatch.pyx:108-111)
-    }
-    const double new_count = __dadd_rn(count0, wsum);
-    const double alpha = 1.0 / new_count;
-    for (int f = threadIdx.x; f < D; f += CS_THREADS) {
+    const int nchunks = (e - s + CS_ROWS - 1) / CS_ROWS;
+    const int tid = threadIdx.x;
+    const double count0 = (MODE == CM_MINIBATCH) ? out_w[k] : 0.0;
+    constexpr int SEGS = CS_FT / VEC;                 // copy segments per row
+    const int n_ft = (D + CS_FT - 1) / CS_FT;
+    double wsum = 0.0;                                // thread CS_THREADS-1: sum of the weights in member order
+
+    for (int ft = 0; ft < n_ft; ++ft) {
+        const int col0 = ft * CS_FT;
+        const int ncols = min(CS_FT, D - col0);
+        // indices and weights of one chunk, fetched by the first CS_ROWS threads
+        auto fetch_meta = [&](int c, uint32_t& idx, double& wv) {
+            const int32_t q = s + c * CS_ROWS + tid;
+            idx = 0u;
+            wv = 0.0;
+            if (tid < CS_ROWS && c < nchunks && q < e) {
+                idx = members[q];
+                wv = w ? w[idx] : 1.0;
+            }
+        };
+        auto publish_and_copy = [&](int c, uint32_t idx, double wv) {
+            if (tid < CS_ROWS) { s_idx[c & 1][tid] = idx; s_w[c & 1][tid] = wv; }
+            __syncthreads();
+            const int rows = min(CS_ROWS, (e - s) - c * CS_ROWS);
+            for (int u = tid; u < rows * SEGS; u += CS_THREADS) {
+                const int r = u / SEGS, sg = u - r * SEGS;
+                const int c_in = sg * VEC;
+                if (c_in < ncols) {
+                    const double* src = X + (int64_t)s_idx[c & 1][r] * ldx + col0 + c_in;
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_x[c & 1][r][c_in]);
+                    if (VEC == 2) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
         double acc = 0.0;
-        if (MODE == CM_MINIBATCH) acc = __dmul_rn(out_wx[k * D + f], count0);
-        int32_t q = s;
-        for (; q + 4 <= e; q += 4) {
-            const uint32_t i0 = members[q], i1 = members[q + 1], i2 = members[q + 2], i3 = members[q + 3];
-            const double x0 = X[(int64_t)i0 * ldx + f], x1 = X[(int64_t)i1 * ldx + f];
-            const double x2 = X[(int64_t)i2 * ldx + f], x3 = X[(int64_t)i3 * ldx + f];
-            const double w0 = w ? w[i0] : 1.0, w1 = w ? w[i1] : 1.0, w2 = w ? w[i2] : 1.0, w3 = w ? w[i3] : 1.0;
-            acc = __dadd_rn(acc, __dmul_rn(x0, w0));
-            acc = __dadd_rn(acc, __dmul_rn(x1, w1));
-            acc = __dadd_rn(acc, __dmul_rn(x2, w2));
-            acc = __dadd_rn(acc, __dmul_rn(x3, w3));
+        const bool owner = tid < ncols;
+        if (MODE == CM_MINIBATCH && owner) acc = __dmul_rn(out_wx[k * D + col0 + tid], count0);
+        uint32_t idx_a, idx_b;
+        double w_a, w_b;
+        fetch_meta(0, idx_a, w_a);
+        fetch_meta(1, idx_b, w_b);
+        if (nchunks > 0) publish_and_copy(0, idx_a, w_a);
+        for (int c = 0; c < nchunks; ++c) {
+            // chunk c+1: its metadata arrived during the previous trip; chunk c+2: start fetching now
+            if (c + 1 < nchunks) publish_and_copy(c + 1, idx_b, w_b);
+            fetch_meta(c + 2, idx_b, w_b);
+            if (c + 1 < nchunks) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            const int rows = min(CS_ROWS, (e - s) - c * CS_ROWS);
+            if (owner) {
+                for (int r = 0; r < rows; ++r) acc = __dadd_rn(acc, __dmul_rn(s_x[c & 1][r][tid], s_w[c & 1][r]));
+            } else if (tid == CS_THREADS - 1 && ft == 0) {
+                for (int r = 0; r < rows; ++r) wsum = __dadd_rn(wsum, s_w[c & 1][r]);
+            }
+            __syncthreads();     // the chunk is consumed before its buffers are refilled
         }
-        for (; q < e; ++q) {
-            const uint32_t i0 = members[q];
-            acc = __dadd_rn(acc, __dmul_rn(X[(int64_t)i0 * ldx + f], w ? w[i0] : 1.0));
+        if (ft == 0) {
+            if (tid == CS_THREADS - 1) s_wsum = wsum;
+            __syncthreads();
         }
-        if (MODE == CM_MINIBATCH) out_wx[k * D + f] = __dmul_rn(acc, alpha);
-        else out_wx[k * D + f] = acc;
+        const double ws = s_wsum;
+        if (MODE == CM_MINIBATCH) {
+            if (!(ws > 0.0)) continue;   // centre untouched (_k_means_minibatch.pyx:108-111)
+            if (owner) out_wx[k * D + col0 + tid] = __dmul_rn(acc, 1.0 / __dadd_rn(count0, ws));
+        } else if (owner) {
+            out_wx[k * D + col0 + tid] = acc;
+        }
     }
-    if (threadIdx.x == 0) out_w[k] = (MODE == CM_MINIBATCH) ? new_count : wsum;
+    if (tid == 0) {
+        const double ws = s_wsum;
+        if (MODE == CM_MINIBATCH) { if (ws > 0.0) out_w[k] = __dadd_rn(count0, ws); }
+        else out_w[k] = ws;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -137,29 +212,27 @@ static int centroid_run(const double* X, int64_t N, int D, int64_t ldx, const do
     Carver cv(workspace, workspace_bytes);
     uint64_t* keys = cv.take<uint64_t>((size_t)(N > 0 ? N : 1));
     uint32_t* vals = cv.take<uint32_t>((size_t)(N > 0 ? N : 1));
-    int32_t* count = cv.take<int32_t>((size_t)sumK + 2);
+    (void)cv.take<int32_t>((size_t)sumK + 2);   // (kept in the layout: mwe_centroid_workspace_bytes is part of the ABI)
     int32_t* seg_start = cv.take<int32_t>((size_t)sumK + 2);
     const size_t sort_bytes = sort_workspace_bytes(N);
     void* sort_ws = cv.take<char>(sort_bytes);
-    const size_t scan_bytes = scan_workspace_bytes(sumK + 2);
-    void* scan_ws = cv.take<char>(scan_bytes);
 
-    MWE_CHECK_CUDA(cudaMemsetAsync(count, 0, (size_t)(sumK + 2) * sizeof(int32_t), s));
     uint64_t* ks = keys;
     uint32_t* vs = vals;
     if (N > 0) {
         int64_t blocks = (N + 255) / 256;
-        const int64_t cap = (int64_t)sm_count() * 8;
+        const int64_t cap = (int64_t)sm_count() * 16;
         if (blocks > cap) blocks = cap;
-        centroid_keys_kernel<<<(unsigned)blocks, 256, 0, s>>>(label, N, sumK, keys, vals, count);
-        MWE_CHECK_LAUNCH();
+        MWE_CHECK_CUDA(launch_pdl(centroid_keys_kernel, dim3((unsigned)blocks), dim3(256), 0, s, label, N, sumK, keys, vals));
         int rc = sort_pairs(keys, vals, N, ceil_log2_u64((uint64_t)sumK + 1), sort_ws, sort_bytes, s, &ks, &vs);
         if (rc != MWE_OK) return rc;
+        MWE_CHECK_CUDA(launch_pdl(centroid_bounds_kernel, dim3((unsigned)blocks), dim3(256), 0, s, ks, N, sumK, seg_start));
+    } else {
+        MWE_CHECK_CUDA(cudaMemsetAsync(seg_start, 0, (size_t)(sumK + 2) * sizeof(int32_t), s));
     }
-    int rc = exclusive_scan_i32(count, seg_start, sumK + 1, nullptr, scan_ws, scan_bytes, s);
-    if (rc != MWE_OK) return rc;
-    centroid_sum_kernel<MODE><<<(unsigned)sumK, CS_THREADS, 0, s>>>(X, ldx, D, w, vs, seg_start, out_wx, out_w);
-    MWE_CHECK_LAUNCH();
+    const bool vec2 = (D % 2 == 0) && (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+    if (vec2) MWE_CHECK_CUDA(launch_pdl(centroid_sum_kernel<MODE, 2>, dim3((unsigned)sumK), dim3(CS_THREADS), 0, s, X, ldx, D, w, vs, seg_start, out_wx, out_w));
+    else MWE_CHECK_CUDA(launch_pdl(centroid_sum_kernel<MODE, 1>, dim3((unsigned)sumK), dim3(CS_THREADS), 0, s, X, ldx, D, w, vs, seg_start, out_wx, out_w));
     return MWE_OK;
 }
 

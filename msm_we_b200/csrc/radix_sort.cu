@@ -22,7 +22,7 @@ static constexpr int RS_ITEMS = 8;
 static constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048
 static constexpr int RS_RADIX = 256;
 static constexpr int RS_WARPS = RS_THREADS / 32;
-static constexpr int RS_FUSED_SCAN_MAX_G = 160;   // up to here the scatter kernel scans the histograms itself
+static constexpr int RS_FUSED_SCAN_MAX_G = 640;   // up to here (every grid this file launches) the scatter kernel scans the histograms itself
 
 // Only the first pass runs this kernel: every scatter pass counts the NEXT pass's per-CTA digits while it stores
 // (it knows where each element lands), so later passes need no histogram launch.  The later histograms are zeroed
