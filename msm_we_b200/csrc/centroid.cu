@@ -51,8 +51,10 @@ __global__ void __launch_bounds__(256)
 enum CentroidMode { CM_ACCUMULATE = 0, CM_MINIBATCH = 1 };
 
 static constexpr int CS_THREADS = 128;
-static constexpr int CS_ROWS = 32;    // member rows per staged chunk
+static constexpr int CS_ROWS = 24;    // member rows per staged chunk (3 stages x 24 rows x 512 B = 36 KB: five CTAs per SM)
 static constexpr int CS_FT = 64;      // feature columns per pass: thread f < CS_FT owns column ft*CS_FT + f
+static constexpr int CS_ST = 3;       // ring depth: two chunks in flight per CTA while one is being added
+static constexpr int CS_SUPER = 8;    // chunks per metadata super-chunk
 
 // One CTA per cluster.  The add chain of a (cluster, feature) pair is sequential by definition (sample order, product
 // and sum rounded separately), so the parallelism is clusters x features; what must not be serial is the MEMORY
@@ -68,13 +70,16 @@ __global__ void __launch_bounds__(CS_THREADS)
                         double* __restrict__ out_wx, double* __restrict__ out_w) {
     pdl_wait();
     pdl_launch_dependents();
-    __shared__ __align__(16) double s_x[2][CS_ROWS][CS_FT];
-    __shared__ double s_w[2][CS_ROWS];
-    __shared__ uint32_t s_idx[2][CS_ROWS];
+    constexpr int SROWS = CS_SUPER * CS_ROWS;         // members whose index + weight are staged together
+    static_assert(SROWS <= 2 * CS_THREADS, "two metadata entries per thread");
+    __shared__ __align__(16) double s_x[CS_ST][CS_ROWS][CS_FT];
+    __shared__ double s_w[2][SROWS];
+    __shared__ uint32_t s_idx[2][SROWS];
     __shared__ double s_wsum;
     const int64_t k = blockIdx.x;
     const int32_t s = seg_start[k], e = seg_start[k + 1];
-    const int nchunks = (e - s + CS_ROWS - 1) / CS_ROWS;
+    const int n = e - s;
+    const int nchunks = (n + CS_ROWS - 1) / CS_ROWS;
     const int tid = threadIdx.x;
     const double count0 = (MODE == CM_MINIBATCH) ? out_w[k] : 0.0;
     constexpr int SEGS = CS_FT / VEC;                 // copy segments per row
@@ -84,55 +89,81 @@ __global__ void __launch_bounds__(CS_THREADS)
     for (int ft = 0; ft < n_ft; ++ft) {
         const int col0 = ft * CS_FT;
         const int ncols = min(CS_FT, D - col0);
-        // indices and weights of one chunk, fetched by the first CS_ROWS threads
-        auto fetch_meta = [&](int c, uint32_t& idx, double& wv) {
-            const int32_t q = s + c * CS_ROWS + tid;
-            idx = 0u;
-            wv = 0.0;
-            if (tid < CS_ROWS && c < nchunks && q < e) {
-                idx = members[q];
-                wv = w ? w[idx] : 1.0;
+        // Member indices and weights (two dependent global loads per member) are fetched a whole super-chunk
+        // (CS_SUPER chunks) ahead into registers and published to shared memory when the copies reach it, so that
+        // chain is paid once per 192 members, behind 8 chunks of work, instead of once per chunk.
+        uint32_t idx_r[2];
+        double w_r[2];
+        auto fetch_super = [&](int sc) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int m = sc * SROWS + h * CS_THREADS + tid;
+                idx_r[h] = 0u;
+                w_r[h] = 0.0;
+                if (h * CS_THREADS + tid < SROWS && m < n) {
+                    idx_r[h] = members[s + m];
+                    w_r[h] = w ? w[idx_r[h]] : 1.0;
+                }
             }
         };
-        auto publish_and_copy = [&](int c, uint32_t idx, double wv) {
-            if (tid < CS_ROWS) { s_idx[c & 1][tid] = idx; s_w[c & 1][tid] = wv; }
+        auto publish_super = [&](int sc) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (h * CS_THREADS + tid < SROWS) {
+                    s_idx[sc & 1][h * CS_THREADS + tid] = idx_r[h];
+                    s_w[sc & 1][h * CS_THREADS + tid] = w_r[h];
+                }
             __syncthreads();
-            const int rows = min(CS_ROWS, (e - s) - c * CS_ROWS);
+        };
+        auto copy_chunk = [&](int c) {
+            const int sc = c / CS_SUPER, r0 = (c % CS_SUPER) * CS_ROWS;
+            const int rows = min(CS_ROWS, n - c * CS_ROWS);
             for (int u = tid; u < rows * SEGS; u += CS_THREADS) {
                 const int r = u / SEGS, sg = u - r * SEGS;
                 const int c_in = sg * VEC;
                 if (c_in < ncols) {
-                    const double* src = X + (int64_t)s_idx[c & 1][r] * ldx + col0 + c_in;
-                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_x[c & 1][r][c_in]);
+                    const double* src = X + (int64_t)s_idx[sc & 1][r0 + r] * ldx + col0 + c_in;
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_x[c % CS_ST][r][c_in]);
                     if (VEC == 2) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
                     else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
                 }
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
         };
         double acc = 0.0;
         const bool owner = tid < ncols;
         if (MODE == CM_MINIBATCH && owner) acc = __dmul_rn(out_wx[k * D + col0 + tid], count0);
-        uint32_t idx_a, idx_b;
-        double w_a, w_b;
-        fetch_meta(0, idx_a, w_a);
-        fetch_meta(1, idx_b, w_b);
-        if (nchunks > 0) publish_and_copy(0, idx_a, w_a);
+        // copies run CS_ST-1 chunks ahead of the adds; one commit group per trip (possibly empty) keeps the group
+        // count in step with the chunk count
+        fetch_super(0);
+        publish_super(0);
+        fetch_super(1);
+        for (int c = 0; c < CS_ST - 1; ++c) {
+            if (c < nchunks) copy_chunk(c);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         for (int c = 0; c < nchunks; ++c) {
-            // chunk c+1: its metadata arrived during the previous trip; chunk c+2: start fetching now
-            if (c + 1 < nchunks) publish_and_copy(c + 1, idx_b, w_b);
-            fetch_meta(c + 2, idx_b, w_b);
-            if (c + 1 < nchunks) asm volatile("cp.async.wait_group 1;" ::: "memory");
-            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            const int cn = c + CS_ST - 1;                     // chunk whose copies are issued this trip
+            if (cn < nchunks) {
+                if (cn % CS_SUPER == 0) {                     // first chunk of a new super-chunk: its metadata is in registers
+                    publish_super(cn / CS_SUPER);
+                    fetch_super(cn / CS_SUPER + 1);
+                }
+                copy_chunk(cn);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group %0;" ::"n"(CS_ST - 1) : "memory");
             __syncthreads();
-            const int rows = min(CS_ROWS, (e - s) - c * CS_ROWS);
+            const int st = c % CS_ST;
+            const int rows = min(CS_ROWS, n - c * CS_ROWS);
+            const double* wc = &s_w[(c / CS_SUPER) & 1][(c % CS_SUPER) * CS_ROWS];
             if (owner) {
-                for (int r = 0; r < rows; ++r) acc = __dadd_rn(acc, __dmul_rn(s_x[c & 1][r][tid], s_w[c & 1][r]));
+                for (int r = 0; r < rows; ++r) acc = __dadd_rn(acc, __dmul_rn(s_x[st][r][tid], wc[r]));
             } else if (tid == CS_THREADS - 1 && ft == 0) {
-                for (int r = 0; r < rows; ++r) wsum = __dadd_rn(wsum, s_w[c & 1][r]);
+                for (int r = 0; r < rows; ++r) wsum = __dadd_rn(wsum, wc[r]);
             }
             __syncthreads();     // the chunk is consumed before its buffers are refilled
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (ft == 0) {
             if (tid == CS_THREADS - 1) s_wsum = wsum;
             __syncthreads();
