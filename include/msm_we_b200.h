@@ -212,6 +212,15 @@ MWE_API size_t mwe_sort_workspace_bytes(int64_t N);
 MWE_API int mwe_sort_pairs_u64_u32(uint64_t* keys, uint32_t* vals, int64_t N, int key_bits, void* workspace,
                            size_t workspace_bytes, void* stream);
 
+/* ---- projection in front of K1 ---------------------------------------
+ * Replaces `self.coordinates.transform(...)` = IncrementalPCA's `(X - mean_) @ components_.T`
+ * (msm_we/_hamsm/_dimensionality.py:243; call sites _clustering.py:1291-1296, :894) for frames that are already on
+ * the device.
+ *   X          [N, D_in] f64, row stride ldx      components [d_out, D_in] f64 row-major (sklearn's components_)
+ *   mean       [D_in] f64 or NULL                 Y          [N, d_out] f64, row stride ldy */
+MWE_API int mwe_project_f64(const double* X, int64_t N, int D_in, int64_t ldx, const double* components, const double* mean,
+                            int d_out, double* Y, int64_t ldy, void* stream);
+
 /* ---- multi-GPU exchange step of the flux path, over NVLink peer memory -------------------------
  * Replaces the driver-side sum of the per-worker iteration matrices and the final "/ nI"
  * (msm_we/_hamsm/_fluxmatrix.py:311-327, :342) when WE iterations are sharded over one process per GPU.

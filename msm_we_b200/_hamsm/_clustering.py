@@ -348,31 +348,46 @@ class ClusteringMixin:
             slot = slots[ci % 2]
             if slot["event"] is not None:
                 slot["event"].synchronize()          # the H2D that last read this buffer has finished
+            featurise, transform = self.processCoordinates, self.coordinates.transform
+            # a fitted linear projection (the reference's PCA ``coordinates.transform``) is applied on the device:
+            # the featurised frames are shipped as they are
+            projection = getattr(self.coordinates, "device_projection", None)
+            projection = projection(dev.device) if callable(projection) else None
+            pool = _staging_pool()
+
+            def featurise_pair(item):
+                parent_coords, child_coords = self.iter_coordinate_pair(item[0])
+                fp, fc = featurise(parent_coords), featurise(child_coords)
+                if projection is None:
+                    fp, fc = transform(fp), transform(fc)
+                return np.asarray(fp), np.asarray(fc)
+
+            # user featurisers / host transforms run on the staging threads (numpy releases the GIL in its loops)
+            feats = list(pool.map(featurise_pair, chunk)) if pool is not None else [featurise_pair(c) for c in chunk]
+            Din = feats[0][0].shape[1] if projection is not None else D
             # pinned staging: pcoords always (small), feature rows only for iterations whose arrays cannot be
             # page-locked in place
-            need = 2 * n * (D + P)
+            need = 2 * n * (Din + P)
             if slot["host"] is None or slot["host"].numel() < need:
                 slot["host"] = torch.empty(need, dtype=torch.float64, pin_memory=True)
             host = slot["host"]
-            hx_t = host[: 2 * n * D].view(2 * n, D)
-            hp_t = host[2 * n * D: need].view(2 * n, P)
+            hx_t = host[: 2 * n * Din].view(2 * n, Din)
+            hp_t = host[2 * n * Din: need].view(2 * n, P)
             hx, hp = hx_t.numpy(), hp_t.numpy()
-            X = torch.empty((2 * n, D), dtype=torch.float64, device=dev.device)
-            pool = _staging_pool()
-            featurise, transform = self.processCoordinates, self.coordinates.transform
+            X = torch.empty((2 * n, Din), dtype=torch.float64, device=dev.device)
 
             def fill(dst, feat):
                 np.copyto(dst, feat)
 
             pos, jobs, staged = 0, [], []
-            for it, s in chunk:
-                parent_coords, child_coords = self.iter_coordinate_pair(it)
+            for (it, s), (fp, fc) in zip(chunk, feats):
                 rec = self._record(it)
                 hp[pos:pos + s] = rec.pcoord0[:, :P]
                 hp[n + pos:n + pos + s] = rec.pcoord1[:, :P]
-                for off, coords in ((pos, parent_coords), (n + pos, child_coords)):
-                    feat = transform(featurise(coords))
-                    if isinstance(feat, np.ndarray) and feat.shape == (s, D) and PINS.ensure(feat):
+                for off, feat in ((pos, fp), (n + pos, fc)):
+                    if feat.shape != (s, Din):
+                        raise ValueError(f"featurised coordinates of iteration {it} have shape {feat.shape}, expected {(s, Din)}")
+                    if PINS.ensure(feat):
                         # the model's own array is page-locked: straight to the device at link speed
                         X[off:off + s].copy_(torch.from_numpy(feat), non_blocking=True)
                     else:
@@ -394,6 +409,10 @@ class ClusteringMixin:
                     hi = staged[k][0] + staged[k][1]
                 X[lo:hi].copy_(hx_t[lo:hi], non_blocking=True)
                 k += 1
+            if projection is not None:
+                from .. import ops as _ops
+
+                X = _ops.project(X, projection[0], projection[1])
             Pc = hp_t.to(dev.device, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(stream)

@@ -31,6 +31,7 @@ SIGNATURES = {
     "mwe_abi_version": (_int, []),
     "mwe_last_error": (C.c_char_p, []),
     "mwe_device_sm_count": (_int, []),
+    "mwe_project_f64": (_int, [_p, _i64, _int, _i64, _p, _p, _int, _p, _i64, _p]),
     "mwe_device_malloc": (_int, [_sz, _p]),
     "mwe_device_free": (_int, [_p]),
     "mwe_ipc_export": (_int, [_p, _p]),

@@ -40,6 +40,24 @@ class LinearCoordinates:
     def transform(self, coords):
         return (np.asarray(coords, dtype=np.float64) - self.mean_) @ self.components_.T
 
+    def device_projection(self, device):
+        """(components [d_out, D_in], mean [D_in]) as CUDA tensors: ``launch_ray_discretization`` then ships the
+        featurised frames as they are and applies the projection on the device (``ops.project``), instead of a
+        host matmul per iteration."""
+        import torch
+
+        cache = self.__dict__.setdefault("_device_cache", {})
+        key = str(device)
+        if key not in cache:
+            cache[key] = (torch.from_numpy(np.ascontiguousarray(self.components_)).to(device),
+                          torch.from_numpy(np.ascontiguousarray(self.mean_)).to(device))
+        return cache[key]
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop("_device_cache", None)
+        return state
+
 
 class modelWE(ClusteringMixin, DataMixin, FluxMatrixMixin):
     class BlockValidationError(Exception):

@@ -137,6 +137,27 @@ def bin_flags(pcoord, mapper: MapperSpec, basis_bounds, target_bounds, we_remap=
     return bin_out, flag
 
 
+def project(X, components, mean=None, out=None):
+    """``(X - mean) @ components.T`` on the device (the reference's ``coordinates.transform`` of a fitted PCA)."""
+    if not X.is_cuda or X.dtype != torch.float64:
+        raise TypeError("X: expected a float64 CUDA tensor (there is no CPU path)")
+    components = components.contiguous()
+    _req(components, torch.float64, "components")
+    if X.dim() != 2 or components.dim() != 2 or X.shape[1] != components.shape[1] or (X.shape[0] > 1 and X.stride(1) != 1):
+        raise ValueError("project: X must be [N, D_in] with unit column stride, components [d_out, D_in]")
+    if mean is not None:
+        _req(mean, torch.float64, "mean")
+        mean = mean.contiguous()
+        if mean.numel() != X.shape[1]:
+            raise ValueError("project: mean must have D_in entries")
+    N, d_out = X.shape[0], components.shape[0]
+    if out is None:
+        out = torch.empty((N, d_out), dtype=torch.float64, device=X.device)
+    check(lib.mwe_project_f64(_ptr(X), N, X.shape[1], X.stride(0), _ptr(components), None if mean is None else _ptr(mean),
+                              d_out, _ptr(out), out.stride(0), _stream()), "mwe_project_f64")
+    return out
+
+
 def centers_sqnorm(centers):
     _req(centers, torch.float64, "centers")
     sumK, D = centers.shape

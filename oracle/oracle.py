@@ -572,3 +572,13 @@ def steady_state(tmatrix):
     p = np.real(vecs[:, k])
     p = p / p.sum()
     return p
+
+
+def linear_transform(X, components, mean=None):
+    """reference: ``self.coordinates.transform`` of the fitted IncrementalPCA (msm_we/_hamsm/_dimensionality.py:243;
+    sklearn < 1.1 ``_BasePCA.transform``: ``X = X - self.mean_; np.dot(X, self.components_.T)``), applied right
+    before every predict (msm_we/_hamsm/_clustering.py:1291-1296)."""
+    X = np.asarray(X, dtype=np.float64)
+    if mean is not None:
+        X = X - np.asarray(mean, dtype=np.float64)
+    return np.dot(X, np.asarray(components, dtype=np.float64).T)

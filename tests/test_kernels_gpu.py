@@ -369,3 +369,27 @@ def test_flux_colour_kat(golden_dir):
     dense = ops.flux_accumulate(t(s0), t(s1), None, 1, col0=t(c0), col1=t(c1), C=2).cpu().numpy()
     assert np.array_equal(dense, O.colour_counts([traj], 3, [0], [2], int(kat["lag"])))
     assert np.allclose(O.normalize_markov_matrix(dense), kat["nmm_tmatrix"])
+
+
+# ------------------------------------------------------------------ projection
+@pytest.mark.parametrize("N,D_in,d_out,use_mean", [
+    (1, 3, 1, True), (1000, 80, 13, True),          # the bundled NTL9 shape: 80 features -> 13 components
+    (777, 33, 9, False),                            # odd D_in: 8-byte copy path
+    (5000, 300, 64, True), (300, 70, 100, True),    # two column blocks
+])
+def test_projection_matches_numpy(N, D_in, d_out, use_mean):
+    """(X - mean) @ components.T: the centred coordinates are rounded like numpy's, only the summation order of the
+    matmul differs from BLAS -> 1e-12 relative to the magnitude of the terms."""
+    ops = _ops()
+    rng = np.random.default_rng(N + D_in)
+    X = rng.normal(size=(N, D_in)) * 3 + 10
+    W = rng.normal(size=(d_out, D_in))
+    mean = X.mean(axis=0) if use_mean else None
+    ref = O.linear_transform(X, W, mean)
+    got = ops.project(t(X), t(W), None if mean is None else t(mean)).cpu().numpy()
+    scale = np.abs(X - (0 if mean is None else mean)) @ np.abs(W).T
+    assert np.all(np.abs(got - ref) <= 1e-12 * scale + 1e-300)
+    # strided input view
+    big = t(np.concatenate([X, X], axis=1))
+    got2 = ops.project(big[:, :D_in], t(W), None if mean is None else t(mean)).cpu().numpy()
+    assert np.array_equal(got, got2)

@@ -303,3 +303,45 @@ def test_peer_memory_flux_allreduce_two_gpus():
     assert out.returncode == 0, out.stderr[-2000:]
     assert "peer path available: True" in out.stdout
     assert "values identical on all ranks: True" in out.stdout
+
+
+@pytest.mark.gpu
+def test_discretization_with_device_projection_matches_host_projection():
+    """A fitted linear projection (the reference's PCA coordinates.transform) in front of predict: shipping the raw
+    features and projecting on the device labels every frame like projecting on the host first."""
+    from msm_we_b200.msm_we import LinearCoordinates
+    from msm_we_b200.stratified_clustering import StratifiedClusters
+
+    cfg, model, mapper, its, centers, basis, target = _build("tiny")
+    rng = np.random.default_rng(3)
+    d_out = 6
+    comps = np.linalg.qr(rng.normal(size=(cfg.dim, cfg.dim)))[0][:d_out]
+    mean = rng.normal(size=cfg.dim)
+    proj_centers = [(c - mean) @ comps.T for c in centers]
+
+    class HostOnly:                       # same transform, no device_projection attribute -> host matmul path
+        def __init__(self, lc):
+            self.lc = lc
+
+        def transform(self, x):
+            return self.lc.transform(x)
+
+    labels = []
+    for coords in (LinearCoordinates(comps, mean), HostOnly(LinearCoordinates(comps, mean))):
+        model.coordinates = coords
+        clusters = StratifiedClusters(mapper, model, cfg.k_per_bin, [])
+        for b in range(cfg.n_bins):
+            clusters.cluster_models[b].cluster_centers_ = proj_centers[b]
+        model.clusters = clusters
+        model.n_clusters = cfg.n_clusters
+        model.pre_discretization_model = model
+        model.launch_ray_discretization()
+        labels.append(np.concatenate(model.pair_dtrajs))
+    same = labels[0] == labels[1]
+    assert same.mean() > 0.9999              # projections differ by rounding only: at most a near-tie may flip
+    # and both agree with the oracle on the host-projected coordinates wherever the oracle is unambiguous
+    it = its[1]
+    Xp = O.linear_transform(it["child"], comps, mean)
+    ref = O.StratifiedOracle(O.RectilinearBinMapperOracle([np.append(np.arange(cfg.n_bins, dtype=np.float32), np.float32(np.inf))]),
+                             proj_centers, basis, target).predict(Xp, it["pcoord1"])
+    assert (model.pair_dtrajs[1][:, 1] == ref).mean() > 0.999
