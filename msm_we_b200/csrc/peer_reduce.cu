@@ -58,6 +58,8 @@ __device__ __forceinline__ void wait_all(const PeerParams& P, int base) {
 }
 
 __global__ void __launch_bounds__(PR_THREADS) flux_peer_allreduce_kernel(const PeerParams P) {
+    pdl_wait();                 // the partial sum is complete (last K3 kernel of this stream)
+    pdl_launch_dependents();
     // ---- my partial is complete (earlier kernels of this stream wrote it): tell everyone ----
     if (blockIdx.x == 0 && (int)threadIdx.x < P.world) {
         __threadfence_system();
@@ -154,7 +156,6 @@ extern "C" int mwe_flux_peer_allreduce_f64(const void* const* partials, void* co
     int64_t grid = (count / world + PR_THREADS - 1) / PR_THREADS;
     if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
     if (grid < 1) grid = 1;
-    flux_peer_allreduce_kernel<<<(unsigned)grid, PR_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(P);
-    MWE_CHECK_LAUNCH();
+    MWE_CHECK_CUDA(launch_pdl(flux_peer_allreduce_kernel, dim3((unsigned)grid), dim3(PR_THREADS), 0, static_cast<cudaStream_t>(stream), P));
     return MWE_OK;
 }
