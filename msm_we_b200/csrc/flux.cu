@@ -91,9 +91,10 @@ __global__ void __launch_bounds__(256)
 // its aggregate, then its inclusive prefix, in one 64-bit word: top 2 bits = status, rest = value).  Tiles take
 // their number from an atomic ticket, so a tile only ever waits for tiles that are already running.
 static constexpr int FM_THREADS = 256;
-static constexpr int FM_ITEMS = 8;
-static constexpr int FM_TILE = FM_THREADS * FM_ITEMS;
+static constexpr int FM_TILE_MIN = FM_THREADS * 2;   // smallest tile the launcher uses (sizes the look-back state)
 
+// FM_ITEMS consecutive elements per thread: 2 while the pass is latency-bound (more tiles in flight), 8 for large N
+template <int FM_ITEMS>
 __global__ void __launch_bounds__(FM_THREADS)
     flux_mark_scan_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t N,
                           uint64_t sentinel, uint64_t cell_mask, bool iter_in_key, const double* __restrict__ w,
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(FM_THREADS)
                           int64_t* __restrict__ total_out, int32_t* __restrict__ err_count) {
     pdl_wait();
     pdl_launch_dependents();
+    constexpr int FM_TILE = FM_THREADS * FM_ITEMS;
     __shared__ int scratch[9];
     __shared__ unsigned int s_tile;
     __shared__ long long s_prefix;
@@ -341,7 +343,7 @@ static size_t flux_ws_bytes(int64_t N) {
     b += 2 * align_up((size_t)N * sizeof(double), 256);    // gathered weights, group sums
     b += align_up((size_t)N * sizeof(uint64_t), 256);      // group keys
     b += align_up((size_t)N, 256) + 256;                   // group flags, group counter
-    b += align_up((size_t)(N / 2048 + 4) * sizeof(unsigned long long), 256);   // look-back tile states + ticket
+    b += align_up((size_t)(N / FM_TILE_MIN + 4) * sizeof(unsigned long long), 256);   // look-back tile states + ticket
     b += sort_workspace_bytes(N);
     b += scan_workspace_bytes(N);
     return b + 1024;
@@ -387,7 +389,7 @@ extern "C" int mwe_flux_accumulate_f64(const int64_t* start, const int64_t* end,
     uint64_t* group_key = cv.take<uint64_t>((size_t)N);
     uint8_t* group_flag = cv.take<uint8_t>((size_t)N);
     int64_t* n_groups = cv.take<int64_t>(1);
-    unsigned long long* tile_state = cv.take<unsigned long long>((size_t)((N + FM_TILE - 1) / FM_TILE) + 2);
+    unsigned long long* tile_state = cv.take<unsigned long long>((size_t)((N + FM_TILE_MIN - 1) / FM_TILE_MIN) + 2);
     const size_t sort_bytes = sort_workspace_bytes(N);
     void* sort_ws = cv.take<char>(sort_bytes);
     const size_t scan_bytes = scan_workspace_bytes(N);
@@ -406,17 +408,24 @@ extern "C" int mwe_flux_accumulate_f64(const int64_t* start, const int64_t* end,
     const uint64_t cell_mask = iter_shift ? (((uint64_t)1 << iter_shift) - 1) : ~(uint64_t)0;
     MWE_CHECK_CUDA(launch_pdl(flux_keys_kernel, dim3((unsigned)blocks), dim3(256), 0, s, start, end, flag0, flag1, col0, col1, N, n_clusters,
                               C, sentinel, iter_offsets, n_iters, iter_shift, keys, vals, err_count, tile_state,
-                              (N + FM_TILE - 1) / FM_TILE + 1));
+                              (N + FM_TILE_MIN - 1) / FM_TILE_MIN + 1));
     uint64_t* ks;
     uint32_t* vs;
     int rc = sort_pairs(keys, vals, N, key_bits, sort_ws, sort_bytes, s, &ks, &vs);
     if (rc != MWE_OK) return rc;
     {
-        const int64_t ntiles = (N + FM_TILE - 1) / FM_TILE;
-        unsigned int* ticket = reinterpret_cast<unsigned int*>(tile_state + ntiles);
-        MWE_CHECK_CUDA(launch_pdl(flux_mark_scan_kernel, dim3((unsigned)ntiles), dim3(FM_THREADS), 0, s, ks, vs, N, sentinel, cell_mask,
-                                  iter_shift != 0, w, iter_offsets, n_iters, wv, sub_head, cell_head, pos, tile_state, ticket,
-                                  n_groups, err_count));
+        const int items = N <= ((int64_t)1 << 22) ? 2 : 8;
+        const int64_t ntiles = (N + FM_THREADS * items - 1) / (FM_THREADS * items);
+        // the ticket lives right behind the state words of the smallest tiling (flux_keys_kernel zeroed all of them)
+        unsigned int* ticket = reinterpret_cast<unsigned int*>(tile_state + (N + FM_TILE_MIN - 1) / FM_TILE_MIN);
+        if (items == 2)
+            MWE_CHECK_CUDA(launch_pdl(flux_mark_scan_kernel<2>, dim3((unsigned)ntiles), dim3(FM_THREADS), 0, s, ks, vs, N, sentinel,
+                                      cell_mask, iter_shift != 0, w, iter_offsets, n_iters, wv, sub_head, cell_head, pos, tile_state,
+                                      ticket, n_groups, err_count));
+        else
+            MWE_CHECK_CUDA(launch_pdl(flux_mark_scan_kernel<8>, dim3((unsigned)ntiles), dim3(FM_THREADS), 0, s, ks, vs, N, sentinel,
+                                      cell_mask, iter_shift != 0, w, iter_offsets, n_iters, wv, sub_head, cell_head, pos, tile_state,
+                                      ticket, n_groups, err_count));
     }
     MWE_CHECK_CUDA(launch_pdl(flux_group_sum_kernel, dim3((unsigned)blocks), dim3(256), 0, s, ks, N, sentinel, cell_mask, wv, w != nullptr,
                               sub_head, pos, cell_head, group_sum, group_flag, group_key));
