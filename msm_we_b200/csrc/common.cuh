@@ -89,9 +89,10 @@ static inline int ceil_log2_u64(uint64_t x) {  // smallest b with 2^b >= x
 // ---- device helpers -----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
-// exclusive scan of one int per thread across a 256-thread block; returns exclusive prefix and
-// writes the block total to *total (same for all threads). scratch: 9 ints of shared memory.
-__device__ __forceinline__ int block_excl_scan_256(int v, int* scratch, int* total) {
+// exclusive scan of one int per thread across a block of NW warps (NW <= 32); returns the exclusive prefix and
+// writes the block total to *total (same for all threads). scratch: NW + 1 ints of shared memory.
+template <int NW>
+__device__ __forceinline__ int block_excl_scan(int v, int* scratch, int* total) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     int inc = v;
 #pragma unroll
@@ -102,21 +103,22 @@ __device__ __forceinline__ int block_excl_scan_256(int v, int* scratch, int* tot
     if (lane == 31) scratch[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-        int s = (lane < 8) ? scratch[lane] : 0;
+        int s = (lane < NW) ? scratch[lane] : 0;
         int si = s;
 #pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
+        for (int o = 1; o < NW; o <<= 1) {
             int n = __shfl_up_sync(0xffffffffu, si, o);
             if (lane >= (uint32_t)o) si += n;
         }
-        if (lane < 8) scratch[lane] = si - s;  // exclusive warp base
-        if (lane == 7) scratch[8] = si;
+        if (lane < NW) scratch[lane] = si - s;  // exclusive warp base
+        if (lane == NW - 1) scratch[NW] = si;
     }
     __syncthreads();
     int r = scratch[warp] + inc - v;
-    *total = scratch[8];
+    *total = scratch[NW];
     __syncthreads();
     return r;
 }
+__device__ __forceinline__ int block_excl_scan_256(int v, int* scratch, int* total) { return block_excl_scan<8>(v, scratch, total); }
 
 }  // namespace mwe

@@ -17,9 +17,10 @@
 
 namespace mwe {
 
-static constexpr int RS_THREADS = 256;
-static constexpr int RS_ITEMS = 8;
+static constexpr int RS_THREADS = 512;      // scatter kernel: 16 warps x 4 items rank a tile in 4 match rounds
+static constexpr int RS_ITEMS = 4;
 static constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048
+static constexpr int RS_HTHREADS = 256;     // histogram / scan kernels: one thread per digit
 static constexpr int RS_RADIX = 256;
 static constexpr int RS_WARPS = RS_THREADS / 32;
 static constexpr int RS_FUSED_SCAN_MAX_G = 640;   // up to here (every grid this file launches) the scatter kernel scans the histograms itself
@@ -27,7 +28,7 @@ static constexpr int RS_FUSED_SCAN_MAX_G = 640;   // up to here (every grid this
 // Only the first pass runs this kernel: every scatter pass counts the NEXT pass's per-CTA digits while it stores
 // (it knows where each element lands), so later passes need no histogram launch.  The later histograms are zeroed
 // here, each CTA its own rows.
-__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t* __restrict__ keys, int64_t N, int shift,
+__global__ void __launch_bounds__(RS_HTHREADS) rs_hist_kernel(const uint64_t* __restrict__ keys, int64_t N, int shift,
                                                             int tiles_per_cta, uint32_t* __restrict__ hist, int later_passes,
                                                             size_t hist_stride) {
     pdl_wait();
@@ -39,7 +40,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t* __r
     const int64_t begin = (int64_t)blockIdx.x * tiles_per_cta * RS_TILE;
     int64_t end = begin + (int64_t)tiles_per_cta * RS_TILE;
     if (end > N) end = N;
-    for (int64_t i = begin + threadIdx.x; i < end; i += RS_THREADS) {
+    for (int64_t i = begin + threadIdx.x; i < end; i += RS_HTHREADS) {
         uint32_t d = (uint32_t)(keys[i] >> shift) & 0xffu;
         atomicAdd(&s_hist[d], 1u);
     }
@@ -77,30 +78,32 @@ __global__ void __launch_bounds__(RS_THREADS)
     __shared__ uint32_t s_tile_total[RS_RADIX];
     __shared__ uint64_t s_keys[RS_TILE];
     __shared__ uint32_t s_vals[RS_TILE];
-    __shared__ int scratch[9];
+    __shared__ int scratch[RS_WARPS + 1];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const bool dthread = tid < RS_RADIX;           // the first 256 threads double as "one thread per digit"
     if (fused_scan) {
         // small grids: every CTA derives its own digit offsets from the raw per-CTA histograms
         // (offsets[c][d] = count) instead of waiting for a separate one-CTA scan kernel
         uint32_t below = 0, total = 0;
         const int G = (int)gridDim.x;
         // 32 independent loads in flight per thread: the loop is pure L2 latency otherwise
-        for (int c0 = 0; c0 < G; c0 += 32) {
-            uint32_t v[32];
+        if (dthread)
+            for (int c0 = 0; c0 < G; c0 += 32) {
+                uint32_t v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = (c0 + i < G) ? offsets[(size_t)(c0 + i) * RS_RADIX + tid] : 0u;
+                for (int i = 0; i < 32; ++i) v[i] = (c0 + i < G) ? offsets[(size_t)(c0 + i) * RS_RADIX + tid] : 0u;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                if (c0 + i < (int)blockIdx.x) below += v[i];
-                total += v[i];
+                for (int i = 0; i < 32; ++i) {
+                    if (c0 + i < (int)blockIdx.x) below += v[i];
+                    total += v[i];
+                }
             }
-        }
         int blk_total;
-        const uint32_t digit_base = (uint32_t)block_excl_scan_256((int)total, scratch, &blk_total);
-        s_base[tid] = digit_base + below;
-    } else {
+        const uint32_t digit_base = (uint32_t)block_excl_scan<RS_WARPS>((int)total, scratch, &blk_total);
+        if (dthread) s_base[tid] = digit_base + below;
+    } else if (dthread) {
         s_base[tid] = offsets[(size_t)blockIdx.x * RS_RADIX + tid];
     }
 
@@ -110,8 +113,7 @@ __global__ void __launch_bounds__(RS_THREADS)
         const int64_t tile_base = span_begin + (int64_t)t * RS_TILE;
         if (tile_base >= N) break;
         const int tile_count = (int)((N - tile_base < RS_TILE) ? (N - tile_base) : RS_TILE);
-#pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) s_warp_cnt[w][tid] = 0;
+        for (uint32_t i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&s_warp_cnt[0][0])[i] = 0;
         __syncthreads();
 
         // warp-striped load: item j of lane l is element warp*256 + j*32 + l of the tile
@@ -147,15 +149,18 @@ __global__ void __launch_bounds__(RS_THREADS)
         // per digit: exclusive prefix over warps, tile total, then exclusive scan over digits
         {
             uint32_t run = 0;
+            if (dthread) {
 #pragma unroll
-            for (int w = 0; w < RS_WARPS; ++w) {
-                uint32_t c = s_warp_cnt[w][tid];
-                s_warp_cnt[w][tid] = run;
-                run += c;
+                for (int w = 0; w < RS_WARPS; ++w) {
+                    uint32_t c = s_warp_cnt[w][tid];
+                    s_warp_cnt[w][tid] = run;
+                    run += c;
+                }
+                s_tile_total[tid] = run;
             }
-            s_tile_total[tid] = run;
             int blk_total;
-            s_tile_excl[tid] = (uint32_t)block_excl_scan_256((int)run, scratch, &blk_total);
+            const uint32_t ex = (uint32_t)block_excl_scan<RS_WARPS>((int)run, scratch, &blk_total);
+            if (dthread) s_tile_excl[tid] = ex;
         }
         __syncthreads();
 #pragma unroll
@@ -183,7 +188,7 @@ __global__ void __launch_bounds__(RS_THREADS)
             }
         }
         __syncthreads();
-        s_base[tid] += s_tile_total[tid];
+        if (dthread) s_base[tid] += s_tile_total[tid];
         __syncthreads();
     }
 }
@@ -231,7 +236,7 @@ int sort_pairs(uint64_t* keys, uint32_t* vals, int64_t N, int key_bits, void* ws
     uint32_t* vout = vals_alt;
     const int passes = (key_bits + 7) / 8;
     const int fused = G <= RS_FUSED_SCAN_MAX_G;
-    MWE_CHECK_CUDA(launch_pdl(rs_hist_kernel, dim3(G), dim3(RS_THREADS), 0, stream, kin, N, 0, tpc, hist, passes - 1, hist_stride));
+    MWE_CHECK_CUDA(launch_pdl(rs_hist_kernel, dim3(G), dim3(RS_HTHREADS), 0, stream, kin, N, 0, tpc, hist, passes - 1, hist_stride));
     for (int p = 0; p < passes; ++p) {
         const int shift = p * 8;
         uint32_t* hp = hist + (size_t)p * hist_stride;
