@@ -362,8 +362,16 @@ class ClusteringMixin:
                     fp, fc = transform(fp), transform(fc)
                 return np.asarray(fp), np.asarray(fc)
 
-            # user featurisers / host transforms run on the staging threads (numpy releases the GIL in its loops)
-            feats = list(pool.map(featurise_pair, chunk)) if pool is not None else [featurise_pair(c) for c in chunk]
+            # user featurisers / host transforms run on the staging threads (numpy releases the GIL in its loops);
+            # a featuriser that only reshapes is cheaper inline than a hand-off to a thread
+            import time as _time
+
+            t0 = _time.perf_counter()
+            feats = [featurise_pair(chunk[0])]
+            if pool is not None and len(chunk) > 1 and _time.perf_counter() - t0 > 2e-4:
+                feats += list(pool.map(featurise_pair, chunk[1:]))
+            else:
+                feats += [featurise_pair(c) for c in chunk[1:]]
             Din = feats[0][0].shape[1] if projection is not None else D
             # pinned staging: pcoords always (small), feature rows only for iterations whose arrays cannot be
             # page-locked in place
