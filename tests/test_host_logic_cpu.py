@@ -166,3 +166,50 @@ def test_sharded_flux_matrix_gloo_world2(tmp_path):
     ref = O.flux_matrix(cfg.n_clusters, per, basis, target)
     # two partial sums instead of one serial sum: 1e-12 relative is the stated multi-GPU tolerance
     assert np.allclose(a, ref, rtol=1e-12, atol=0) and abs(a.sum() - 1.0) < 1e-12
+
+
+def test_lean_flux_gather_equals_full_gather_and_keeps_seg_weights():
+    """get_fluxMatrix loads all but the last iteration of a pass through a lean gather: same four arrays as the
+    reference-shaped loader, NaN-coordinate segments zero-weighted, seg_weights recorded."""
+    import dataclasses
+
+    from msm_we_b200 import synthetic
+    from msm_we_b200.msm_we import modelWE
+
+    cfg = dataclasses.replace(synthetic.CONFIGS["tiny"], n_iters=6)
+    means, _ = synthetic.make_centers(cfg)
+    its = synthetic.generate_host(cfg, means)
+    its[2]["child"][5, 3] = np.nan                      # a broken frame in iteration 3
+    basis, target = synthetic.region_bounds(cfg)
+    model = modelWE()
+    model.initialize(synthetic.to_iteration_source(its), None, "t", basis_pcoord_bounds=basis, target_pcoord_bounds=target,
+                     tau=1.0, pcoord_ndim=1)
+    model.get_iterations()
+    rng = np.random.default_rng(0)
+    model.pair_dtrajs = [rng.integers(0, 10, size=(cfg.n_segs, 2)) for _ in range(cfg.n_iters)]
+    for n_iter in (1, 3, 5):
+        full = model._gather_flux_inputs(n_iter)
+        model.seg_weights.pop(n_iter)
+        lean = model._gather_flux_inputs_lean(n_iter)
+        for a, b in zip(full, lean):
+            assert np.array_equal(np.asarray(a), np.asarray(b))
+        assert np.array_equal(model.seg_weights[n_iter], its[n_iter - 1]["weights"])
+    assert model._gather_flux_inputs_lean(3)[3][5] == 0.0
+
+
+def test_host_pinning_degrades_without_a_gpu():
+    """HostPins.ensure never raises: arrays it cannot page-lock (no device here, wrong dtype/layout, disabled) are
+    reported as not pinned and the caller stages them."""
+    from msm_we_b200._pinning import HostPins
+
+    pins = HostPins()
+    a = np.zeros((64, 8))
+    assert pins.ensure(a[:, :4]) is False               # not contiguous
+    assert pins.ensure(a.astype(np.float32)) is False   # not float64
+    assert pins.ensure("nope") is False
+    got = pins.ensure(a)                                # needs a CUDA device: False here, never an exception
+    assert got in (False, True)
+    pins.enabled = False
+    assert pins.ensure(np.ones(16)) is False
+    view = a.reshape(-1)[8:24]
+    assert HostPins._owner(view) is a
