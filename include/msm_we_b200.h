@@ -204,6 +204,10 @@ MWE_API int mwe_debug_set_tc_scores(float* buf);
 MWE_API int mwe_debug_tc_columns(int32_t max_k);
 /* tuning hook: device uint64[20] (or NULL) accumulating per-role wait cycles of the tcgen05 kernel */
 MWE_API int mwe_debug_set_tc_profile(unsigned long long* buf);
+/* tuning hook: device uint64[8] (or NULL) accumulating per-phase clock cycles of the resident-centre fp64 kernel
+ * (assign_res.cu: consumers [0] wait for data, [1] metadata, [2] k loop, [3] fold + epilogue, [4] groups;
+ * producers [5] wait for a buffer, [6] claim + copy issue) */
+MWE_API int mwe_debug_set_k1_profile(unsigned long long* buf);
 
 /* ---- shared primitive, exported for tests ---------------------------------------------------
  * Stable LSD radix sort of (key, value) pairs on the low `key_bits` bits of the key.

@@ -60,6 +60,7 @@ SIGNATURES = {
                                     _i32, _int, _i64, _f64, _p, _p, _p, _sz, _p, _p]),
     "mwe_debug_set_tc_scores": (_int, [_p]),
     "mwe_debug_tc_columns": (_int, [_i32]),
+    "mwe_debug_set_k1_profile": (_int, [_p]),
     "mwe_debug_set_tc_profile": (_int, [_p]),
     "mwe_sort_workspace_bytes": (_sz, [_i64]),
     "mwe_sort_pairs_u64_u32": (_int, [_p, _p, _i64, _int, _p, _sz, _p]),

@@ -442,8 +442,10 @@ __global__ void __launch_bounds__(CW * 32, (CW == 4 ? (NT <= 4 ? 4 : 2) : 1)) as
                     // ||x|| <= sqrt(D) max|x_k|, max|x_k| < the double whose high word is xh + 1 (inf/NaN -> inf)
                     const float xnorm = __double2float_ru(__hiloint2double((int)(min(xh, 0x7ff00000u) + 1u), 0)) * p.sqrt_d;
                     const float tolf = 2.0f * (float)p.tie_scale * cmax * (2.0f * xnorm + cmax);
-                    const double gap_lb = ((double)ru - (double)bs) - 1.2e-7 * fabs((double)bs);
-                    if (!(gap_lb > (double)tolf)) p.recheck_list[atomicAdd(p.recheck_count, 1)] = pt;
+                    // lower bound of the true gap, in fp32 with directed rounding (fp64 arithmetic here would queue
+                    // behind the other warps' DMMAs on the fp64 pipe)
+                    const float gap_lb = __fsub_rd(__fsub_rd(ru, bs), __fmul_ru(1.2e-7f, fabsf(bs)));
+                    if (!(gap_lb > tolf)) p.recheck_list[atomicAdd(p.recheck_count, 1)] = pt;
                 }
                 m1f[mt] = m2f[mt] = finf;
                 besti[mt] = 0;

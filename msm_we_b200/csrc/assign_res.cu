@@ -33,6 +33,11 @@ static constexpr int AR_MAX_BUFS = 32;
 static constexpr int AR_NP = 4;                // producer warps (groups are dealt round-robin to them)
 static constexpr int AR_META_INTS = 21;        // idx[16], coff, kb, cbuf, nrows, tag (group number being filled)
 
+// tuning hook (mwe_debug_set_k1_profile): device uint64[8] accumulating clock cycles per phase, summed over warps
+//   consumers: [0] ticket -> data ready, [1] metadata + accumulator seed, [2] k loop, [3] fold + epilogue, [4] groups
+//   producers: [5] waiting for a free buffer, [6] claiming + copy issue, [7] bin changes
+static unsigned long long* g_k1_profile = nullptr;
+
 struct ResShared {
     int32_t pidx[AR_NP][AR_TP];    // per producer warp: point indices of the tile being issued (16-byte aligned rows)
     uint64_t full[AR_MAX_BUFS];
@@ -45,8 +50,10 @@ struct ResShared {
 
 //   NT : 8-column centre sub-tiles (K_pad = NT*8 >= every bin's centre count)
 //   NW : consumer warps
-template <int NT, int NW>
-__global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_kernel(const AssignParams p, int nbufs, int xld, int nks) {
+// PROF: compile-time switch of the per-phase cycle counters (the product path runs the PROF = false instantiation)
+template <int NT, int NW, bool PROF>
+__global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_kernel(const AssignParams p, int nbufs, int xld, int nks, unsigned long long* prof_buf) {
+    unsigned long long* const prof = PROF ? prof_buf : nullptr;
     pdl_wait();
     pdl_launch_dependents();
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -165,7 +172,9 @@ __global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_ker
             uint32_t use = (uint32_t)((q + gi0) / nbufs);
             for (int gi = gi0; gi < ngroups; gi += AR_NP) {
                 const int32_t qq = q + gi;
+                const long long t_p0 = prof ? clock64() : 0;
                 mbar_wait(&sh->empty[b], (use & 1u) ^ 1u);
+                const long long t_p1 = prof ? clock64() : 0;
                 const int nrows = min(AR_GROUP, d_cur.y - gi * AR_GROUP);
                 const int32_t* gidx = s_idx + gi * AR_GROUP;
                 if (lane < AR_GROUP) sh->meta[b][lane] = gidx[lane];
@@ -215,6 +224,10 @@ __global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_ker
                 cp_async_arrive_noinc(&sh->full[b]);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sh->full[b]);   // releases the metadata written above
+                if (prof && lane == 0) {
+                    atomicAdd(prof + 5, (unsigned long long)(t_p1 - t_p0));
+                    atomicAdd(prof + 6, (unsigned long long)(clock64() - t_p1));
+                }
                 b += AR_NP;
                 if (b >= nbufs) { b -= nbufs; ++use; }
             }
@@ -235,11 +248,13 @@ __global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_ker
         const int32_t total = sh->total_groups;
         const uint32_t nbufs_magic = (uint32_t)((((uint64_t)1 << 32) + (uint32_t)nbufs - 1) / (uint32_t)nbufs);
         int32_t q_next = 0;
-        if (lane == 0) q_next = atomicAdd(&sh->ticket, 1);
+        long long c_wait = 0, c_meta = 0, c_mma = 0, c_fold = 0, c_groups = 0, t_a = prof ? clock64() : 0;
         while (true) {
+            // the ticket is taken only now, when the warp is free: a ticket reserved earlier would pin this warp to a
+            // group whose data may land long after groups that idle warps could have taken
+            if (lane == 0) q_next = atomicAdd(&sh->ticket, 1);
             const int32_t q = __shfl_sync(0xffffffffu, q_next, 0);
             if (q >= total) break;
-            if (lane == 0) q_next = atomicAdd(&sh->ticket, 1);   // next ticket: its latency hides under this group's math
             const uint32_t use = __umulhi((uint32_t)q, nbufs_magic);     // q / nbufs (exact for q < 2^32 / nbufs)
             const int b = q - (int32_t)use * nbufs;
             // Tickets can run ahead of the fills by more than nbufs groups (other consumers keep finishing groups
@@ -255,6 +270,7 @@ __global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_ker
                 }
             }
             mbar_wait(&sh->full[b], use & 1u);
+            if (prof) { const long long t_b = clock64(); c_wait += t_b - t_a; t_a = t_b; }
             const int32_t* meta = sh->meta[b];
             const int32_t coff = meta[16], kb = meta[17], cbuf = meta[18], nrows = meta[19];
             int32_t out_pt[2];
@@ -287,6 +303,7 @@ __global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_ker
                 }
             }
             uint32_t xhi[2] = {0u, 0u};
+            if (prof) { const long long t_b = clock64(); c_meta += t_b - t_a; t_a = t_b; }
 #pragma unroll 2
             for (int kp = 0; kp < (nks >> 1); ++kp) {
                 const double2 a0 = *reinterpret_cast<const double2*>(xa0 + kp * 8);
@@ -314,6 +331,7 @@ __global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_ker
             // which the producer relies on when it reuses one)
             __syncwarp();
             if (lane == 0) mbar_arrive(&sh->empty[b]);
+            if (prof) { const long long t_b = clock64(); c_mma += t_b - t_a; t_a = t_b; }
 
             // fp32 candidates: sf = round-down(score) = -2 * round-up(acc); smallest, its column, second smallest
             float m1f[2] = {finf, finf}, m2f[2] = {finf, finf};
@@ -360,10 +378,20 @@ __global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_ker
                     // ||x|| <= sqrt(D) max|x_k|, max|x_k| < the double whose high word is xh + 1 (inf/NaN -> NaN -> re-check)
                     const float xnorm = __double2float_ru(__hiloint2double((int)(min(xh, 0x7ff00000u) + 1u), 0)) * p.sqrt_d;
                     const float tolf = 2.0f * (float)p.tie_scale * cmax * (2.0f * xnorm + cmax);
-                    const double gap_lb = ((double)ru - (double)bs) - 1.2e-7 * fabs((double)bs);
-                    if (!(gap_lb > (double)tolf)) p.recheck_list[atomicAdd(p.recheck_count, 1)] = pt;
+                    // lower bound of the true gap, in fp32 with directed rounding (fp64 arithmetic here would queue
+                    // behind the other warps' DMMAs on the fp64 pipe)
+                    const float gap_lb = __fsub_rd(__fsub_rd(ru, bs), __fmul_ru(1.2e-7f, fabsf(bs)));
+                    if (!(gap_lb > tolf)) p.recheck_list[atomicAdd(p.recheck_count, 1)] = pt;
                 }
             }
+            if (prof) { const long long t_b = clock64(); c_fold += t_b - t_a; t_a = t_b; ++c_groups; }
+        }
+        if (prof && lane == 0) {
+            atomicAdd(prof + 0, (unsigned long long)c_wait);
+            atomicAdd(prof + 1, (unsigned long long)c_meta);
+            atomicAdd(prof + 2, (unsigned long long)c_mma);
+            atomicAdd(prof + 3, (unsigned long long)c_fold);
+            atomicAdd(prof + 4, (unsigned long long)c_groups);
         }
     }
 }
@@ -401,7 +429,8 @@ template <int NT, int NW>
 static int launch_resident(const AssignParams& p, const ResidentPlan& pl, int64_t max_tiles, cudaStream_t stream) {
     static size_t configured = 0;
     if (configured < pl.smem) {
-        MWE_CHECK_CUDA(cudaFuncSetAttribute(assign_dmma_resident_kernel<NT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        MWE_CHECK_CUDA(cudaFuncSetAttribute(assign_dmma_resident_kernel<NT, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        MWE_CHECK_CUDA(cudaFuncSetAttribute(assign_dmma_resident_kernel<NT, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         configured = pl.smem;
     }
     int64_t grid = sm_count();
@@ -410,8 +439,12 @@ static int launch_resident(const AssignParams& p, const ResidentPlan& pl, int64_
     cudaEvent_t ev0, ev1;
     timing_events(&ev0, &ev1);
     if (ev0) MWE_CHECK_CUDA(cudaEventRecord(ev0, stream));
-    MWE_CHECK_CUDA(launch_pdl(assign_dmma_resident_kernel<NT, NW>, dim3((unsigned)grid), dim3((NW + AR_NP) * 32), pl.smem, stream, p,
-                              pl.nbufs, pl.xld, (pl.xld - 8) / 4));
+    if (g_k1_profile)
+        MWE_CHECK_CUDA(launch_pdl(assign_dmma_resident_kernel<NT, NW, true>, dim3((unsigned)grid), dim3((NW + AR_NP) * 32), pl.smem, stream, p,
+                                  pl.nbufs, pl.xld, (pl.xld - 8) / 4, g_k1_profile));
+    else
+        MWE_CHECK_CUDA(launch_pdl(assign_dmma_resident_kernel<NT, NW, false>, dim3((unsigned)grid), dim3((NW + AR_NP) * 32), pl.smem, stream, p,
+                                  pl.nbufs, pl.xld, (pl.xld - 8) / 4, g_k1_profile));
     if (ev1) MWE_CHECK_CUDA(cudaEventRecord(ev1, stream));
     return MWE_OK;
 }
@@ -421,6 +454,15 @@ int assign_resident_tile_points(int D, int32_t max_k, bool vec2) {
     ResidentPlan pl;
     return resident_plan(D, max_k, vec2, &pl) ? AR_TP : 0;
 }
+
+}  // namespace mwe
+
+extern "C" int mwe_debug_set_k1_profile(unsigned long long* buf) {
+    mwe::g_k1_profile = buf;
+    return MWE_OK;
+}
+
+namespace mwe {
 
 int launch_assign_resident(AssignParams p, int32_t max_k, bool vec2, int64_t max_tiles, cudaStream_t stream) {
     ResidentPlan pl;
