@@ -130,7 +130,7 @@ __global__ void __launch_bounds__((NW + AR_NP) * 32, 1) assign_dmma_resident_ker
         __syncwarp();
         fetch_idx(d_next, idx_next);
         int32_t q = 0;                 // next group number
-        int32_t cur_coff = -1, cur_cbuf = 1, bins_seen = 0, groups_in_bin = 0;
+        int32_t cur_coff = -1, cur_cbuf = 1, bins_seen = 0, groups_in_bin = 0;   // (the last two: centre-buffer reuse rule below)
         uint32_t cuse[2] = {0u, 0u};   // fills of each centre buffer so far
         for (int ti = 0; ti < count; ++ti) {
             if (d_cur.z != cur_coff) {

@@ -138,3 +138,18 @@ def test_flux_matrix_conventions():
     # a child in both regions ends up in the basis (override order of _fluxmatrix.py:135-137)
     F2 = O.iter_flux_matrix(n, pairs[:1], p0[:1], np.array([[0.5]]), w[:1], np.array([[0.0, 1.0]]), np.array([[0.2, 1.0]]))
     assert F2[0, n] == 0.1 and F2[0, n + 1] == 0.0
+
+
+def test_linear_transform_restatement_matches_sklearn_pca_transform():
+    """oracle.linear_transform restates the reference's coordinates.transform (sklearn < 1.1: (X - mean_) @
+    components_.T).  The installed sklearn evaluates X @ components_.T - mean_ @ components_.T instead: same map,
+    different rounding, so the two agree to 1e-12 of the magnitude of the terms."""
+    from sklearn.decomposition import IncrementalPCA
+
+    rng = np.random.default_rng(11)
+    X = rng.normal(size=(400, 30)) * 2 + 5
+    pca = IncrementalPCA(n_components=7).fit(X)
+    ours = O.linear_transform(X, pca.components_, pca.mean_)
+    theirs = pca.transform(X)
+    scale = (np.abs(X) + np.abs(pca.mean_)) @ np.abs(pca.components_).T
+    assert np.all(np.abs(ours - theirs) <= 1e-12 * scale)
