@@ -147,44 +147,50 @@ class FluxMatrixMixin:
         errors = ops.DeviceErrors(dev)
         mapper = ops.MapperSpec.precomputed(1)
         chunk = int(getattr(self, "flux_chunk_transitions", DEFAULT_FLUX_CHUNK))
-        W = 2 * P + 3                       # staged row: parent pcoord | child pcoord | weight | parent label | child label
+        # Staged as five contiguous field arrays (parent pcoord | child pcoord | weight | parent label | child label):
+        # every per-iteration write is one contiguous copy, and the device needs no slicing / dtype conversion kernels.
         stagebuf = _FLUX_STAGE          # module-level: a model stays picklable / deep-copyable
         lens = []
         n = 0
+        fields = (("p0", (P,), torch.float64), ("p1", (P,), torch.float64), ("w", (), torch.float64),
+                  ("ls", (), torch.int64), ("le", (), torch.int64))
 
-        def rows(need):
-            """numpy view of the pinned staging rows, grown (contents kept) to hold ``need`` rows."""
+        def views(need):
+            """numpy views of the pinned field arrays, grown (contents kept) to hold ``need`` transitions."""
             if stagebuf["pending"] is not None:
-                stagebuf["pending"].synchronize()    # the H2D that last read the buffer has finished
+                stagebuf["pending"].synchronize()    # the H2D copies that last read the buffers have finished
                 stagebuf["pending"] = None
             host = stagebuf["host"]
-            if host is None or host.shape[1] != W or host.shape[0] < need:
-                cap = max(need, 1 << 14, 2 * (host.shape[0] if host is not None and host.shape[1] == W else 0))
-                grown = torch.empty((cap, W), dtype=torch.float64, pin_memory=True)
-                if host is not None and host.shape[1] == W and n > 0:
-                    grown[:n] = host[:n]
-                stagebuf["host"] = host = grown
-            return host.numpy()
+            if not isinstance(host, dict) or host["P"] != P or host["cap"] < need:
+                old = host if isinstance(host, dict) and host["P"] == P else None
+                cap = max(need, 1 << 14, 2 * (old["cap"] if old else 0))
+                host = {"P": P, "cap": cap}
+                for name, shape, dtype in fields:
+                    host[name] = torch.empty((cap,) + shape, dtype=dtype, pin_memory=True)
+                    if old is not None and n > 0:
+                        host[name][:n] = old[name][:n]
+                host["np"] = {name: host[name].numpy() for name, _, _ in fields}
+                stagebuf["host"] = host
+            return host["np"]
 
         def flush():
             nonlocal n
             if not lens:
                 return
             if n > 0:
-                d = stagebuf["host"][:n].to(dev, non_blocking=True)
+                host = stagebuf["host"]
+                d = {name: host[name][:n].to(dev, non_blocking=True) for name, _, _ in fields}
                 ev = torch.cuda.Event()
                 ev.record(torch.cuda.current_stream())
                 stagebuf["pending"] = ev
                 offs = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)).to(dev)
                 zeros = torch.zeros(n, dtype=torch.int32, device=dev)
-                _, f0 = ops.bin_flags(d[:, :P].contiguous(), mapper, self.basis_pcoord_bounds, self.target_pcoord_bounds,
-                                      errors=errors, bin_out=zeros)
-                _, f1 = ops.bin_flags(d[:, P:2 * P].contiguous(), mapper, self.basis_pcoord_bounds,
-                                      self.target_pcoord_bounds, errors=errors, bin_out=zeros)
-                start = d[:, 2 * P + 1].to(torch.int64)      # labels < 2^53 are exact in fp64; one H2D, not two
-                end = d[:, 2 * P + 2].to(torch.int64)
-                ops.flux_accumulate(start, end, d[:, 2 * P].contiguous(), int(self.n_clusters), flag0=f0, flag1=f1,
-                                    iter_offsets=offs, dense=dense, errors=errors)
+                _, f0 = ops.bin_flags(d["p0"], mapper, self.basis_pcoord_bounds, self.target_pcoord_bounds, errors=errors,
+                                      bin_out=zeros)
+                _, f1 = ops.bin_flags(d["p1"], mapper, self.basis_pcoord_bounds, self.target_pcoord_bounds, errors=errors,
+                                      bin_out=zeros)
+                ops.flux_accumulate(d["ls"], d["le"], d["w"], int(self.n_clusters), flag0=f0, flag1=f1, iter_offsets=offs,
+                                    dense=dense, errors=errors)
             lens.clear()
             n = 0
 
@@ -200,11 +206,12 @@ class FluxMatrixMixin:
                     raise ValueError("row, column, and data array must all be the same length")
                 if index_pairs.ndim != 2 or index_pairs.shape[1] != 2:
                     raise ValueError("pair_dtrajs entries must be [S, 2]")
-                h = rows(n + s)
-                h[n:n + s, :P] = p0.reshape(s, P)
-                h[n:n + s, P:2 * P] = p1.reshape(s, P)
-                h[n:n + s, 2 * P] = w
-                h[n:n + s, 2 * P + 1:] = index_pairs
+                h = views(n + s)
+                h["p0"][n:n + s] = p0.reshape(s, P)
+                h["p1"][n:n + s] = p1.reshape(s, P)
+                h["w"][n:n + s] = w
+                h["ls"][n:n + s] = index_pairs[:, 0]
+                h["le"][n:n + s] = index_pairs[:, 1]
                 n += s
             lens.append(s)
             if progress is not None:
