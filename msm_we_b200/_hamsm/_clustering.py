@@ -436,9 +436,8 @@ class ClusteringMixin:
 
         with ProgressBar(progress_bar) as progress:
             task = progress.add_task(description="Discretizing trajectories", total=n_iters)
-            for ci, chunk in enumerate(chunks):
-                stage(ci, chunk)
-            for chunk, n, lh, bh, fh, done in inflight:
+            def collect(item):
+                chunk, n, lh, bh, fh, done = item
                 done.synchronize()
                 labels_h, bins_h, flags_h = lh.numpy(), bh.numpy(), fh.numpy()
                 is_target = (flags_h & 2) != 0
@@ -457,6 +456,14 @@ class ClusteringMixin:
                     pair_dtrajs[it - 1] = pairs_all[pos:pos + s]
                     pos += s
                 progress.update(task, advance=len(chunk))
+
+            # the results of chunk i are unpacked while chunk i+1 is being copied and labelled
+            for ci, chunk in enumerate(chunks):
+                stage(ci, chunk)
+                if ci >= 1:
+                    collect(inflight[ci - 1])
+            if inflight:
+                collect(inflight[-1])
             dev.check_errors()
 
         self.dtrajs = [d for d in dtrajs if d is not None]
