@@ -107,7 +107,7 @@ def _cpu_inputs(cfg_name, n_iters):
     if key not in _CPU_CACHE:
         import dataclasses
 
-        from msm_we_b200 import synthetic
+        import workloads as synthetic
 
         cfg = dataclasses.replace(synthetic.CONFIGS[cfg_name], n_iters=n_iters)
         means, centers = synthetic.make_centers(cfg)
@@ -119,7 +119,7 @@ def _cpu_inputs(cfg_name, n_iters):
 def _cpu_chunk(args):
     os.environ["OMP_NUM_THREADS"] = "1"
     from oracle import oracle as O
-    from msm_we_b200 import synthetic
+    import workloads as synthetic
 
     cfg_name, lo, hi, n_total = args[0], args[1], args[2], None
     cfg, centers, its = _cpu_inputs(cfg_name, _CPU_SAMPLE[0])
@@ -247,7 +247,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
-    from msm_we_b200 import synthetic  # host-only import is fine without a GPU
+    import workloads as synthetic
 
     cfg = synthetic.CONFIGS[args.workload]
     cores = os.cpu_count() or 1
@@ -449,7 +449,7 @@ def run_e2e(cfg, rank, world, dev, steps):
     import torch
     import torch.distributed as dist
 
-    from msm_we_b200 import synthetic
+    import workloads as synthetic
     from msm_we_b200.binning import RectilinearBinMapper
     from msm_we_b200.msm_we import modelWE
     from msm_we_b200.stratified_clustering import StratifiedClusters

@@ -24,7 +24,7 @@ pytestmark = pytest.mark.gpu
 def cfg2():
     import torch
 
-    from msm_we_b200 import synthetic
+    import workloads as synthetic
     from msm_we_b200.binning import RectilinearBinMapper
     from msm_we_b200.engine import DeviceClusters
 
@@ -123,7 +123,8 @@ def test_flux_blockwise_accumulation_is_bit_identical_and_weights_are_conserved(
 def test_discretization_pinned_source_path_equals_staged_path(monkeypatch):
     import dataclasses
 
-    from msm_we_b200 import synthetic, _pinning
+    import workloads as synthetic
+    from msm_we_b200 import _pinning
     from msm_we_b200.binning import RectilinearBinMapper
     from msm_we_b200.msm_we import modelWE
     from msm_we_b200.stratified_clustering import StratifiedClusters

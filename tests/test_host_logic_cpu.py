@@ -173,7 +173,7 @@ def test_lean_flux_gather_equals_full_gather_and_keeps_seg_weights():
     reference-shaped loader, NaN-coordinate segments zero-weighted, seg_weights recorded."""
     import dataclasses
 
-    from msm_we_b200 import synthetic
+    import workloads as synthetic
     from msm_we_b200.msm_we import modelWE
 
     cfg = dataclasses.replace(synthetic.CONFIGS["tiny"], n_iters=6)

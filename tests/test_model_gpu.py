@@ -18,7 +18,7 @@ RTOL = 1e-12
 
 
 def _build(cfg_name="tiny", use_weights=False):
-    from msm_we_b200 import synthetic
+    import workloads as synthetic
     from msm_we_b200.binning import RectilinearBinMapper
     from msm_we_b200.msm_we import modelWE
 
@@ -261,7 +261,7 @@ def test_ntl9_fixture_replay_sparsity(golden_dir):
 def test_hotpath_step_matches_separate_kernels_and_oracle():
     """The one-call C entry (K0 -> K1 -> K3 -> / nI) on a stacked batch equals the modelWE-level results."""
     import torch
-    from msm_we_b200 import synthetic
+    import workloads as synthetic
 
     cfg, model, its, centers, basis, target, om = _with_fixed_centers()
     model.launch_ray_discretization()

@@ -2,7 +2,7 @@
 import cProfile, pstats, sys, time, dataclasses, io
 sys.path.insert(0, ".")
 import torch
-from msm_we_b200 import synthetic
+import workloads as synthetic
 from msm_we_b200.binning import RectilinearBinMapper
 from msm_we_b200.msm_we import modelWE
 from msm_we_b200.stratified_clustering import StratifiedClusters

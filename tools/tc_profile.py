@@ -2,7 +2,8 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from msm_we_b200 import _lib, ops, synthetic
+import workloads as synthetic
+from msm_we_b200 import _lib, ops
 from msm_we_b200.binning import RectilinearBinMapper
 from msm_we_b200.engine import DeviceClusters
 

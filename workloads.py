@@ -113,7 +113,7 @@ def _features(cfg, means, pc, rng):
 
 
 def to_iteration_source(its):
-    from ._hamsm._data import ArrayIterationSource, IterationRecord
+    from msm_we_b200._hamsm._data import ArrayIterationSource, IterationRecord
 
     src = ArrayIterationSource()
     for i, it in enumerate(its, start=1):
