@@ -96,6 +96,11 @@ MWE_API int mwe_bin_flags_f64(const double* pcoord, int64_t N, int P, int mapper
                       const double* target_lohi_host, const int32_t* we_remap, int32_t* bin_out, uint8_t* flag_out,
                       int32_t* bin_count, int32_t* err_count, void* stream);
 
+/* Rows of X [N, D] (row stride ldx) that contain a NaN -> out [N] uint8 (1 / 0).
+ * Replaces the NaN scan of get_transition_data_lag0 (msm_we/_hamsm/_data.py:302-313: such segments get transition
+ * weight 0), which the reference repeats in the flux pass by re-reading every structure from disk. */
+MWE_API int mwe_rows_with_nan_f64(const double* X, int64_t N, int D, int64_t ldx, uint8_t* out, void* stream);
+
 /* ---- K1: stratified nearest-centre assignment -----------------------------------------------
  * Replaces the per-segment MiniBatchKMeans.predict([coord]) loop of StratifiedClusters.predict
  * (msm_we/stratified_clustering.py:152-203) and the E step of partial_fit / KMeans.fit
@@ -146,6 +151,22 @@ MWE_API int mwe_lloyd_finalize_f64(const double* sum_wx, const double* sum_w, in
                            void* stream);
 MWE_API int mwe_minibatch_finalize_f64(const double* sum_wx, const double* sum_w, int64_t sumK, int D, double* centers,
                                double* counts, void* stream);
+
+/* ---- group-by-label + per-label statistics ----------------------------
+ * Replaces the O(n_clusters x iterations) np.where loops of ClusteringMixin.get_cluster_centers
+ * (msm_we/_hamsm/_clustering.py:1528-1599: nanmean / nanmin / nanmax of the end pcoord of every cluster's
+ * members) and the per-segment list appends of update_cluster_structures (:1398-1526).
+ *   mwe_group_by_label: stable sort of the N labels; members_out [N] uint32 = indices grouped by label, each
+ *     group in input order; seg_start_out [n_labels + 2] int32 = first position of every label's group
+ *     ([n_labels] = where the out-of-range labels begin, [n_labels+1] = N).  Workspace:
+ *     mwe_centroid_workspace_bytes(N, n_labels).
+ *   mwe_label_stats_f64: NaN-skipping count / sum / min / max of values[member * ldv] per label (an empty
+ *     label gets count 0, sum 0, min +inf, max -inf); one warp per label, fixed reduction order. */
+MWE_API int mwe_group_by_label(const int64_t* label, int64_t N, int64_t n_labels, uint32_t* members_out,
+                               int32_t* seg_start_out, void* workspace, size_t workspace_bytes, void* stream);
+MWE_API int mwe_label_stats_f64(const double* values, int64_t ldv, const uint32_t* members, const int32_t* seg_start,
+                                int64_t n_labels, int64_t* count, double* sum, double* vmin, double* vmax, void* stream);
+
 
 /* ---- K3: weighted transition scatter into the flux matrix -----------------------------------
  * Replaces FluxMatrixMixin.build_flux_matrix + .todense() + the per-iteration accumulation of

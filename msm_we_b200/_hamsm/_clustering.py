@@ -1,16 +1,21 @@
-"""Clustering + discretization mixin: the reference's method names and control flow, GPU arithmetic.
+"""Clustering + discretization mixin: the reference's method names and results, GPU arithmetic.
 
 reference: msm_we/_hamsm/_clustering.py -- ``cluster_coordinates`` (:142-195), ``cluster_stratified``
-(:525-746), ``do_stratified_clustering`` (:748-918), ``launch_ray_discretization`` (:1144-1242),
-``do_stratified_ray_discretization`` (:1244-1329), ``find_nearest_bin`` (:1331-1396).
+(:525-746), ``do_stratified_clustering`` (:748-918), ``organize_stratified`` (:920-1142),
+``launch_ray_discretization`` (:1144-1242), ``do_stratified_ray_discretization`` (:1244-1329),
+``find_nearest_bin`` (:1331-1396), ``update_cluster_structures`` (:1398-1526), ``get_cluster_centers``
+(:1528-1599), ``update_sorted_cluster_centers`` (:1601-1611).
 
 What changed underneath:
 * no Ray, no fork-per-iteration ``ProcessPoolExecutor``: ``use_ray`` is accepted and ignored;
-* ``do_stratified_clustering`` keeps the reference's batching rule (pull iterations until every seen WE
-  bin holds >= n_clusters segments) but runs all WE bins of a batch through one K1 + one K2 launch;
-* ``launch_ray_discretization`` stages many iterations into one pinned buffer, and K0 + K1 label every
-  parent and child frame of the chunk in a single launch sequence instead of one sklearn call per
-  segment.
+* ``do_stratified_clustering`` first PLANS a batch from progress coordinates alone (which iterations it pulls,
+  which rows go to which WE bin -- the reference's rule, including its row-pairing quirk), then gathers the
+  coordinates once and runs all WE bins of the batch through one K1 + one K2 launch;
+* ``launch_ray_discretization`` stages many iterations into one pinned buffer (HDF5 sources read straight into
+  it), and K0 + K1 label every parent and child frame of the chunk in a single launch sequence instead of one
+  sklearn call per segment;
+* ``get_cluster_centers`` / ``update_cluster_structures`` are a device group-by-label (stable sort + per-label
+  reduction) instead of one ``np.where`` over every iteration per cluster.
 """
 from __future__ import annotations
 
@@ -44,6 +49,23 @@ def _staging_pool():
     return _STAGING_POOL or None
 
 
+def connected_sets(C, directed=True):
+    """Strongly connected components of the graph whose edges are the non-zero entries of ``C``, each as a sorted
+    index array, largest first (components of equal size in order of their first discovery label) -- the contract
+    of the reference's ``find_connected_sets`` (msm_we/utils.py:21-84, itself msmtools' routine); host-side graph
+    work on an (n+2)^2 matrix, as in the reference."""
+    from scipy.sparse import csr_matrix, issparse
+    from scipy.sparse.csgraph import connected_components
+
+    if not issparse(C):
+        C = csr_matrix(C)
+    nc, comp = connected_components(C, directed=directed, connection="strong")
+    order = np.argsort(comp, kind="stable")
+    bounds = np.concatenate([[0], np.cumsum(np.bincount(comp, minlength=nc))])
+    sets = [np.sort(order[bounds[i]:bounds[i + 1]]) for i in range(nc)]
+    return sorted(sets, key=lambda s: -len(s))
+
+
 class _RemoteShim:
     """``obj.method.remote(...)`` compatibility for code written against the ``@ray.remote`` functions:
     runs synchronously and returns the result itself."""
@@ -67,7 +89,14 @@ def _do_stratified_ray_discretization(model, kmeans_model, iteration, processCoo
     children, ``predict`` twice (reference :1244-1329).  Empty iterations return the reference's
     3-tuple ``(None, 0, iteration)``."""
     self = model
-    kmeans_model = deepcopy(kmeans_model)
+    # the reference's caller detaches .model before shipping the clusterer (:1171-1174); copying it with the model
+    # attached would duplicate everything the model holds
+    original, attached = kmeans_model, kmeans_model.model
+    original.model = None
+    try:
+        kmeans_model = deepcopy(original)
+    finally:
+        original.model = attached
     kmeans_model.model = self
     self.load_iter_data(iteration)
     self.get_transition_data_lag0()
@@ -96,6 +125,11 @@ class ClusteringMixin:
     targetRMSD_centers = None
     targetRMSD_minmax = None
     targetRMSD_all = None
+    all_centers = None
+    sorted_centers = None
+    pcoord_cache = None
+    cluster_structures = None
+    cluster_structure_weights = None
     pre_discretization_model = None
     post_cluster_model = None
 
@@ -140,10 +174,7 @@ class ClusteringMixin:
             log.info("Loading user-specified bin mapper for stratified clustering.")
             bin_mapper = user_bin_mapper
         else:
-            bin_mapper = getattr(self, "bin_mapper", None)
-            if bin_mapper is None:
-                raise Exception("No bin mapper: the reference unpickles it from the WESTPA HDF5 file with westpa, "
-                                "which is not available here; pass user_bin_mapper=")
+            bin_mapper = self._load_bin_mapper(bin_iteration)
             if type(bin_mapper) not in SUPPORTED_MAPPERS:
                 log.warning(f"{type(bin_mapper)} mapper loaded, but supported mappers are {SUPPORTED_MAPPERS} and "
                             f"others may produce inconsistent bins between iterations. Please provide a supported "
@@ -204,7 +235,72 @@ class ClusteringMixin:
         self.clusters.toggle = False
         self.launch_ray_discretization(progress_bar)
 
+    def _load_bin_mapper(self, bin_iteration=2):
+        """The reference unpickles the mapper WESTPA stored in the HDF5 file (``analysis.Run(file).iteration(n)
+        .bin_mapper``, :588-590).  That needs westpa; a model can also carry one in ``self.bin_mapper``."""
+        bin_mapper = getattr(self, "bin_mapper", None)
+        if bin_mapper is not None:
+            return bin_mapper
+        try:
+            from westpa import analysis
+        except ImportError:
+            raise Exception("No bin mapper: the reference unpickles it from the WESTPA HDF5 file with westpa, which is "
+                            "not importable here; pass user_bin_mapper= or set model.bin_mapper") from None
+        log.debug(f"Obtaining bin definitions from iteration {bin_iteration} in file {self.fileList[0]}")
+        return analysis.Run(self.fileList[0]).iteration(bin_iteration).bin_mapper
+
     # ------------------------------------------------------------------------------------------
+    def _plan_stratified_batch(self, bin_mapper, min_coords, iters_to_use):
+        """The batching rule of do_stratified_clustering (:794-886), evaluated on progress coordinates alone.
+
+        Iterations are pulled until every WE bin seen so far holds >= ``min_coords`` usable segments (parents outside
+        basis / target); if the iterations run out, under-filled bins are folded into the nearest filled bin.  Returns
+        ``(pulled, rows_per_iter, assignments, unique_bins, unfilled_bins)``: ``assignments[j]`` is the WE bin of the
+        j-th USABLE segment of the pulled iterations.  (The reference then uses j as a row number of the UNFILTERED
+        coordinate array, :892-899 / SURVEY Appendix A.5; the caller reproduces that.)"""
+        P = self.pcoord_ndim
+        pulled, rows_per_iter, kept_bins = [], [], []
+        counts = np.zeros(bin_mapper.nbins, dtype=np.int64)
+        unfilled_bins = []
+        pos = 0
+        while True:
+            if pos >= len(iters_to_use):
+                seen = np.flatnonzero(counts)
+                log.warning(f"At iteration {pulled[-1] if pulled else None} (pulled {len(pulled) - 1} extra), couldn't get "
+                            f"segments in all bins, and no iterations left.")
+                unfilled_bins = seen[counts[seen] < min_coords]
+                filled_bins = np.setdiff1d(seen, unfilled_bins)
+                assignments = np.concatenate(kept_bins) if kept_bins else np.array([])
+                for unfilled_bin in unfilled_bins:
+                    nearest = self.find_nearest_bin(bin_mapper, unfilled_bin, list(filled_bins))
+                    log.warning(f"Remapping segments from unfilled bin {unfilled_bin} to {nearest} for stratified clustering")
+                    assignments[assignments == unfilled_bin] = nearest
+                return pulled, rows_per_iter, assignments, filled_bins, unfilled_bins
+            iteration = iters_to_use[pos]
+            if iteration > self.maxIter:
+                log.warning(f"At iteration {iteration} (pulled {len(pulled) - 1} extra), couldn't get segments in all "
+                            f"bins, and no iterations left")
+                break
+            pos += 1
+            if self.iteration_source.has(iteration):
+                rec = self._record(iteration, coords=False)
+                pc0 = rec.pcoord0[:, :P]
+            else:
+                pc0 = np.empty((0, P))
+            pulled.append(iteration)
+            rows_per_iter.append(pc0.shape[0])
+            usable = ~(self.is_WE_target(pc0) | self.is_WE_basis(pc0)) if pc0.shape[0] else np.zeros(0, dtype=bool)
+            if usable.any():
+                b = np.asarray(bin_mapper.assign(pc0[usable])).astype(np.int64)
+                kept_bins.append(b)
+                counts += np.bincount(b, minlength=bin_mapper.nbins)
+            seen = np.flatnonzero(counts)
+            # np.all of an empty comparison is True: an iteration whose parents are all in the basis "fills" nothing
+            if np.all(counts[seen] >= min_coords):
+                break
+        assignments = np.concatenate(kept_bins) if kept_bins else np.array([])
+        return pulled, rows_per_iter, assignments, np.flatnonzero(counts), unfilled_bins
+
     def do_stratified_clustering(self, arg):
         """reference: _clustering.py:748-918.  Returns ``(kmeans_models, used_iters, unique_bins,
         unfilled_bins)``.  The per-bin ``partial_fit`` calls of the reference (:890-916) are issued as ONE
@@ -212,79 +308,34 @@ class ClusteringMixin:
         from ..clustering_ops import partial_fit_models
 
         self, kmeans_models, iters_to_use, processCoordinates, ignored_bins = arg
-        iters_to_use = list(iters_to_use)
         bin_mapper = kmeans_models.bin_mapper
         min_coords = kmeans_models.cluster_args["n_clusters"]
-        all_bins_have_segments = False
-        used_iters = -1
-        iter_coords = []
-        seg_weights = None
-        pcoords = []
-        unique_bins = np.array([])
-        counts = np.array([])
-        we_bin_assignments = np.array([])
-        unfilled_bins = []
-        iteration = None
+        pulled, rows_per_iter, assignments, unique_bins, unfilled_bins = self._plan_stratified_batch(
+            bin_mapper, min_coords, list(iters_to_use))
+        used_iters = len(pulled) - 1
 
-        while not all_bins_have_segments:
-            unfilled_bins = []
-            try:
-                iteration = iters_to_use.pop(0)
-            except IndexError:
-                log.warning(f"At iteration {iteration} (pulled {used_iters} extra), couldn't get segments in all "
-                            f"bins, and no iterations left.")
-                unfilled_bins = unique_bins[counts < min_coords]
-                filled_bins = np.setdiff1d(unique_bins, unfilled_bins)
-                for unfilled_bin in unfilled_bins:
-                    nearest_filled_bin = self.find_nearest_bin(bin_mapper, unfilled_bin, list(filled_bins))
-                    unfilled_bin_indices = np.where(we_bin_assignments == unfilled_bin)
-                    log.warning(f"Remapping {len(unfilled_bin_indices)} segments from unfilled bin {unfilled_bin} to "
-                                f"{nearest_filled_bin} for stratified clustering")
-                    we_bin_assignments[unfilled_bin_indices] = nearest_filled_bin
-                unique_bins = filled_bins
-                break
+        # Row j of the FILTERED assignment array indexes row j of the UNFILTERED coordinates / weights (the reference's
+        # pairing, :892-899), so only the first len(assignments) unfiltered rows are ever touched.
+        need = int(assignments.shape[0])
+        coords, weights, have = [], [], 0
+        for k, iteration in enumerate(pulled):
+            c = self.get_iter_coordinates(iteration)           # drops rows with NaN coordinates (:543-553)
+            assert c.shape[0] == rows_per_iter[k], f"({rows_per_iter[k]}, {self.pcoord_ndim}), {c.shape}"
+            if have < need:
+                coords.append(c)
+                # (the reference appends later iterations' weights only when they are used, :856-857)
+                weights.append(self.seg_weights[iteration] if (k == 0 or self.use_weights_in_clustering) else None)
+                have += c.shape[0]
+        iter_coords = np.concatenate(coords, axis=0) if coords else np.empty((0, self.nAtoms or 0, self.coord_ndim or 3))
+        seg_weights = np.concatenate([w for w in weights if w is not None]) if self.use_weights_in_clustering and weights \
+            else (weights[0] if weights else np.array([]))
 
-            if iteration > self.maxIter:
-                log.warning(f"At iteration {iteration} (pulled {used_iters} extra), couldn't get segments in all "
-                            f"bins, and no iterations left")
-                break
-
-            used_iters += 1
-            _iter_coords = self.get_iter_coordinates(iteration)
-            _seg_weights = self.seg_weights[iteration]
-            if used_iters == 0:
-                iter_coords = _iter_coords
-                seg_weights = _seg_weights
-                pcoords = [x for x in self.pcoord0List]
-            else:
-                iter_coords = np.append(iter_coords, _iter_coords, axis=0)
-                pcoords.extend(self.pcoord0List)
-                if self.use_weights_in_clustering:
-                    seg_weights = np.append(seg_weights, _seg_weights, axis=0)
-
-            pcoord_array = np.array(pcoords)
-            assert pcoord_array.shape[0] == iter_coords.shape[0], f"{pcoord_array.shape}, {iter_coords.shape}"
-
-            # segments whose PARENT pcoord is in the basis or target are ignored (:872-874)
-            pcoord_is_target = self.is_WE_target(pcoord_array)
-            pcoord_is_basis = self.is_WE_basis(pcoord_array)
-            pcoord_array = pcoord_array[~(pcoord_is_target | pcoord_is_basis)]
-            if len(pcoord_array) > 0:
-                we_bin_assignments = np.asarray(bin_mapper.assign(pcoord_array))
-            else:
-                we_bin_assignments = np.array([])
-            unique_bins, counts = np.unique(we_bin_assignments, return_counts=True)
-            all_bins_have_segments = np.all(counts >= min_coords)
-
-        # one batched GPU step over every bin that received segments.  NOTE: as in the reference
-        # (:892-899) the row indices computed on the basis/target-FILTERED pcoord array index the
-        # UNFILTERED coordinates and weights; reproduced deliberately.
         batch = []
         for _bin in unique_bins:
-            segs_in_bin = np.argwhere(we_bin_assignments == _bin)
+            segs_in_bin = np.argwhere(assignments == _bin)
             transformed_coords = self.coordinates.transform(processCoordinates(np.squeeze(iter_coords[segs_in_bin])))
-            weights = seg_weights[segs_in_bin].squeeze() if self.use_weights_in_clustering else None
-            batch.append((kmeans_models.cluster_models[int(_bin)], transformed_coords, weights))
+            w = seg_weights[segs_in_bin].squeeze() if self.use_weights_in_clustering else None
+            batch.append((kmeans_models.cluster_models[int(_bin)], transformed_coords, w))
         try:
             partial_fit_models(batch)
         except ValueError as e:
@@ -299,9 +350,13 @@ class ClusteringMixin:
         ``np.array(list(zip(parent, child)))`` gives the flux code)."""
         import torch
 
+        from .._pinning import PINS
+        from .. import ops as _ops
+
         self.check_connect_ray()
         self.dtrajs = []
         if self.pre_discretization_model is None:
+            # (iteration sources are shared by copies, so this snapshots the model state, not the data set)
             self.pre_discretization_model = deepcopy(self)
         else:
             log.debug("Using cached model for discretization")
@@ -314,9 +369,25 @@ class ClusteringMixin:
         pair_dtrajs = [None] * n_iters
         D = dev.D
         P = self.pcoord_ndim
-        row_bytes = 2 * (D + P) * 8
+        src = self.iteration_source
         seg_counts = [int(self.numSegments[it - 1]) if self.numSegments is not None and it <= len(self.numSegments)
                       else None for it in range(1, self.maxIter)]
+
+        featurise, transform = self.processCoordinates, self.coordinates.transform
+        # a fitted linear projection (the reference's PCA ``coordinates.transform``) is applied on the device:
+        # the featurised frames are shipped as they are
+        projection = getattr(self.coordinates, "device_projection", None)
+        projection = projection(dev.device) if callable(projection) else None
+        identity_transform = projection is not None or getattr(self.coordinates, "is_identity", False)
+        # structures can be read from the source straight into the pinned rows when nothing but a flatten stands
+        # between the stored structure and the feature row
+        default_featuriser = getattr(getattr(type(self), "processCoordinates", None), "_mwe_flatten", False) \
+            and "processCoordinates" not in self.__dict__
+        direct_read = default_featuriser and identity_transform and hasattr(src, "read_pair_into")
+        Din_hint = None
+        if projection is not None:
+            Din_hint = int(projection[0].shape[1])
+        row_bytes = 2 * ((Din_hint or D) + P) * 8
 
         # plan chunks of whole iterations; each chunk is staged in ONE pinned buffer (features | pcoords),
         # copied with one async H2D and labelled by one K0 + K1 launch sequence.  Two staging buffers
@@ -339,20 +410,22 @@ class ClusteringMixin:
 
         stream = torch.cuda.current_stream()
         slots = [dict(event=None, host=None, n=0), dict(event=None, host=None, n=0)]
-        inflight = []   # (chunk, n, labels_host, bins_host, flags_host, done_event)
+        inflight = []   # (chunk, n, labels_host, bins_host, flags_host, nan_host, done_event)
+
+        def source_owned(feat, rec):
+            """True when ``feat`` is a view of an array the iteration source holds for the model's lifetime -- only
+            those may be page-locked in place (a featuriser's temporary would be unlocked and freed while its
+            asynchronous copy is still queued)."""
+            if not getattr(src, "owns_arrays", False):
+                return False
+            owner = PINS._owner(feat)
+            return any(owner is PINS._owner(a) for a in (rec.parent_coords, rec.child_coords) if a is not None)
 
         def stage(ci, chunk):
-            from .._pinning import PINS
-
             n = sum(s for _, s in chunk)
             slot = slots[ci % 2]
             if slot["event"] is not None:
                 slot["event"].synchronize()          # the H2D that last read this buffer has finished
-            featurise, transform = self.processCoordinates, self.coordinates.transform
-            # a fitted linear projection (the reference's PCA ``coordinates.transform``) is applied on the device:
-            # the featurised frames are shipped as they are
-            projection = getattr(self.coordinates, "device_projection", None)
-            projection = projection(dev.device) if callable(projection) else None
             pool = _staging_pool()
 
             def featurise_pair(item):
@@ -362,17 +435,21 @@ class ClusteringMixin:
                     fp, fc = transform(fp), transform(fc)
                 return np.asarray(fp), np.asarray(fc)
 
-            # user featurisers / host transforms run on the staging threads (numpy releases the GIL in its loops);
-            # a featuriser that only reshapes is cheaper inline than a hand-off to a thread
-            import time as _time
-
-            t0 = _time.perf_counter()
-            feats = [featurise_pair(chunk[0])]
-            if pool is not None and len(chunk) > 1 and _time.perf_counter() - t0 > 2e-4:
-                feats += list(pool.map(featurise_pair, chunk[1:]))
+            feats = None
+            if direct_read:
+                Din = Din_hint or D
             else:
-                feats += [featurise_pair(c) for c in chunk[1:]]
-            Din = feats[0][0].shape[1] if projection is not None else D
+                # user featurisers / host transforms run on the staging threads (numpy releases the GIL in its loops);
+                # a featuriser that only reshapes is cheaper inline than a hand-off to a thread
+                import time as _time
+
+                t0 = _time.perf_counter()
+                feats = [featurise_pair(chunk[0])]
+                if pool is not None and len(chunk) > 1 and _time.perf_counter() - t0 > 2e-4:
+                    feats += list(pool.map(featurise_pair, chunk[1:]))
+                else:
+                    feats += [featurise_pair(c) for c in chunk[1:]]
+                Din = feats[0][0].shape[1] if projection is not None else D
             # pinned staging: pcoords always (small), feature rows only for iterations whose arrays cannot be
             # page-locked in place
             need = 2 * n * (Din + P)
@@ -384,26 +461,37 @@ class ClusteringMixin:
             hx, hp = hx_t.numpy(), hp_t.numpy()
             X = torch.empty((2 * n, Din), dtype=torch.float64, device=dev.device)
 
-            def fill(dst, feat):
-                np.copyto(dst, feat)
-
             pos, jobs, staged = 0, [], []
-            for (it, s), (fp, fc) in zip(chunk, feats):
-                rec = self._record(it)
+            for k, (it, s) in enumerate(chunk):
+                rec = self._record(it, coords=not direct_read)
                 hp[pos:pos + s] = rec.pcoord0[:, :P]
                 hp[n + pos:n + pos + s] = rec.pcoord1[:, :P]
+                if direct_read:
+                    def read(it=it, pos=pos, s=s):
+                        if not src.read_pair_into(it, hx[pos:pos + s], hx[n + pos:n + pos + s]):
+                            pc_, cc_ = self.iter_coordinate_pair(it)
+                            np.copyto(hx[pos:pos + s], pc_.reshape(s, -1))
+                            np.copyto(hx[n + pos:n + pos + s], cc_.reshape(s, -1))
+                    if pool is None:
+                        read()
+                    else:
+                        jobs.append(pool.submit(read))
+                    staged += [(pos, s), (n + pos, s)]
+                    pos += s
+                    continue
+                fp, fc = feats[k]
                 for off, feat in ((pos, fp), (n + pos, fc)):
                     if feat.shape != (s, Din):
                         raise ValueError(f"featurised coordinates of iteration {it} have shape {feat.shape}, expected {(s, Din)}")
-                    if PINS.ensure(feat):
+                    if source_owned(feat, rec) and PINS.ensure(feat):
                         # the model's own array is page-locked: straight to the device at link speed
                         X[off:off + s].copy_(torch.from_numpy(feat), non_blocking=True)
                     else:
                         # featurised / projected on the fly (or not lockable): stage through the pinned rows
                         if pool is None:
-                            fill(hx[off:off + s], feat)
+                            np.copyto(hx[off:off + s], feat)
                         else:
-                            jobs.append(pool.submit(fill, hx[off:off + s], feat))
+                            jobs.append(pool.submit(np.copyto, hx[off:off + s], feat))
                         staged.append((off, s))
                 pos += s
             for j in jobs:
@@ -417,27 +505,34 @@ class ClusteringMixin:
                     hi = staged[k][0] + staged[k][1]
                 X[lo:hi].copy_(hx_t[lo:hi], non_blocking=True)
                 k += 1
+            Xin = X
             if projection is not None:
-                from .. import ops as _ops
-
                 X = _ops.project(X, projection[0], projection[1])
             Pc = hp_t.to(dev.device, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(stream)
             slot["event"] = ev
             labels, bins, flags = dev.predict(X, Pc, pcoord_host=hp)
+            # segments with a NaN start / end coordinate (their transition weight is zeroed by the flux pass,
+            # _data.py:302-313): found here, where the coordinates already are on the device
+            nan_rows = _ops.rows_with_nan(Xin) if direct_read else None
             lh = torch.empty(2 * n, dtype=torch.int64, pin_memory=True)
             bh = torch.empty(2 * n, dtype=torch.int32, pin_memory=True)
             fh = torch.empty(2 * n, dtype=torch.uint8, pin_memory=True)
+            nh = None
             lh.copy_(labels, non_blocking=True); bh.copy_(bins, non_blocking=True); fh.copy_(flags, non_blocking=True)
+            if nan_rows is not None:
+                nh = torch.empty(2 * n, dtype=torch.uint8, pin_memory=True)
+                nh.copy_(nan_rows, non_blocking=True)
             done = torch.cuda.Event()
             done.record(stream)
-            inflight.append((chunk, n, lh, bh, fh, done))
+            inflight.append((chunk, n, lh, bh, fh, nh, done))
 
         with ProgressBar(progress_bar) as progress:
             task = progress.add_task(description="Discretizing trajectories", total=n_iters)
+
             def collect(item):
-                chunk, n, lh, bh, fh, done = item
+                chunk, n, lh, bh, fh, nh, done = item
                 done.synchronize()
                 labels_h, bins_h, flags_h = lh.numpy(), bh.numpy(), fh.numpy()
                 is_target = (flags_h & 2) != 0
@@ -450,10 +545,19 @@ class ClusteringMixin:
                 pairs_all[:, 0] = labels_h[:n]
                 pairs_all[:, 1] = labels_h[n:2 * n]
                 child_all = labels_h[n:2 * n].copy()
+                nan_seg = None
+                if nh is not None:
+                    nan_h = nh.numpy()
+                    nan_seg = (nan_h[:n] | nan_h[n:2 * n]) != 0
+                    if not nan_seg.any():
+                        nan_seg = False
                 pos = 0
                 for it, s in chunk:
                     dtrajs[it - 1] = child_all[pos:pos + s]
                     pair_dtrajs[it - 1] = pairs_all[pos:pos + s]
+                    if nan_seg is not None:
+                        self.note_nan_segments(it, np.zeros(0, np.int64) if nan_seg is False
+                                               else np.flatnonzero(nan_seg[pos:pos + s]))
                     pos += s
                 progress.update(task, advance=len(chunk))
 
@@ -499,3 +603,222 @@ class ClusteringMixin:
             if closest >= _bin_idx:
                 closest += 1
         return closest
+
+    # ------------------------------------------------------------------------------------------
+    def organize_stratified(self, use_ray=True, progress_bar=None):
+        """reference: _clustering.py:920-1142.  Removes every cluster outside the largest strongly connected set
+        of the raw flux matrix from its WE bin's model, remaps WE bins that lost all their clusters, then runs the
+        hot path a second time: re-discretize (K0 + K1), per-cluster pcoord statistics (group-by-label), re-flux
+        (K3), and orders the cleaned matrix by mean pcoord."""
+        fmatrix_original = self.fluxMatrixRaw.copy()
+        fmatrix = self.fluxMatrixRaw.copy()
+        fmatrix[-1, -2] = 1.0
+        sets = connected_sets(fmatrix, directed=True)
+        start_cleaning_idx = 1
+        if len(sets) == 1:
+            log.info("Nothing to clean")
+            states_to_remove = np.array([], dtype=np.int64)
+        else:
+            states_to_remove = np.concatenate(sets[start_cleaning_idx:])
+            log.debug(f"Cleaning states {states_to_remove}")
+
+        models = self.clusters.cluster_models
+        nbins = self.clusters.bin_mapper.nbins
+        sizes = np.array([len(m.cluster_centers_) if hasattr(m, "cluster_centers_") else 0 for m in models], dtype=np.int64)
+        offsets = np.concatenate([[0], np.cumsum(sizes)])
+        remove = np.zeros(max(int(offsets[-1]), self.fluxMatrixRaw.shape[0]), dtype=bool)
+        remove[states_to_remove] = True
+        empty_we_bins = set()
+        for we_bin in range(nbins):
+            lo, hi = int(offsets[we_bin]), int(offsets[we_bin + 1])
+            drop = np.flatnonzero(remove[lo:hi])
+            if drop.size == 0:
+                if hi == lo:
+                    empty_we_bins.add(we_bin)
+                continue
+            if drop.size == hi - lo:
+                empty_we_bins.add(we_bin)
+            # (a bin that loses everything keeps a zero-row centre array, as np.delete leaves it in the reference)
+            models[we_bin].cluster_centers_ = np.delete(models[we_bin].cluster_centers_, drop, 0)
+
+        log.info(f"Started with {self.n_clusters} clusters, and removed {len(states_to_remove)}")
+        self.n_clusters = self.n_clusters - len(states_to_remove)
+        assert self.n_clusters > 1, "All clusters would be cleaned! You probably need more data, fewer clusters, or both."
+
+        populated_we_bins = np.setdiff1d(range(nbins), list(empty_we_bins))
+        if len(empty_we_bins) > 0:
+            log.warning(f"All clusters were cleaned from bins {empty_we_bins} (This is normal for the source/target WE "
+                        f"bins, and this can be ignored if only those are listed here.)")
+        for empty_we_bin in empty_we_bins:
+            self.clusters.we_remap[empty_we_bin] = self.find_nearest_bin(self.clusters.bin_mapper, empty_we_bin,
+                                                                         populated_we_bins)
+        for we_bin in range(nbins):
+            target = self.clusters.we_remap[we_bin]
+            if not hasattr(models[target], "cluster_centers_"):
+                log.error(f"Error obtaining clusters for WE bin {we_bin}, remapped to {target}. "
+                          f"Target {self.clusters.target_bins}, basis {self.clusters.basis_bins}")
+                raise AttributeError(f"'{type(models[target]).__name__}' object has no attribute 'cluster_centers_'")
+
+        # re-discretize on the cleaned centres
+        self.clusters.toggle = False
+        self.clusters.processing_from = False
+        self.launch_ray_discretization(progress_bar=progress_bar)
+
+        pcoord_sort_indices = self.get_cluster_centers()
+
+        # and recalculate the flux matrix (the toggle is vestigial: get_fluxMatrix reads pair_dtrajs)
+        self.clusters.toggle = True
+        self.clusters.processing_from = True
+        self.get_fluxMatrix(*self._fluxMatrixParams, use_ray=use_ray, progress_bar=progress_bar)
+        self.clusters.processing_from = False
+        self.clusters.toggle = False
+
+        fluxMatrix = self.fluxMatrixRaw[pcoord_sort_indices, :][:, pcoord_sort_indices]
+        self.fluxMatrix = fluxMatrix / np.sum(fluxMatrix)
+        self.fluxMatrixRaw = fmatrix_original
+
+        self.indBasis = np.array([self.n_clusters])
+        self.indTargets = np.array([self.n_clusters + 1])
+        self.nBins = self.n_clusters + 2
+        self.update_sorted_cluster_centers()
+        self.cluster_mapping = {x: x for x in range(self.n_clusters + 2)}
+
+        fmatrix = self.fluxMatrix.copy()
+        fmatrix[-1, -2] = 1.0
+        sets = connected_sets(fmatrix, directed=True)
+        log.debug(f"After cleaning, shape is {fmatrix.shape} and disconnected sets are: {sets[1:]}")
+        assert len(sets[start_cleaning_idx:]) == 0, "Still not clean after cleaning!"
+
+    # ------------------------------------------------------------------------------------------
+    def _stacked_dtrajs(self, dtrajs=None):
+        dtrajs = self.dtrajs if dtrajs is None else dtrajs
+        if len(dtrajs) == 0:
+            return np.zeros(0, dtype=np.int64)
+        return np.ascontiguousarray(np.concatenate([np.asarray(d, dtype=np.int64) for d in dtrajs]))
+
+    def get_cluster_centers(self):
+        """reference: _clustering.py:1528-1599.  Mean / min / max of pcoord dimension 0 over the members of every
+        cluster, then the permutation that sorts the clusters by that mean.
+
+        The reference loops over clusters and, for each, runs ``np.where`` over every iteration's dtraj
+        (O(n_clusters x frames)); here the stacked dtrajs are grouped by label once on the device and every label is
+        reduced by one warp.  Quirks kept: only pcoord dimension 0 is read (``pcoordSet[idx, 0]``) and broadcast over
+        the pcoord dimensions; the basis / target rows take ``self.basis_bin_center`` / ``self.target_bin_center``
+        (singular: attributes the reference initialises to None and never sets -> NaN rows, which argsort puts
+        last); clusters without members get NaN and a warning."""
+        import torch
+
+        from .. import ops
+        from ..engine import require_cuda
+
+        n = int(self.n_clusters)
+        P = self.pcoord_ndim
+        centers = np.zeros((n + 2, P))
+        ranges = np.zeros((n + 2, P, 2))
+        centers[n + 1] = getattr(self, "target_bin_center", None)
+        centers[n] = getattr(self, "basis_bin_center", None)
+        ranges[n + 1] = [getattr(self, "target_bin_center", None)] * 2
+        ranges[n] = [getattr(self, "basis_bin_center", None)] * 2
+
+        labels = self._stacked_dtrajs()
+        N = labels.shape[0]
+        if self.pcoordSet is None or self.pcoordSet.shape[0] < N:
+            raise IndexError(f"pcoordSet holds {0 if self.pcoordSet is None else self.pcoordSet.shape[0]} segments but "
+                             f"the dtrajs hold {N}; run get_coordSet() over the discretized iterations first")
+        dev = require_cuda()
+        lab_d = torch.from_numpy(labels).to(dev)
+        val_d = torch.from_numpy(np.ascontiguousarray(self.pcoordSet[:N, 0])).to(dev)
+        members, seg_start = ops.group_by_label(lab_d, n)
+        count, total, vmin, vmax = ops.label_stats(val_d, members, seg_start, n)
+        members_h = members.cpu().numpy()
+        seg_h = seg_start.cpu().numpy()
+        count_h, total_h, vmin_h, vmax_h = (t.cpu().numpy() for t in (count, total, vmin, vmax))
+
+        group_size = np.diff(seg_h[: n + 1])
+        empty = group_size == 0
+        for cluster in np.flatnonzero(empty):
+            log.warning(f"No trajectories in cluster {cluster}! (Target was {n + 1})")
+        with np.errstate(invalid="ignore", divide="ignore"):
+            mean = total_h / count_h                  # members that are all NaN: 0/0 = NaN, as nanmean gives
+        lo = np.where(count_h > 0, vmin_h, np.nan)
+        hi = np.where(count_h > 0, vmax_h, np.nan)
+        centers[:n] = mean[:, None]
+        ranges[:n, :, 0] = lo[:, None]
+        ranges[:n, :, 1] = hi[:, None]
+
+        pcoord_sort_indices = np.argsort(centers[:, 0])
+        self.targetRMSD_centers = centers[pcoord_sort_indices]
+        self.targetRMSD_minmax = ranges[pcoord_sort_indices]
+        # per-cluster member pcoords, as views of ONE gathered array (the reference builds a Python list per cluster)
+        gathered = self.pcoordSet[:N, 0][members_h[: seg_h[n]]] if N else np.zeros(0)
+        per_cluster = np.empty(n + 2, dtype=object)
+        for c in range(n):
+            per_cluster[c] = gathered[seg_h[c]:seg_h[c + 1]]
+        per_cluster[n] = []
+        per_cluster[n + 1] = []
+        self.targetRMSD_all = per_cluster[pcoord_sort_indices]
+        return pcoord_sort_indices
+
+    def update_sorted_cluster_centers(self):
+        """reference: _clustering.py:1601-1611."""
+        log.info("Note: Sorting bins, assuming that pcoord 0 is meaningful for sorting")
+        bin_centers = self.targetRMSD_centers[:, 0]
+        bin_centers[self.indTargets] = self.target_bin_centers
+        bin_centers[self.indBasis] = self.basis_bin_centers
+        self.all_centers = bin_centers
+        self.sorted_centers = np.argsort(bin_centers)
+
+    def update_cluster_structures(self, build_pcoord_cache=False):
+        """reference: _clustering.py:1398-1526.  ``cluster_structures[c]`` / ``cluster_structure_weights[c]``: the
+        end structures and WE weights of every segment discretized into cluster ``c`` over iterations
+        ``1 .. maxIter-2``, in (iteration, segment) order.  The grouping is one device group-by-label of the stacked
+        dtrajs; the structures are then gathered per cluster."""
+        import torch
+
+        from .. import ops
+        from ..engine import require_cuda
+
+        assert self.clusters is not None, "Clusters have not been computed!"
+        last = self.maxIter - 1
+        iters = list(range(1, last))
+        seg_counts = [int(self.numSegments[it - 1]) for it in iters]
+        labels = self._stacked_dtrajs([np.asarray(self.dtrajs[it - 1])[:s] for it, s in zip(iters, seg_counts)])
+        N = labels.shape[0]
+        coords, weights, pcoords, where = [], [], [], []
+        for it, s in zip(iters, seg_counts):
+            if it not in self.seg_weights.keys():
+                self.load_iter_data(it)
+            c = self.get_iter_coordinates(it)
+            coords.append(c[:s])
+            weights.append(np.asarray(self.seg_weights[it])[:s])
+            pcoords.append(self.pcoord1List[:s])
+            where.append(np.stack([np.full(s, it), self.segindList[:s], self.westList[:s]], axis=1))
+        if N and any(int(lbl) in self.removed_clusters for lbl in np.unique(labels)):
+            raise Exception("This dtraj point was in a removed cluster -- this should never happen!")
+        n_labels = int(labels.max()) + 1 if N else 1
+        dev = require_cuda()
+        members, seg_start = ops.group_by_label(torch.from_numpy(labels).to(dev), n_labels)
+        members_h, seg_h = members.cpu().numpy(), seg_start.cpu().numpy()
+        all_coords = np.concatenate(coords) if coords else np.zeros((0, 0, 0))
+        all_weights = np.concatenate(weights) if weights else np.zeros(0)
+        all_pcoords = np.concatenate(pcoords) if pcoords else np.zeros((0, self.pcoord_ndim))
+        all_where = np.concatenate(where) if where else np.zeros((0, 3), dtype=np.int64)
+        cluster_structures, cluster_structure_weights, structure_iteration_segments = {}, {}, {}
+        pcoord_cache = {} if build_pcoord_cache else None
+        # dictionary keys in order of first appearance, as the reference's incremental construction gives
+        _, first_pos = np.unique(labels, return_index=True)
+        for c in labels[np.sort(first_pos)]:
+            idx = members_h[seg_h[c]:seg_h[c + 1]]
+            c = int(c)
+            cluster_structures[c] = list(all_coords[idx])
+            cluster_structure_weights[c] = list(all_weights[idx])
+            structure_iteration_segments[c] = [[int(a), int(b), self.fileList[int(f)] if self.fileList else int(f)]
+                                               for a, b, f in all_where[idx]]
+            if build_pcoord_cache:
+                pcoord_cache[c] = list(all_pcoords[idx])
+        assert len(cluster_structures) == len(cluster_structure_weights), "Structures and weights have different numbers of bins?"
+        self.cluster_structures = cluster_structures
+        self.cluster_structure_weights = cluster_structure_weights
+        self.pcoord_cache = pcoord_cache
+        self.structure_iteration_segments = structure_iteration_segments
+        log.debug("Cluster structure mapping completed.")

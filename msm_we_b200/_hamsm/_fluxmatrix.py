@@ -222,6 +222,21 @@ class FluxMatrixMixin:
         errors.check()
         return dense
 
+    def organize_fluxMatrix(self, use_ray=False, progress_bar=None, **args):
+        """reference: _fluxmatrix.py:347-415.  Dispatch to the cleaning pass of the clustering method; only the
+        stratified one exists on this path (``organize_aggregated`` raises DeprecationWarning in the reference)."""
+        if not hasattr(self, "clustering_method") or self.clustering_method is None:
+            log.warning("self.clustering_method is not set. This may be a model saved before stratified was implemented, "
+                        "or you may not have run cluster_coordinates! Assuming the former and setting to aggregated.")
+            self.clustering_method = "aggregated"
+        if self.clustering_method == "stratified":
+            self.organize_stratified(use_ray, progress_bar)
+        elif self.clustering_method == "aggregated":
+            raise NotImplementedError("msm_we_b200 implements the stratified path only (organize_aggregated is deprecated "
+                                      "in the reference, _fluxmatrix.py:452)")
+        else:
+            raise Exception(f"Unrecognized clustering_method (Had: {self.clustering_method})")
+
     def get_iter_fluxMatrix(self, n_iter):
         """reference: _fluxmatrix.py:21-72.  Dense ``(n_clusters+2)^2`` ndarray for one iteration."""
         return self._flux_device([n_iter]).cpu().numpy()

@@ -42,6 +42,7 @@ SIGNATURES = {
     "mwe_host_unregister": (_int, [_p]),
     "mwe_set_timing_events": (_int, [_p, _p]),
     "mwe_bin_flags_f64": (_int, [_p, _i64, _int, _int, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "mwe_rows_with_nan_f64": (_int, [_p, _i64, _int, _i64, _p, _p]),
     "mwe_assign_workspace_bytes": (_sz, [_i64, _i32]),
     "mwe_assign_workspace_bytes_ex": (_sz, [_i64, _i32, _int, _i32, _int]),
     "mwe_centers_sqnorm_f64": (_int, [_p, _i64, _int, _p, _p]),
@@ -51,6 +52,8 @@ SIGNATURES = {
     "mwe_minibatch_update_f64": (_int, [_p, _i64, _int, _i64, _p, _p, _i64, _p, _p, _p, _sz, _p]),
     "mwe_lloyd_finalize_f64": (_int, [_p, _p, _i64, _int, _p, _p]),
     "mwe_minibatch_finalize_f64": (_int, [_p, _p, _i64, _int, _p, _p, _p]),
+    "mwe_group_by_label": (_int, [_p, _i64, _i64, _p, _p, _p, _sz, _p]),
+    "mwe_label_stats_f64": (_int, [_p, _i64, _p, _p, _i64, _p, _p, _p, _p, _p]),
     "mwe_flux_workspace_bytes": (_sz, [_i64]),
     "mwe_flux_accumulate_f64": (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _int, _p, _i64, _p, _p, _p, _p, _p, _p, _sz, _p, _p]),
     "mwe_divide_f64": (_int, [_p, _i64, _f64, _p]),

@@ -124,6 +124,28 @@ __global__ void __launch_bounds__(BF_THREADS) bin_flags_kernel(const BinFlagPara
     }
 }
 
+
+// Rows holding a NaN.  reference: get_transition_data_lag0 zeroes the weight of every segment whose start or end
+// structure contains a NaN (msm_we/_hamsm/_data.py:302-313) and re-reads all structures in the flux pass only to
+// find them; the discretization pass has the rows on the device anyway.  One warp per row, coalesced.
+__global__ void __launch_bounds__(256)
+    rows_with_nan_kernel(const double* __restrict__ X, int64_t N, int D, int64_t ldx, uint8_t* __restrict__ out) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < N; r += warps) {
+        const double* row = X + r * ldx;
+        bool bad = false;
+        for (int c = lane; c < D; c += 32) {
+            const double x = row[c];
+            bad |= (x != x);
+        }
+        const unsigned any = __ballot_sync(0xffffffffu, bad);
+        if (lane == 0) out[r] = any ? 1 : 0;
+    }
+}
+
 }  // namespace mwe
 
 extern "C" int mwe_bin_flags_f64(const double* pcoord, int64_t N, int P, int mapper_kind, const float* mapper_data,
@@ -170,5 +192,18 @@ extern "C" int mwe_bin_flags_f64(const double* pcoord, int64_t N, int P, int map
     if (P == 1) MWE_CHECK_CUDA(launch_pdl(bin_flags_kernel<1>, g, b, 0, st, p));
     else if (P == 2) MWE_CHECK_CUDA(launch_pdl(bin_flags_kernel<2>, g, b, 0, st, p));
     else MWE_CHECK_CUDA(launch_pdl(bin_flags_kernel<0>, g, b, 0, st, p));
+    return MWE_OK;
+}
+
+extern "C" int mwe_rows_with_nan_f64(const double* X, int64_t N, int D, int64_t ldx, uint8_t* out, void* stream) {
+    using namespace mwe;
+    MWE_REQUIRE(N >= 0 && D >= 1 && ldx >= D, "rows_with_nan: bad shape");
+    if (N == 0) return MWE_OK;
+    MWE_REQUIRE(X && out, "rows_with_nan: null pointer");
+    int64_t blocks = (N + 7) / 8;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    MWE_CHECK_CUDA(launch_pdl(rows_with_nan_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                              X, N, D, ldx, out));
     return MWE_OK;
 }

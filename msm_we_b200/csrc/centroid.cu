@@ -267,6 +267,85 @@ static int centroid_run(const double* X, int64_t N, int D, int64_t ldx, const do
     return MWE_OK;
 }
 
+
+// ---- label-keyed grouping and per-label statistics ---------------------------------
+// reference: ClusteringMixin.get_cluster_centers (msm_we/_hamsm/_clustering.py:1528-1599) walks all dtrajs once
+// PER CLUSTER (np.where over every iteration) and takes nanmean / nanmin / nanmax of the members' end pcoords;
+// update_cluster_structures (:1398-1526) appends every segment to a per-cluster Python list.  Both are a
+// group-by-label: the stable sort of K2 yields each label's members contiguous and in input order.
+
+// One warp per label.  Lane l takes members s+l, s+l+32, ... in order; the 32 partials are combined with a fixed
+// butterfly, so the result does not depend on scheduling.  NaN values are skipped (numpy nan* semantics).
+__global__ void __launch_bounds__(256)
+    label_stats_kernel(const double* __restrict__ v, int64_t ldv, const uint32_t* __restrict__ members,
+                       const int32_t* __restrict__ seg_start, int64_t n_labels, int64_t* __restrict__ count,
+                       double* __restrict__ sum, double* __restrict__ mn, double* __restrict__ mx) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t k = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); k < n_labels; k += warps) {
+        const int32_t s = seg_start[k], e = seg_start[k + 1];
+        double acc = 0.0, lo = __longlong_as_double(0x7ff0000000000000LL), hi = __longlong_as_double(0xfff0000000000000LL);
+        long long c = 0;
+        for (int32_t m = s + lane; m < e; m += 32) {
+            const double x = v[(int64_t)members[m] * ldv];
+            if (x == x) {
+                acc += x;
+                lo = fmin(lo, x);
+                hi = fmax(hi, x);
+                ++c;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+        }
+        if (lane == 0) {
+            count[k] = c;
+            sum[k] = acc;
+            mn[k] = lo;
+            mx[k] = hi;
+        }
+    }
+}
+
+static int group_by_label(const int64_t* label, int64_t N, int64_t n_labels, uint32_t* members_out, int32_t* seg_start_out,
+                          void* workspace, size_t workspace_bytes, cudaStream_t s) {
+    MWE_REQUIRE(N >= 0 && N < ((int64_t)1 << 31), "group_by_label: N must be < 2^31 per call");
+    MWE_REQUIRE(n_labels >= 1 && n_labels < ((int64_t)1 << 31), "group_by_label: bad label count");
+    MWE_REQUIRE(members_out && seg_start_out && (label || N == 0), "group_by_label: null pointer");
+    if (workspace_bytes < centroid_ws_bytes(N, n_labels)) {
+        set_last_error("group_by_label: workspace too small (%zu < %zu)", workspace_bytes, centroid_ws_bytes(N, n_labels));
+        return MWE_E_WORKSPACE;
+    }
+    if (N == 0) {
+        MWE_CHECK_CUDA(cudaMemsetAsync(seg_start_out, 0, (size_t)(n_labels + 2) * sizeof(int32_t), s));
+        return MWE_OK;
+    }
+    Carver cv(workspace, workspace_bytes);
+    uint64_t* keys = cv.take<uint64_t>((size_t)N);
+    uint32_t* vals = cv.take<uint32_t>((size_t)N);
+    (void)cv.take<int32_t>((size_t)n_labels + 2);
+    (void)cv.take<int32_t>((size_t)n_labels + 2);
+    const size_t sort_bytes = sort_workspace_bytes(N);
+    void* sort_ws = cv.take<char>(sort_bytes);
+    uint64_t* ks = keys;
+    uint32_t* vs = vals;
+    int64_t blocks = (N + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    MWE_CHECK_CUDA(launch_pdl(centroid_keys_kernel, dim3((unsigned)blocks), dim3(256), 0, s, label, N, n_labels, keys, vals));
+    int rc = sort_pairs(keys, vals, N, ceil_log2_u64((uint64_t)n_labels + 1), sort_ws, sort_bytes, s, &ks, &vs);
+    if (rc != MWE_OK) return rc;
+    MWE_CHECK_CUDA(launch_pdl(centroid_bounds_kernel, dim3((unsigned)blocks), dim3(256), 0, s, ks, N, n_labels, seg_start_out));
+    MWE_CHECK_CUDA(cudaMemcpyAsync(members_out, vs, (size_t)N * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    return MWE_OK;
+}
+
 }  // namespace mwe
 
 extern "C" size_t mwe_centroid_workspace_bytes(int64_t N, int64_t sumK) { return mwe::centroid_ws_bytes(N, sumK); }
@@ -310,5 +389,25 @@ extern "C" int mwe_minibatch_finalize_f64(const double* sum_wx, const double* su
     minibatch_finalize_kernel<<<(unsigned)blocks, 256, 0, s>>>(sum_wx, sum_w, sumK, D, centers, counts);
     counts_add_kernel<<<(unsigned)((sumK + 255) / 256), 256, 0, s>>>(counts, sum_w, sumK);
     MWE_CHECK_LAUNCH();
+    return MWE_OK;
+}
+
+extern "C" int mwe_group_by_label(const int64_t* label, int64_t N, int64_t n_labels, uint32_t* members_out,
+                                  int32_t* seg_start_out, void* workspace, size_t workspace_bytes, void* stream) {
+    return mwe::group_by_label(label, N, n_labels, members_out, seg_start_out, workspace, workspace_bytes,
+                               static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mwe_label_stats_f64(const double* values, int64_t ldv, const uint32_t* members, const int32_t* seg_start,
+                                   int64_t n_labels, int64_t* count, double* sum, double* vmin, double* vmax, void* stream) {
+    using namespace mwe;
+    MWE_REQUIRE(n_labels >= 0 && ldv >= 1, "label_stats: bad shape");
+    if (n_labels == 0) return MWE_OK;
+    MWE_REQUIRE(values && members && seg_start && count && sum && vmin && vmax, "label_stats: null pointer");
+    int64_t blocks = (n_labels + 7) / 8;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    MWE_CHECK_CUDA(launch_pdl(label_stats_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                              values, ldv, members, seg_start, n_labels, count, sum, vmin, vmax));
     return MWE_OK;
 }

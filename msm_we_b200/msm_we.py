@@ -22,6 +22,8 @@ from ._logging import log
 class Coordinates:
     """Identity transform (reference: msm_we/_hamsm/_dimensionality.py:23-34)."""
 
+    is_identity = True
+
     def __init__(self):
         self.explanation = "coordinate object"
 
@@ -84,6 +86,15 @@ class modelWE(ClusteringMixin, DataMixin, FluxMatrixMixin):
         self.pre_discretization_model = None
         self.dimReduceMethod = "none"
         self.seg_weights = {}
+        # (sic) the reference initialises these singular names to None and never sets them; get_cluster_centers reads
+        # them (msm_we.py:98,109; _clustering.py:1544-1555)
+        self.target_bin_center = None
+        self.basis_bin_center = None
+        self.reference_coord = None
+        self.reference_structure = None
+        self.basis_coords = None
+        self.indBasis = None
+        self.indTargets = None
 
     # the reference expects users to monkey-patch this featurizer (docs/usage.rst:41-60)
     def processCoordinates(self, coords):
@@ -93,6 +104,10 @@ class modelWE(ClusteringMixin, DataMixin, FluxMatrixMixin):
         if coords.ndim == 2 and self.nAtoms is not None and coords.shape == (self.nAtoms, self.coord_ndim):
             return coords.reshape(1, -1)
         return coords
+
+    # marks the default featuriser: when nothing but this flatten stands between a stored structure and its feature
+    # row, the staging code may read structures from the iteration source straight into its pinned buffer
+    processCoordinates._mwe_flatten = True
 
     # ------------------------------------------------------------------------------------------
     def initialize(self, fileSpecifier, refPDBfile=None, modelName=None, basis_pcoord_bounds=None,
@@ -117,35 +132,93 @@ class modelWE(ClusteringMixin, DataMixin, FluxMatrixMixin):
             self.iteration_source = fileSpecifier
             self.fileList = []
         else:
-            files = fileSpecifier.split(" ") if isinstance(fileSpecifier, str) else list(fileSpecifier)
+            if isinstance(fileSpecifier, str):
+                log.warning("HDF5 file paths were provided in a string -- this is now deprecated, please pass as a list "
+                            "of paths.")
+                files = fileSpecifier.split(" ")
+            else:
+                files = list(fileSpecifier)
             self.fileList = files
-            self.iteration_source = H5IterationSource(files, auxpath=auxpath, pcoord_ndim=pcoord_ndim)
+            self.iteration_source = H5IterationSource(files, auxpath=auxpath, pcoord_ndim=pcoord_ndim,
+                                                      pcoord_len=self.pcoord_len)
         self.n_data_files = len(self.fileList)
         if tau is None:
             log.warning("No tau provided, defaulting to 1.")
             tau = 1.0
         self.tau = float(tau)
-        self.dimReduceMethod = dim_reduce_method
+        if refPDBfile is not None:
+            self.set_topology(refPDBfile)
+        if dim_reduce_method is None:
+            log.warning("No dimensionality reduction method provided to initialize(). Defaulting to pca.")
+            self.dimReduceMethod = "pca"
+        else:
+            self.dimReduceMethod = dim_reduce_method
         if self.dimReduceMethod == "none":
             self.coordinates = Coordinates()
         self.use_weights_in_clustering = use_weights_in_clustering
         try:
             self.load_iter_data(1)
-            rec = self.iteration_source.get(1)
+            rec = self._record(1)
             c = rec.child_coords
-            self.nAtoms = c.shape[1]
-            self.coord_ndim = c.shape[2] if c.ndim == 3 else 1
+            if self.nAtoms is None:
+                self.nAtoms = c.shape[1]
+                self.coord_ndim = c.shape[2] if c.ndim == 3 else 1
             self.coordsExist = True
         except KeyError:
-            log.error("Problem getting coordinates, they don't exist yet.")
+            if not _suppress_boundary_warning:
+                log.warning("Model initialized, but coordinates do not exist yet.")
             self.coordsExist = False
         log.debug("msm_we model successfully initialized")
 
+    def set_topology(self, topology):
+        """reference: msm_we.py:1011-1078.  Only ``nAtoms`` / ``coord_ndim`` matter to the hot path; a dict
+        ``{"coords", "nAtoms", "coord_ndim"}`` needs no MD library, PDB / prmtop paths go through mdtraj when it is
+        importable."""
+        if isinstance(topology, dict):
+            self.reference_coord = topology["coords"]
+            self.nAtoms = topology["nAtoms"]
+            self.coord_ndim = topology["coord_ndim"]
+            return
+        if isinstance(topology, str) and topology[-3:] == "dat":
+            self.reference_coord = np.loadtxt(topology)
+            self.nAtoms = 1
+            self.coord_ndim = 3
+            return
+        try:
+            import mdtraj as md
+        except ImportError:
+            log.warning("mdtraj is not importable: the topology is not loaded, nAtoms is taken from the stored coordinates")
+            return
+        if isinstance(topology, str):
+            struct = md.load_prmtop(topology) if topology[-6:] == "prmtop" else md.load(topology)
+        elif type(topology) in [md.Trajectory, md.Topology]:
+            struct = topology
+        else:
+            raise NotImplementedError("Unsupported topology")
+        self.reference_structure = struct
+        self.nAtoms = struct.n_atoms if hasattr(struct, "n_atoms") and not hasattr(struct, "topology") else struct.topology.n_atoms
+        if hasattr(struct, "_xyz"):
+            self.reference_coord = np.squeeze(struct._xyz)
+        self.coord_ndim = 3
+
     def dimReduce(self, *args, **kwargs):
-        """Only the identity ('none') is fitted here; fitting PCA/TICA/VAMP is out of scope.  Assign a fitted
-        object with a ``.transform`` (e.g. ``LinearCoordinates``) to ``self.coordinates`` to use one."""
-        if self.dimReduceMethod == "none" or self.coordinates is None:
+        """reference: _dimensionality.py:110-345.  FITTING a dimensionality reduction (streaming PCA / TICA / VAMP) is
+        outside the path this package covers; APPLYING a fitted one is on it (``LinearCoordinates`` runs on the
+        device).  So: ``"none"`` installs the identity; any other method requires that a fitted object with a
+        ``.transform`` has been assigned to ``self.coordinates`` beforehand -- silently clustering on raw features
+        instead would give a different discretization than the reference's."""
+        if self.dimReduceMethod == "none":
             self.coordinates = Coordinates()
+            self.ndim = None if self.nAtoms is None else int(self.coord_ndim) * int(self.nAtoms)
+            return
+        if self.coordinates is None or isinstance(self.coordinates, Coordinates):
+            raise NotImplementedError(
+                f"dim_reduce_method={self.dimReduceMethod!r}: msm_we_b200 does not fit dimensionality reductions. Fit it "
+                f"with the reference (or sklearn) and assign the result to model.coordinates (e.g. "
+                f"LinearCoordinates(components_, mean_)) before dimReduce(); arguments {sorted(kwargs)} were not used.")
+        comp = getattr(self.coordinates, "components_", None)
+        if comp is not None:
+            self.ndim = int(np.shape(comp)[0])
 
     # ---- bounds (reference: msm_we.py:279-440) -------------------------------------------------
     def _check_bounds(self, bounds):
@@ -224,16 +297,32 @@ class modelWE(ClusteringMixin, DataMixin, FluxMatrixMixin):
         return self._in_region(pcoords, self.target_pcoord_bounds)
 
     # ---- one-shot driver (reference: msm_we.py:588-882), hot-path steps ----------------------------
+    HOST_ANALYSIS_STEPS = ("get_Tmatrix", "get_steady_state", "get_steady_state_target_flux")
+
+    def _host_analysis(self):
+        """Transition matrix / steady state / target flux are small host-side linear algebra the north star leaves on
+        the host; they live in the reference's AnalysisMixin, which can be mixed into this class unchanged (it reads
+        ``fluxMatrix``, ``indBasis``, ``indTargets``, ``nBins``).  Runs them when present; returns whether it did."""
+        for step in self.HOST_ANALYSIS_STEPS:
+            if not hasattr(self, step):
+                log.info(f"{step} is not part of msm_we_b200 (host-side analysis); stopping after the cleaned flux matrix")
+                return False
+            getattr(self, step)()
+        return True
+
     def build_analyze_model(self, file_paths, ref_struct, modelName, basis_pcoord_bounds, target_pcoord_bounds,
                             dimreduce_method, tau, n_clusters, ray_kwargs={}, max_coord_iter=-1, stratified=True,
                             streaming=True, use_ray=True, fluxmatrix_iters=[1, -1], fluxmatrix_iters_to_use=None,
                             cross_validation_groups=2, cross_validation_blocks=4, show_live_display=True,
                             allow_validation_failure=False, step_kwargs={}):
+        """reference: msm_we.py:588-882, same steps in the same order (no Ray initialisation, no live table)."""
         model = self
         model.initialize(fileSpecifier=file_paths, refPDBfile=ref_struct, modelName=modelName,
                          basis_pcoord_bounds=basis_pcoord_bounds, target_pcoord_bounds=target_pcoord_bounds,
                          dim_reduce_method=dimreduce_method, tau=tau, **step_kwargs.get("initialize", {}))
         model.get_iterations()
+        _max_coord_iter = [max_coord_iter, model.maxIter][max_coord_iter == -1]
+        model.get_coordSet(_max_coord_iter)
         model.dimReduce(**step_kwargs.get("dimReduce", {}))
         model.cluster_coordinates(n_clusters=n_clusters, streaming=streaming, use_ray=use_ray, stratified=stratified,
                                   store_validation_model=cross_validation_groups > 0,
@@ -244,14 +333,55 @@ class modelWE(ClusteringMixin, DataMixin, FluxMatrixMixin):
             _fluxmatrix_iters[1] = model.maxIter
         model.get_fluxMatrix(n_lag=0, first_iter=_fluxmatrix_iters[0], last_iter=_fluxmatrix_iters[1],
                              iters_to_use=fluxmatrix_iters_to_use, use_ray=use_ray, **step_kwargs.get("fluxmatrix", {}))
-        # downstream host steps run only when the corresponding reference mixins are present
-        for step, kw in (("organize_fluxMatrix", {"use_ray": use_ray, **step_kwargs.get("organize", {})}),
-                         ("get_Tmatrix", {}), ("get_steady_state", {}), ("get_steady_state_target_flux", {})):
-            if not hasattr(model, step):
-                log.info(f"{step} is not part of msm_we_b200 (host-side analysis); stopping after the flux matrix")
-                break
-            getattr(model, step)(**kw)
+        model.organize_fluxMatrix(use_ray=use_ray, **step_kwargs.get("organize", {}))
+        model._host_analysis()
+        if cross_validation_groups > 0:
+            try:
+                model.do_block_validation(cross_validation_groups=cross_validation_groups,
+                                          cross_validation_blocks=cross_validation_blocks, use_ray=use_ray,
+                                          **step_kwargs.get("block_validation", {}))
+            except Exception as e:
+                log.error(e)
+                if not allow_validation_failure:
+                    raise e
         return model
+
+    def do_block_validation(self, cross_validation_groups, cross_validation_blocks, use_ray=True, progress_bar=None):
+        """reference: msm_we.py:884-1009.  The iterations are cut into ``cross_validation_blocks`` uniform blocks dealt
+        round-robin to ``cross_validation_groups`` groups; every group gets a copy of the post-clustering model and runs
+        the flux hot path (K3 over its iteration subset), the cleaning pass (re-discretize + re-flux) and, when mixed in,
+        the host analysis.  Copies share the iteration source, so a group costs the model state, not the data set."""
+        from copy import deepcopy
+
+        assert hasattr(self, "post_cluster_model") and self.post_cluster_model is not None, (
+            "Perform clustering with cluster_coordinates() before attempting"
+            "block validation -- self.post_cluster_model is not set.")
+        validation_models = [deepcopy(self.post_cluster_model) for _ in range(cross_validation_groups)]
+        max_iter = self.post_cluster_model.maxIter
+        iters_per_block = max_iter // cross_validation_blocks
+        block_iterations = [[start, start + iters_per_block] for start in range(1, max_iter, iters_per_block)]
+        block_iterations[-1][-1] = block_iterations[-1][-1] - 1
+        group_blocks = [range(start, cross_validation_blocks, cross_validation_groups)
+                        for start in range(cross_validation_groups)]
+        validation_iterations = []
+        for group in range(cross_validation_groups):
+            group_iterations = []
+            for block in group_blocks[group]:
+                group_iterations.extend(range(*block_iterations[block]))
+            validation_iterations.append(group_iterations)
+            try:
+                log.info(f"Beginning analysis of cross-validation group {group + 1}/{cross_validation_groups}.")
+                _model = validation_models[group]
+                _model.get_fluxMatrix(0, iters_to_use=validation_iterations[group], use_ray=use_ray,
+                                      progress_bar=progress_bar)
+                _model.organize_fluxMatrix(use_ray=use_ray, progress_bar=progress_bar)
+                _model._host_analysis()
+            except Exception as e:
+                log.error("Error during block validation!")
+                log.exception(e)
+                raise modelWE.BlockValidationError(e)
+        self.validation_iterations = validation_iterations
+        self.validation_models = validation_models
 
 
 __all__ = ["modelWE", "Coordinates", "LinearCoordinates", "ArrayIterationSource"]

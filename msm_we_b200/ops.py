@@ -283,3 +283,44 @@ def sort_pairs_(keys_i64, vals_i32, key_bits: int):
     ws = Workspace.get(keys_i64.device, nbytes)
     check(lib.mwe_sort_pairs_u64_u32(_ptr(keys_i64), _ptr(vals_i32), N, int(key_bits), _ptr(ws), ws.numel(), _stream()),
           "mwe_sort_pairs_u64_u32")
+
+
+def group_by_label(labels, n_labels):
+    """Stable grouping of ``labels`` [N] int64: ``(members int32 [N], seg_start int32 [n_labels + 2])`` -- the indices
+    of every label's members are ``members[seg_start[l]:seg_start[l + 1]]``, in input order; indices of labels outside
+    ``[0, n_labels)`` sit in ``members[seg_start[n_labels]:]``."""
+    _req(labels, torch.int64, "labels")
+    N = labels.numel()
+    dev = labels.device
+    members = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+    seg_start = torch.empty(int(n_labels) + 2, dtype=torch.int32, device=dev)
+    nbytes = lib.mwe_centroid_workspace_bytes(N, int(n_labels))
+    ws = Workspace.get(dev, nbytes)
+    check(lib.mwe_group_by_label(_ptr(labels), N, int(n_labels), _ptr(members), _ptr(seg_start), _ptr(ws), ws.numel(),
+                                 _stream()), "mwe_group_by_label")
+    return members[:N], seg_start
+
+
+def label_stats(values, members, seg_start, n_labels):
+    """NaN-skipping per-label ``(count int64, sum, min, max)`` of ``values`` ([N] or one column of an [N, P] tensor)."""
+    if not values.is_cuda or values.dtype != torch.float64 or values.dim() != 1:
+        raise TypeError("values: expected a 1-D CUDA float64 tensor (a column view is fine)")
+    _req(members, torch.int32, "members"); _req(seg_start, torch.int32, "seg_start")
+    dev = values.device
+    n = int(n_labels)
+    count = torch.empty(n, dtype=torch.int64, device=dev)
+    out = torch.empty((3, n), dtype=torch.float64, device=dev)
+    ldv = values.stride(0) if values.numel() > 1 else 1
+    check(lib.mwe_label_stats_f64(_ptr(values), ldv, _ptr(members), _ptr(seg_start), n, _ptr(count), _ptr(out[0]),
+                                  _ptr(out[1]), _ptr(out[2]), _stream()), "mwe_label_stats_f64")
+    return count, out[0], out[1], out[2]
+
+
+def rows_with_nan(X):
+    """uint8 [N]: 1 where row of X [N, D] float64 holds a NaN."""
+    if not X.is_cuda or X.dtype != torch.float64 or X.dim() != 2 or X.stride(1) != 1:
+        raise TypeError("X: expected a CUDA float64 [N, D] tensor with unit column stride")
+    N, D = X.shape
+    out = torch.empty(N, dtype=torch.uint8, device=X.device)
+    check(lib.mwe_rows_with_nan_f64(_ptr(X), N, D, X.stride(0) if N > 1 else D, _ptr(out), _stream()), "mwe_rows_with_nan_f64")
+    return out
