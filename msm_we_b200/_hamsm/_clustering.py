@@ -575,6 +575,83 @@ class ClusteringMixin:
         log.debug("Discretization complete")
 
     # ------------------------------------------------------------------------------------------
+    def lloyd_refine_clusters(self, n_iter=10, iters_to_use=None, max_device_bytes=None):
+        """Full-batch Lloyd refinement of every WE bin's cluster model from its current centres -- the stratified
+        counterpart of the ``KMeans.fit`` the reference runs on its aggregated path (_clustering.py:289,491; sklearn
+        ``lloyd_iter_chunked_dense``), and what BASELINE config 5 calls "10 Lloyd iters".  The end-of-segment frames of
+        ``iters_to_use`` (default: every discretizable iteration) are featurised, shipped to the GPU once and kept
+        resident for all ``n_iter`` iterations; as in the streaming clustering they are binned by the PARENT progress
+        coordinate and frames whose parent sits in the basis / target are left out (:849-877).  Updates
+        ``cluster_models[b].cluster_centers_`` in place; returns the number of frames used."""
+        import torch
+
+        from .._pinning import PINS
+        from .. import ops as _ops
+        from ..clustering_ops import lloyd_fit
+
+        clusters = self.clusters
+        dev = clusters.device_state()
+        iters = list(range(1, self.maxIter) if iters_to_use is None else iters_to_use)
+        P = self.pcoord_ndim
+        src = self.iteration_source
+        counts = [int(src.n_segments(it)) if src.has(it) else 0 for it in iters]
+        n = int(sum(counts))
+        if n == 0:
+            return 0
+        projection = getattr(self.coordinates, "device_projection", None)
+        projection = projection(dev.device) if callable(projection) else None
+        Din = int(projection[0].shape[1]) if projection is not None else dev.D
+        budget = max_device_bytes or int(0.6 * torch.cuda.mem_get_info(dev.device)[0])
+        if n * (Din + P + 4) * 8 > budget:
+            raise MemoryError(f"{n} frames x {Din} features do not fit the device budget ({budget} bytes); pass fewer "
+                              f"iterations (iters_to_use=) -- config 5 is sized for iteration-range shards over 8 GPUs")
+        X = torch.empty((n, Din), dtype=torch.float64, device=dev.device)
+        hp_t = torch.empty((n, P), dtype=torch.float64, pin_memory=True)
+        hp = hp_t.numpy()
+        stage_rows = max(counts)
+        stage, stage_ev, n_staged = None, [None, None], 0
+        pos = 0
+        for it, s in zip(iters, counts):
+            if s == 0:
+                continue
+            rec = self._record(it)
+            feat = self.processCoordinates(self._as_structures(rec.child_coords))
+            if projection is None:
+                feat = self.coordinates.transform(feat)
+            feat = np.asarray(feat)
+            if feat.shape != (s, Din):
+                raise ValueError(f"featurised coordinates of iteration {it} have shape {feat.shape}, expected {(s, Din)}")
+            hp[pos:pos + s] = rec.pcoord0[:, :P]
+            owned = getattr(src, "owns_arrays", False) and PINS._owner(feat) is PINS._owner(rec.child_coords)
+            if owned and PINS.ensure(feat):
+                X[pos:pos + s].copy_(torch.from_numpy(feat), non_blocking=True)
+            else:
+                if stage is None:
+                    stage = [torch.empty((stage_rows, Din), dtype=torch.float64, pin_memory=True) for _ in range(2)]
+                k = n_staged & 1
+                n_staged += 1
+                if stage_ev[k] is not None:
+                    stage_ev[k].synchronize()
+                np.copyto(stage[k].numpy()[:s], feat)
+                X[pos:pos + s].copy_(stage[k][:s], non_blocking=True)
+                stage_ev[k] = torch.cuda.Event()
+                stage_ev[k].record(torch.cuda.current_stream())
+            pos += s
+        if projection is not None:
+            X = _ops.project(X, projection[0], projection[1])
+        pc = hp_t.to(dev.device, non_blocking=True)
+        bins, flags = dev.bins_and_flags(pc, pcoord_host=hp)
+        centers = dev.centers.clone()
+        lloyd_fit(X, None, bins, centers, dev.bin_offset, dev.max_k, int(n_iter), flags_dev=flags, errors=dev.errors)
+        centers_h = centers.cpu().numpy()
+        dev.check_errors()
+        offs = dev.bin_offset_host
+        for b, m in enumerate(clusters.cluster_models):
+            if hasattr(m, "cluster_centers_") and offs[b + 1] > offs[b]:
+                m.cluster_centers_ = np.ascontiguousarray(centers_h[offs[b]:offs[b + 1]])
+        return n
+
+    # ------------------------------------------------------------------------------------------
     @staticmethod
     def find_nearest_bin(bin_mapper, bin_idx, filled_bins):
         """reference: _clustering.py:1331-1396."""

@@ -67,21 +67,83 @@ def partial_fit_models(batch, device=None):
         model._finish(Xc, reassign)
 
 
-def lloyd_fit(X_dev, w_dev, bins_dev, centers_dev, bin_offset_dev, max_k, n_iter, group=None):
-    """``n_iter`` full Lloyd iterations of every bin's model on device-resident data (BASELINE cfg 5;
-    reference arithmetic: sklearn/cluster/_k_means_lloyd.pyx:23-165).  With a process group the partial
-    sums are all-reduced, which is the only exchange step of the clustering path.  Returns labels of
-    the last E step."""
+def lloyd_fit(X_dev, w_dev, bins_dev, centers_dev, bin_offset_dev, max_k, n_iter, group=None, flags_dev=None,
+              path=None, errors=None, relocate_empty=True):
+    """``n_iter`` full Lloyd iterations of every WE bin's model on device-resident data (BASELINE config 5): per
+    iteration ONE K1 launch sequence labels the points of all bins, ONE K2 launch sequence forms every cluster's
+    ``sum w x`` / ``sum w`` in sample order, and the mean replaces the centre (clusters without members keep theirs
+    unless relocated).  ``centers_dev`` is updated in place; returns the labels of the last E step.
+
+    reference arithmetic: ``KMeans.fit`` -> ``lloyd_iter_chunked_dense(update_centers=True)``
+    (sklearn/cluster/_k_means_lloyd.pyx:23-165; reached from msm_we/_hamsm/_clustering.py:289,491), including its
+    empty-cluster relocation (``_relocate_empty_clusters_dense``, sklearn/cluster/_k_means_common.pyx): a cluster that
+    received no weight takes the point farthest from its own centre, which is removed from its old cluster's sum.
+
+    With a process group every rank holds its own points (iteration-range shard); the partial sums are all-reduced --
+    the only exchange step of the clustering path -- and every rank applies the identical finalize."""
+    from . import _lib
+
+    if path is None:
+        path = _lib.ASSIGN_AUTO
     labels = None
     sumK = centers_dev.shape[0]
     for _ in range(n_iter):
-        labels = ops.assign_stratified(X_dev, bins_dev, None, centers_dev, ops.centers_sqnorm(centers_dev), bin_offset_dev,
-                                       max_k)
+        labels = ops.assign_stratified(X_dev, bins_dev, flags_dev, centers_dev, ops.centers_sqnorm(centers_dev),
+                                       bin_offset_dev, max_k, path=path, errors=errors)
         sum_wx, sum_w = ops.centroid_accumulate(X_dev, w_dev, labels, sumK)
         if group is not None:
             import torch.distributed as dist
 
             dist.all_reduce(sum_wx, group=group)
             dist.all_reduce(sum_w, group=group)
+        if relocate_empty:
+            _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bin_offset_dev, sum_wx, sum_w, group)
         ops.lloyd_finalize(sum_wx, sum_w, centers_dev)
     return labels
+
+
+def _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bin_offset_dev, sum_wx, sum_w, group):
+    """sklearn's ``_relocate_empty_clusters_dense`` per WE-bin model, applied to the (all-reduced) partial sums before
+    the mean.  Empty clusters are rare (they need duplicate or far-off initial centres), so the decision is taken on
+    the host: one [sumK] read per Lloyd iteration to find them, and only for an affected bin the distances of its
+    points to their own centres (numpy, the formula sklearn uses)."""
+    sw = sum_w.cpu().numpy()
+    if (sw != 0).all():
+        return
+    offs = bin_offset_dev.cpu().numpy()
+    world, rank = 1, 0
+    if group is not None:
+        import torch.distributed as dist
+
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+    changed = False
+    for b in range(len(offs) - 1):
+        lo, hi = int(offs[b]), int(offs[b + 1])
+        if hi == lo:
+            continue
+        empty = lo + np.flatnonzero(sw[lo:hi] == 0)
+        if empty.size == 0 or sw[lo:hi].sum() == 0:       # a model without any point is not being fitted at all
+            continue
+        sel = torch.nonzero((labels >= lo) & (labels < hi)).squeeze(1)
+        Xb = X_dev[sel].cpu().numpy()
+        lb = labels[sel].cpu().numpy()
+        wb = np.ones(len(lb)) if w_dev is None else w_dev[sel].cpu().numpy()
+        cb = centers_dev[lo:hi].cpu().numpy()
+        dist2 = ((Xb - cb[lb - lo]) ** 2).sum(axis=1)
+        n_empty = int(empty.size)
+        take = min(n_empty, len(dist2))
+        far = np.argpartition(dist2, -take)[:-take - 1:-1] if take else np.zeros(0, dtype=np.int64)
+        cand = [(float(dist2[i]), Xb[i].copy(), float(wb[i]), int(lb[i])) for i in far]
+        if world > 1:
+            import torch.distributed as dist
+
+            gathered = [None] * world
+            dist.all_gather_object(gathered, cand, group=group)
+            cand = sorted((c for part in gathered for c in part), key=lambda c: -c[0])[:n_empty]
+        for new_id, (_, x, wt, old_id) in zip(empty, cand):
+            sum_wx[old_id] -= torch.from_numpy(x * wt).to(sum_wx.device)
+            sum_wx[new_id] = torch.from_numpy(x * wt).to(sum_wx.device)
+            sum_w[new_id] = wt
+            sum_w[old_id] -= wt
+            changed = True
+    return changed

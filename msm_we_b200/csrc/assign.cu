@@ -571,7 +571,8 @@ static int launch_assign(AssignParams p, int64_t max_tiles, cudaStream_t stream)
     if (nstages > AS_MAX_STAGES) nstages = AS_MAX_STAGES;
     if (nstages < 2) nstages = 2;
     const size_t smem = stage_bytes * nstages + table_bytes;
-    static size_t configured = 0;
+    static size_t configured_dev[MWE_MAX_DEVICES] = {};   // the attribute is per device, not per process
+        size_t& configured = configured_dev[device_slot()];
     if (configured < smem) {
         MWE_CHECK_CUDA(cudaFuncSetAttribute(assign_dmma_kernel<NT, VEC, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;

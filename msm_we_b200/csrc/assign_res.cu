@@ -427,7 +427,8 @@ static bool resident_plan(int D, int32_t max_k, bool vec2, ResidentPlan* pl) {
 
 template <int NT, int NW>
 static int launch_resident(const AssignParams& p, const ResidentPlan& pl, int64_t max_tiles, cudaStream_t stream) {
-    static size_t configured = 0;
+    static size_t configured_dev[MWE_MAX_DEVICES] = {};   // the attribute is per device, not per process
+        size_t& configured = configured_dev[device_slot()];
     if (configured < pl.smem) {
         MWE_CHECK_CUDA(cudaFuncSetAttribute(assign_dmma_resident_kernel<NT, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         MWE_CHECK_CUDA(cudaFuncSetAttribute(assign_dmma_resident_kernel<NT, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));

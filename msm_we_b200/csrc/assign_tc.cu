@@ -653,7 +653,8 @@ int launch_assign_tc(const AssignParams& p_in, int32_t max_k, int64_t N, void* p
     cudaEvent_t ev0, ev1;
     timing_events(&ev0, &ev1);
     if (vec2) {
-        static size_t configured = 0;
+        static size_t configured_dev[MWE_MAX_DEVICES] = {};   // the attribute is per device, not per process
+        size_t& configured = configured_dev[device_slot()];
         if (configured < smem) {
             MWE_CHECK_CUDA(cudaFuncSetAttribute(assign_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured = smem;
@@ -661,7 +662,8 @@ int launch_assign_tc(const AssignParams& p_in, int32_t max_k, int64_t N, void* p
         if (ev0) MWE_CHECK_CUDA(cudaEventRecord(ev0, stream));
         assign_tc_kernel<2><<<(unsigned)grid, TC_THREADS, smem, stream>>>(q);
     } else {
-        static size_t configured = 0;
+        static size_t configured_dev[MWE_MAX_DEVICES] = {};   // the attribute is per device, not per process
+        size_t& configured = configured_dev[device_slot()];
         if (configured < smem) {
             MWE_CHECK_CUDA(cudaFuncSetAttribute(assign_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured = smem;

@@ -10,6 +10,9 @@ namespace mwe {
 
 void set_last_error(const char* fmt, ...);
 int sm_count();
+// index of the current device, clamped to [0, MWE_MAX_DEVICES): per-device caches (function attributes, SM count)
+static constexpr int MWE_MAX_DEVICES = 64;
+int device_slot();
 // optional CUDA events recorded around the dominant kernel of the next calls (bench roofline timing)
 void timing_events(cudaEvent_t* start, cudaEvent_t* stop);
 

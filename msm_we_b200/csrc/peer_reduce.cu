@@ -20,7 +20,8 @@ namespace mwe {
 
 static constexpr int PR_THREADS = 256;
 static constexpr int PR_MAX_WORLD = 16;
-static constexpr int PR_SPIN_LIMIT = 1 << 24;
+static constexpr unsigned long long PR_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;   // a peer is gone, not late
+static constexpr uint32_t PR_POISON = 0xFFFFFFFFu;   // written instead of an epoch by a rank that gave up
 
 struct PeerParams {
     const double* partial[PR_MAX_WORLD];
@@ -42,19 +43,44 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// wait until flags[base + p] of THIS rank has reached `epoch` for every peer p (threads 0..world-1 of the CTA)
-__device__ __forceinline__ void wait_all(const PeerParams& P, int base) {
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Wait until flags[base + p] of THIS rank has reached `epoch` for every peer p (threads 0..world-1 of the CTA).
+// Returns false -- for the whole CTA -- when a peer poisoned its flag or did not show up within PR_TIMEOUT_NS: the
+// caller must then neither reduce nor deliver (a stale partial would otherwise be summed into everybody's result).
+__device__ __forceinline__ bool wait_all(const PeerParams& P, int base) {
+    __shared__ int s_abort;
+    if (threadIdx.x == 0) s_abort = 0;
+    __syncthreads();
     if ((int)threadIdx.x < P.world) {
         const uint32_t* f = P.flags[P.rank] + base + threadIdx.x;
-        int spins = 0;
-        while ((int32_t)(ld_acquire_sys(f) - P.epoch) < 0) {
-            if (++spins > PR_SPIN_LIMIT) {     // a peer died: never hang the GPU, report instead
-                atomicAdd(&P.err_count[MWE_ERR_INTERNAL], 1);
-                break;
+        unsigned long long t0 = 0;
+        unsigned spins = 0;
+        for (;;) {
+            const uint32_t v = ld_acquire_sys(f);
+            if (v == PR_POISON) { atomicExch(&s_abort, 1); break; }
+            if ((int32_t)(v - P.epoch) >= 0) break;
+            if (++spins > 4096u) {
+                __nanosleep(200);
+                if (t0 == 0) t0 = global_ns();
+                else if (global_ns() - t0 > PR_TIMEOUT_NS) { atomicExch(&s_abort, 1); break; }
             }
         }
     }
     __syncthreads();
+    return s_abort == 0;
+}
+// Give up: count the error locally and poison this rank's "ready" and "delivered" words in EVERY rank, so that every
+// peer's wait fails too and every rank raises -- nobody returns a matrix built from a stale partial.
+__device__ __forceinline__ void poison_all(const PeerParams& P) {
+    if (threadIdx.x == 0) atomicAdd(&P.err_count[MWE_ERR_INTERNAL], 1);
+    if ((int)threadIdx.x < P.world) {
+        st_release_sys(P.flags[threadIdx.x] + P.rank, PR_POISON);
+        st_release_sys(P.flags[threadIdx.x] + P.world + P.rank, PR_POISON);
+    }
 }
 
 __global__ void __launch_bounds__(PR_THREADS) flux_peer_allreduce_kernel(const PeerParams P) {
@@ -65,7 +91,10 @@ __global__ void __launch_bounds__(PR_THREADS) flux_peer_allreduce_kernel(const P
         __threadfence_system();
         st_release_sys(P.flags[threadIdx.x] + P.rank, P.epoch);
     }
-    wait_all(P, 0);
+    if (!wait_all(P, 0)) {
+        poison_all(P);
+        return;
+    }
     // ---- my slice of the cells: sum in rank order, divide, deliver to every rank ----
     const int64_t lo = P.count * P.rank / P.world, hi = P.count * (P.rank + 1) / P.world;
     const bool divide = P.divisor != 0.0 && P.divisor != 1.0;
@@ -83,13 +112,14 @@ __global__ void __launch_bounds__(PR_THREADS) flux_peer_allreduce_kernel(const P
     __syncthreads();
     if (!s_last) return;
     if (threadIdx.x == 0) *P.cta_counter = 0;
+    __syncthreads();
     if ((int)threadIdx.x < P.world) {
         __threadfence_system();
         st_release_sys(P.flags[threadIdx.x] + P.world + P.rank, P.epoch);
     }
     // the grid (hence the stream) does not complete before every peer's slice is in my result buffer, and
     // before every peer has finished reading my partial (a peer signals only after its reads)
-    wait_all(P, P.world);
+    if (!wait_all(P, P.world)) poison_all(P);
 }
 
 }  // namespace mwe

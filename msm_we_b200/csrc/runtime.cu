@@ -24,6 +24,15 @@ void timing_events(cudaEvent_t* start, cudaEvent_t* stop) {
     *stop = g_ev_stop;
 }
 
+int device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return dev < 0 ? 0 : (dev >= MWE_MAX_DEVICES ? MWE_MAX_DEVICES - 1 : dev);
+}
+
 int sm_count() {
     static thread_local int cached_dev = -1;
     static thread_local int cached = 148;

@@ -55,6 +55,9 @@ def allreduce_flux(local_sum, n_iters_total, group=None):
         red = peer_reducer(local_sum.shape, local_sum.device, group)
         if red is not None:
             red.partial.copy_(local_sum)
+            # ranks gather their iterations on the host at different speeds: meet here, so the kernel's spin only has
+            # to cover launch skew (its timeout means "a peer is gone", and then EVERY rank raises)
+            dist.barrier(group)
             out = red.reduce(float(n_iters_total))
             red.errors.check()
             return out.clone()
@@ -128,30 +131,37 @@ class PeerFluxAllreduce:
     them; ``PeerFluxAllreduce.create`` returns None when that is not available and the caller keeps the NCCL path.
     Handles travel once, through ``torch.distributed`` object collectives."""
 
-    def __init__(self, shape, rank, world, device, group=None):
+    def __init__(self, shape, rank, world, device):
+        """Local half only (allocate + export); nothing here talks to other ranks, so a failure cannot leave the
+        ranks in mismatched collectives.  ``create`` exchanges the handles and calls ``_open_peers``."""
         import ctypes as C
 
         import torch
-        import torch.distributed as dist
 
-        from . import _lib
+        from . import _lib, ops
 
         self.rank, self.world, self.device, self.shape = rank, world, device, tuple(shape)
         self.count = int(np.prod(self.shape))
         self.epoch = 0
+        self._opened = []
+        self._bufs = []
         self._bufs = [_RawDeviceBuffer(self.count * 8, "<f8", self.shape), _RawDeviceBuffer(self.count * 8, "<f8", self.shape),
                       _RawDeviceBuffer(2 * world * 4 + 4, "<u4", (2 * world + 1,))]
         self.partial = torch.as_tensor(self._bufs[0], device=device)
         self.out = torch.as_tensor(self._bufs[1], device=device)
-        self._flags = self._bufs[2]
-        handles = []
+        self.handles = []
         for b in self._bufs:
             h = (C.c_ubyte * 64)()
             _lib.check(_lib.lib.mwe_ipc_export(b.ptr, h), "mwe_ipc_export")
-            handles.append(bytes(h))
-        gathered = [None] * world
-        dist.all_gather_object(gathered, handles, group=group)
-        self._opened = []
+            self.handles.append(bytes(h))
+        self.errors = ops.DeviceErrors(device)
+
+    def _open_peers(self, gathered):
+        import ctypes as C
+
+        from . import _lib
+
+        world, rank = self.world, self.rank
         ptrs = [[0] * world for _ in range(3)]
         for r in range(world):
             for k in range(3):
@@ -166,12 +176,11 @@ class PeerFluxAllreduce:
         arr = C.c_void_p * world
         self._partials, self._outs, self._flagps = arr(*ptrs[0]), arr(*ptrs[1]), arr(*ptrs[2])
         self._counter = self._bufs[2].ptr + 2 * world * 4      # the spare u32 behind the flags
-        from . import ops
-
-        self.errors = ops.DeviceErrors(device)
 
     @classmethod
     def create(cls, shape, device, group=None):
+        """None when the ranks cannot map each other's memory (the caller keeps the NCCL path).  Every rank takes part
+        in exactly two object collectives whatever fails locally: (handles or None), then (peers opened or not)."""
         import torch.distributed as dist
 
         if not (dist.is_available() and dist.is_initialized()):
@@ -179,11 +188,19 @@ class PeerFluxAllreduce:
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         if world < 2 or world > 16:
             return None
-        ok = True
+        obj = None
         try:
-            obj = cls(shape, rank, world, device, group)
-        except Exception:          # no peer access / IPC between these processes: NCCL path
-            obj, ok = None, False
+            obj = cls(shape, rank, world, device)
+        except Exception:          # allocation / export failed on this rank
+            obj = None
+        gathered = [None] * world
+        dist.all_gather_object(gathered, None if obj is None else obj.handles, group=group)
+        ok = obj is not None and all(g is not None for g in gathered)
+        if ok:
+            try:
+                obj._open_peers(gathered)
+            except Exception:      # no peer access / IPC between these processes
+                ok = False
         flags = [None] * world
         dist.all_gather_object(flags, ok, group=group)
         if not all(flags):

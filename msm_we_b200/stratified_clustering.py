@@ -16,6 +16,7 @@ order as sklearn does.
 from __future__ import annotations
 
 import numbers
+import zlib
 
 import numpy as np
 
@@ -238,7 +239,8 @@ class StratifiedClusters:
                 parts.append(None)
             else:
                 c = np.asarray(c)
-                parts.append((id(c), c.shape, c.__array_interface__["data"][0], float(c.ravel()[::61].sum())))
+                # the centres are small (K x D per bin): hash all of them, so an in-place edit is never missed
+                parts.append((c.shape, zlib.crc32(np.ascontiguousarray(c).view(np.uint8).reshape(-1))))
         model = self.model
         bounds = (np.asarray(model.basis_pcoord_bounds).tobytes(), np.asarray(model.target_pcoord_bounds).tobytes())
         return (tuple(parts), tuple(sorted(self.we_remap.items())), id(self.bin_mapper), bounds)

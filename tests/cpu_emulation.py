@@ -42,6 +42,7 @@ def emulate_kernels(monkeypatch):
     monkeypatch.setattr(cops, "require_cuda", lambda device=None: cpu)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _Stream())
     monkeypatch.setattr(torch.cuda, "Event", _Event)
+    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda *a, **k: (64 << 30, 64 << 30))
     real_empty = torch.empty
 
     def empty(*a, pin_memory=False, **k):
@@ -111,6 +112,23 @@ def emulate_kernels(monkeypatch):
 
     def minibatch_update(X, w, label, centers, counts):
         O.minibatch_update(_np(X), _np(w), centers.numpy(), counts.numpy(), _np(label))
+
+    def centroid_accumulate(X, w, label, sumK):
+        x, lab = _np(X), _np(label)
+        ww = np.ones(len(lab)) if w is None else _np(w)
+        sums = np.zeros((sumK, x.shape[1]))
+        wsum = np.zeros(sumK)
+        ok = (lab >= 0) & (lab < sumK)
+        for i in np.flatnonzero(ok):                 # sample order, product and sum rounded separately
+            wsum[lab[i]] += ww[i]
+            sums[lab[i]] = sums[lab[i]] + x[i] * ww[i]
+        return torch.from_numpy(sums), torch.from_numpy(wsum)
+
+    def lloyd_finalize(sum_wx, sum_w, centers):
+        sw = _np(sum_w)
+        nz = sw > 0
+        c = centers.numpy()
+        c[nz] = _np(sum_wx)[nz] * (1.0 / sw[nz])[:, None]
 
     def flux_accumulate(start, end, w, n_clusters, flag0=None, flag1=None, col0=None, col1=None, C=1, iter_offsets=None,
                         dense=None, want_coo=False, errors=None):
@@ -184,7 +202,8 @@ def emulate_kernels(monkeypatch):
         return torch.from_numpy(np.ascontiguousarray(r))
 
     for name, fn in dict(centers_sqnorm=centers_sqnorm, bin_flags=bin_flags, assign_stratified=assign_stratified,
-                         minibatch_update=minibatch_update, flux_accumulate=flux_accumulate, divide_=divide_,
+                         minibatch_update=minibatch_update, centroid_accumulate=centroid_accumulate,
+                         lloyd_finalize=lloyd_finalize, flux_accumulate=flux_accumulate, divide_=divide_,
                          group_by_label=group_by_label, label_stats=label_stats, rows_with_nan=rows_with_nan,
                          project=project).items():
         monkeypatch.setattr(ops, name, fn)

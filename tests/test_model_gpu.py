@@ -298,7 +298,7 @@ def test_peer_memory_flux_allreduce_two_gpus():
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "peer_reduce_test.py")],
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "peer_reduce_check.py")],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "peer path available: True" in out.stdout

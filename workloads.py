@@ -44,6 +44,7 @@ CONFIGS = {
     "cfg2": WEConfig("cfg2", 200, 1000, 64, 30, 20, 20261018),
     "cfg3": WEConfig("cfg3", 1000, 4000, 3000, 50, 50, 20261019),
     "cfg5": WEConfig("cfg5", 5000, 8000, 256, 100, 100, 20261021),
+    # configs[3] (flux-matrix stress) has no feature data: see generate_cfg4_device
     # reduced variants that keep the per-frame shape (D, bins, K) but fit quick runs
     "cfg3s": WEConfig("cfg3s", 50, 4000, 3000, 50, 50, 20261019),
     "cfg5s": WEConfig("cfg5s", 250, 8000, 256, 100, 100, 20261021),
@@ -165,3 +166,35 @@ def generate_device(cfg: WEConfig, device, means=None, seed_offset=0, iters=None
         prev_pc, prev_x = pc1, X[sl_c]
     offs = torch.arange(0, N + 1, S, dtype=torch.int64, device=device)
     return {"X": X, "pcoord": pc, "weights": w, "iter_offsets": offs, "n": N, "means": means}
+
+
+def generate_cfg4_device(device, n_transitions, n_clusters=20000, segs_per_iter=8000, seed_offset=0):
+    """BASELINE config 4 (flux-matrix stress): ``n_transitions`` weighted transitions between
+    ``n_clusters`` clusters x 2 history colours.  Start labels are Zipf-ish over the clusters (a few hot states, a long
+    tail), the end label is the start label plus a two-sided geometric offset (locality: nnz << M^2), colours are
+    Bernoulli(0.5) with the basis / target rule (a transition INTO the first / last cluster takes colour 0 / 1),
+    weights exp(N(0, 3)) normalised per iteration of ``segs_per_iter`` transitions.  Device-resident CUDA tensors."""
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(20261020 + seed_offset)
+    N = int(n_transitions)
+    u = torch.rand(N, generator=g, device=device, dtype=torch.float64)
+    start = (float(n_clusters) ** u - 1.0).to(torch.int64).clamp_(0, n_clusters - 1)          # log-uniform ~ Zipf(1)
+    perm = torch.randperm(n_clusters, generator=g, device=device)                               # hot states scattered
+    start = perm[start]
+    mag = torch.empty(N, device=device, dtype=torch.float64).geometric_(0.15, generator=g).to(torch.int64) - 1
+    sign = torch.randint(0, 2, (N,), generator=g, device=device) * 2 - 1
+    end = (start + sign * mag).clamp_(0, n_clusters - 1)
+    col0 = torch.randint(0, 2, (N,), generator=g, device=device, dtype=torch.uint8)
+    col1 = col0.clone()
+    col1[end == 0] = 0
+    col1[end == n_clusters - 1] = 1
+    w = torch.exp(3.0 * torch.randn(N, generator=g, device=device, dtype=torch.float64))
+    n_it = (N + segs_per_iter - 1) // segs_per_iter
+    offs = torch.clamp(torch.arange(0, n_it + 1, dtype=torch.int64, device=device) * segs_per_iter, max=N)
+    seg = torch.div(torch.arange(N, device=device), segs_per_iter, rounding_mode="floor")
+    tot = torch.zeros(n_it, dtype=torch.float64, device=device).index_add_(0, seg, w)
+    w = w / tot[seg]
+    return {"start": start.contiguous(), "end": end.contiguous(), "col0": col0, "col1": col1, "w": w, "iter_offsets": offs,
+            "n": N, "n_clusters": n_clusters}
