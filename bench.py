@@ -51,6 +51,14 @@ RESIDENT_ITERS = {"cfg5": 2000, "cfg3": 300, "cfg2": 200, "cfg5s": 250, "cfg3s":
 LLOYD_ITERS = {"cfg5": 10, "cfg5s": 10}
 
 
+_T0 = time.time()
+
+
+def log(msg):
+    """Progress on stderr (rank 0 only by convention of the callers): a stuck leg must be identifiable from the log."""
+    print(f"[bench {time.time() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -318,6 +326,8 @@ def step_work(cfg, n_frames, lloyd, P=1):
 # ----------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    if args.impl == "reference":
+        os.environ["OMP_NUM_THREADS"] = "1"        # the reference requires it (msm_we/msm_we.py:75-80); set before sklearn loads
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -335,10 +345,12 @@ def main():
         if rank != 0:
             return 0
         procs, sample = cpu_plan(cfg, cores, args.steps + args.warmup, budget_s=150.0)
+        log(f"reference arm: {procs} processes, {args.cpu_sample_iters or sample} iterations per step")
         sample = args.cpu_sample_iters or sample
         times, frames, used = [], 0, procs
         for step in range(args.warmup + args.steps):
             frames, dt, used = cpu_reference_pass(args.workload, sample, procs, lloyd)
+            log(f"reference arm step {step}: {dt:.1f} s")
             if step >= args.warmup:
                 times.append(dt)
         total = sum(times)
@@ -370,8 +382,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    if rank == 0:
+        log(f"b200 arm: {workload_text(cfg, iters_total, lloyd)}; world {world}")
     res = run_b200(cfg, args.workload, iters_total, lloyd, args.precision_path, args.steps, args.warmup, rank, world, dev,
                    local_rank)
+    if rank == 0:
+        log(f"resident measurement done: {res['ms_per_step']:.3f} ms/step, {res['value']:.4g} frames/s")
     line = None
     if rank == 0:
         line = res
@@ -379,17 +395,15 @@ def main():
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(cfg, lloyd, rank, world, dev, args.e2e_iters)
+        if rank == 0:
+            log(f"e2e done: {e2e['value']:.4g} frames/s (staged {e2e['staged_value']:.4g}, first call {e2e['first_call_value']:.4g})")
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        procs, sample = cpu_plan(cfg, cores, 1, budget_s=20.0)
-        sample = args.cpu_sample_iters or sample
-        frames, dt, used = cpu_reference_pass(args.workload, sample, procs, lloyd)
-        cpu = {"value": frames / dt, "unit": UNIT, "cores": used, "kind": "port",
-               "sample": f"{sample} iterations of the same shape ({frames} frames): sklearn KMeans Lloyd per WE bin + literal "
-                         f"reference loop, {dt:.1f} s wall"}
+        cpu = run_cpu_baseline(args, cfg, cores)
     extra = None
     if rank == 0 and world == 1 and not args.no_extra:
         extra = run_extra(dev, local_rank, args.workload)
+        log("extra lines done")
     if rank == 0:
         line["e2e"] = e2e
         line["cpu_baseline"] = cpu
@@ -399,6 +413,33 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def run_cpu_baseline(args, cfg, cores):
+    """The CPU leg runs in a FRESH interpreter (this file with --impl reference, one step): the worker processes are
+    forked, and forking a process that has initialised CUDA, page-locked gigabytes and started OpenMP / staging thread
+    pools is where fork-unsafe libraries deadlock (a forked sklearn KMeans waits forever on the parent's OpenMP pool)."""
+    procs, sample = cpu_plan(cfg, cores, 1, budget_s=20.0)
+    sample = args.cpu_sample_iters or sample
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload, "--steps", "1",
+           "--warmup", "0", "--cpu-sample-iters", str(sample)]
+    if args.iters:
+        cmd += ["--iters", str(args.iters)]
+    if args.lloyd_iters >= 0:
+        cmd += ["--lloyd-iters", str(args.lloyd_iters)]
+    env = dict(os.environ, OMP_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    log(f"cpu_baseline: {' '.join(cmd[2:])}")
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env)
+        line = json.loads(out.stdout.strip().splitlines()[-1])
+        cb = line["cpu_baseline"]
+        cb["sample"] += f", {line['ms_per_step'] / 1e3:.1f} s wall"
+        return cb
+    except Exception as e:
+        log(f"cpu_baseline failed: {e!r}")
+        return {"value": None, "unit": UNIT, "cores": procs, "kind": "port", "sample": f"failed: {e!r}"[:300]}
 
 
 def run_b200(cfg, name, iters_total, lloyd, precision_path, steps, warmup, rank, world, dev, local_rank, quiet_clocks=False):
@@ -420,6 +461,9 @@ def run_b200(cfg, name, iters_total, lloyd, precision_path, steps, warmup, rank,
     engine = DeviceClusters(mapper, centers, {b: b for b in range(cfg.n_bins)}, basis, target, 1, device=dev)
     centers0 = engine.centers.clone()
     data = workloads.generate_device(cfg, dev, means=means, seed_offset=rank, iters=my_iters)
+    torch.cuda.synchronize()
+    if rank == 0:
+        log(f"{name}: {my_iters} iterations generated on the device ({data['X'].numel() * 8 / 1e9:.1f} GB of features)")
     N = data["n"]
     n_clusters = cfg.n_clusters
     M = n_clusters + 2
@@ -468,6 +512,8 @@ def run_b200(cfg, name, iters_total, lloyd, precision_path, steps, warmup, rank,
         step()
     torch.cuda.synchronize()
     engine.check_errors()
+    if rank == 0:
+        log(f"{name}: warm-up done")
 
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     kevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]

@@ -549,6 +549,367 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// main kernel, second generation: the split A operand lives in TENSOR MEMORY
+// ---------------------------------------------------------------------------------------------------------
+// The kernel above is bound by shared-memory bandwidth, not by HBM or the tensor pipe: per 32-element k-chunk of a
+// 128-point tile (32 KB of HBM traffic) the shared-memory port moves 32 KB of cp.async writes, 32 KB of converter
+// reads, 32 KB of hi/lo operand stores, 48 KB of UMMA A-operand reads (hi twice, lo once), 43 KB of UMMA B reads and
+// 28 KB of centre-block TMA writes = 215 KB, i.e. 1 680 port cycles against the 1 460 cycles the chunk's HBM share
+// takes -- and the two 69 KB operand stages leave room for only two fp64 staging buffers (~32 KB of loads in flight
+// per SM, short of what the HBM latency needs).  Here the converter threads own one point ROW each (the TMEM lane of
+// that row), read its k-slice from the fp64 staging ring and write the TF32 hi / lo values straight into tensor
+// memory with tcgen05.st; the MMAs take A from TMEM ([d], [a], b-desc form).  That removes the operand stores and the
+// A reads from shared memory (135 KB per chunk instead of 215 KB) and frees 74 KB for the staging ring (4 stages).
+//
+// TMEM columns: [0, 2 n_pad) two accumulators; then n_a A stages of 64 columns (32 hi + 32 lo, K = 32 per chunk).
+// Warp roles as above; a converter warp may only touch the TMEM lane quarter (warp id % 4), so warp w converts rows
+// 32 (w % 4) .. +31 and the k-half ((w - 6) / 4) of the chunk: 16 elements per thread and chunk.
+
+static constexpr int TC2_A_STAGE_COLS = 64;
+static constexpr int TC2_MAX_A_STAGES = 4;
+static constexpr int TC2_MAX_B_STAGES = 4;
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+
+struct Tc2Params {
+    TcParams t;
+    int n_a;          // A stages in tensor memory
+    int n_b;          // centre-block stages in shared memory
+    uint32_t a_col0;  // first TMEM column of the A stages
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(TC_THREADS, 1) assign_tc2_kernel(const Tc2Params qq) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const TcParams& q = qq.t;
+    const AssignParams& p = q.a;
+    __shared__ uint64_t raw_full[TC_MAX_STAGES], raw_empty[TC_MAX_STAGES];   // fp64 staging ring (cp.async)
+    __shared__ uint64_t a_full[TC2_MAX_A_STAGES], a_empty[TC2_MAX_A_STAGES]; // A stages in TMEM
+    __shared__ uint64_t b_full[TC2_MAX_B_STAGES], b_empty[TC2_MAX_B_STAGES]; // centre blocks in shared memory
+    __shared__ uint64_t tmem_full[2], tmem_empty[2], xn_full[2], xn_empty[2];
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ float s_xn[2][2][TC_TP];                  // [buffer][k-half][row]: partial centred ||x'||^2
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_raw = q.nstages_raw, n_a = qq.n_a, n_b = qq.n_b;
+    const int ng = q.n_pad / 8;
+    const uint32_t b_bytes = (uint32_t)(2 * ng * TC_SBO);
+    unsigned char* b_base = smem_raw;
+    unsigned char* raw_base = smem_raw + (size_t)n_b * b_bytes;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < n_raw; ++s) {
+            mbar_init(&raw_full[s], TC_CONV_WARPS * 32);      // every staging thread: cp.async ... arrive.noinc
+            mbar_init(&raw_empty[s], TC_CONV_WARPS);          // one lane per converter warp
+        }
+        for (int s = 0; s < n_a; ++s) {
+            mbar_init(&a_full[s], TC_CONV_WARPS);             // one lane per converter warp, after its tcgen05.st
+            mbar_init(&a_empty[s], 1);                        // tcgen05.commit
+        }
+        for (int s = 0; s < n_b; ++s) {
+            mbar_init(&b_full[s], 1);                         // the centre warp's expect_tx arrive
+            mbar_init(&b_empty[s], 1);                        // tcgen05.commit
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);    // tcgen05.commit
+            mbar_init(&tmem_empty[i], 4);   // one lane per epilogue warp
+            mbar_init(&xn_full[i], TC_CONV_WARPS);
+            mbar_init(&xn_empty[i], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    TileTables tt{p.tile_prefix, p.bin_start, p.bin_offset, p.nbins};
+    if (p.nbins <= AS_TABLE_BINS) {
+        int32_t* s_tp = reinterpret_cast<int32_t*>(raw_base + (size_t)n_raw * TC_RAW_BYTES);
+        int32_t* s_bs = s_tp + (p.nbins + 1);
+        int64_t* s_bo = reinterpret_cast<int64_t*>(s_bs + (p.nbins + 1));
+        for (int b = threadIdx.x; b <= p.nbins; b += TC_THREADS) {
+            s_tp[b] = p.tile_prefix[b];
+            s_bs[b] = p.bin_start[b];
+            s_bo[b] = p.bin_offset[b];
+        }
+        tt = TileTables{s_tp, s_bs, s_bo, p.nbins};
+    }
+    if (warp == TC_MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(q.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    const int32_t n_tiles = tt.tile_prefix[p.nbins];
+    const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int ncb = p.ncb, nch = p.nch;
+    const bool prof = q.dbg_prof != nullptr;
+    long long w0 = 0, w1 = 0, w2 = 0;
+    const long long t_begin = clock64();
+
+    if (warp == TC_MMA_WARP) {
+        // =========================== MMA issuer (one lane) ===========================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(q.n_pad >> 3) << 17) | ((uint32_t)(TC_TP >> 4) << 24);
+            int as = 0, bs = 0;
+            uint32_t aph = 0, bph = 0;
+            uint32_t tph0 = 0, tph1 = 0;
+            int unit = 0;
+            for (int ti = 0; ti < my_tiles; ++ti)
+                for (int cb = 0; cb < ncb; ++cb, ++unit) {
+                    const int ab = unit & 1;
+                    timed_wait(&tmem_empty[ab], (ab ? tph1 : tph0) ^ 1u, w0, prof);   // epilogue has drained this accumulator
+                    if (ab) tph1 ^= 1u; else tph0 ^= 1u;
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(ab * q.n_pad);
+                    for (int kc = 0; kc < nch; ++kc) {
+                        timed_wait(&b_full[bs], bph, w2, prof);
+                        timed_wait(&a_full[as], aph, w1, prof);
+                        tc_fence_after();
+                        const uint32_t a_hi = tmem_base + qq.a_col0 + (uint32_t)(as * TC2_A_STAGE_COLS), a_lo = a_hi + TC_KC;
+                        const uint32_t b_hi = smem_u32(b_base + (size_t)bs * b_bytes), b_lo = b_hi + (uint32_t)(ng * TC_SBO);
+#pragma unroll
+                        for (int j = 0; j < TC_KC / 8; ++j) {
+                            const uint32_t ko = (uint32_t)(j * 2 * TC_LBO);
+                            const uint64_t dbh = make_smem_desc(b_hi + ko), dbl = make_smem_desc(b_lo + ko);
+                            umma_tf32_ts(d_tmem, a_hi + 8u * j, dbh, idesc, (kc | j) != 0);   // hi.hi (first MMA overwrites)
+                            umma_tf32_ts(d_tmem, a_hi + 8u * j, dbl, idesc, 1);              // hi.lo
+                            umma_tf32_ts(d_tmem, a_lo + 8u * j, dbh, idesc, 1);              // lo.hi
+                        }
+                        umma_commit(&a_empty[as]);       // stages reusable once these MMAs have read them
+                        umma_commit(&b_empty[bs]);
+                        if (kc == nch - 1) umma_commit(&tmem_full[ab]);
+                        if (++as == n_a) { as = 0; aph ^= 1u; }
+                        if (++bs == n_b) { bs = 0; bph ^= 1u; }
+                    }
+                }
+        }
+    } else if (warp == TC_CENTRE_WARP) {
+        // =========================== centre-block producer (one lane) ===========================
+        if (lane == 0) {
+            TileWalk<TC_TP> w{0, 0, 0, 0, 0, 0, 0, 0};
+            w.load(tt, my_tiles);
+            int bs = 0;
+            uint32_t bph = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                for (int cb = 0; cb < ncb; ++cb)
+                    for (int kc = 0; kc < nch; ++kc) {
+                        timed_wait(&b_empty[bs], bph ^ 1u, w0, prof);
+                        unsigned char* dst = b_base + (size_t)bs * b_bytes;
+                        const unsigned char* src = q.bprep + ((size_t)(w.bin * ncb + cb) * nch + kc) * b_bytes;
+                        mbar_expect_tx(&b_full[bs], b_bytes);
+                        bulk_copy_g2s(dst, src, b_bytes, &b_full[bs]);
+                        if (++bs == n_b) { bs = 0; bph ^= 1u; }
+                    }
+                w.next_tile(tt, my_tiles);
+            }
+        }
+    } else if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + 4) {
+        // =========================== epilogue: one point per thread ===========================
+        const int row = (warp - TC_EPI_WARP0) * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)((warp - TC_EPI_WARP0) * 32) << 16;
+        const float finf = __int_as_float(0x7f800000);
+        TileWalk<TC_TP> w{0, 0, 0, 0, 0, 0, 0, 0};
+        w.load(tt, my_tiles);
+        uint32_t tph0 = 0, tph1 = 0, xph0 = 0, xph1 = 0;
+        int unit = 0;
+        const int ncols = ncb * q.n_pad;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int32_t pt = (row < w.pcount) ? p.perm[w.pstart + row] : -1;   // label destination, fetched early
+            const float* csqf = q.csqf + (size_t)w.bin * ncols;
+            float m1 = finf, m2 = finf;
+            int32_t bi = 0;
+            for (int cb = 0; cb < ncb; ++cb, ++unit) {
+                const int ab = unit & 1;
+                timed_wait(&tmem_full[ab], ab ? tph1 : tph0, w0, prof);
+                if (ab) tph1 ^= 1u; else tph0 ^= 1u;
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(ab * q.n_pad);
+                for (int c0 = 0; c0 < q.n_pad; c0 += 16) {
+                    if (cb * q.n_pad + c0 >= w.kb) break;   // only padding beyond here (warp-uniform)
+                    float v[16];
+                    tmem_ld16(taddr + (uint32_t)c0, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int c = cb * q.n_pad + c0 + j;
+                        const float sf = fmaf(-2.0f, v[j], __ldg(csqf + c));   // +inf on padding columns
+                        if (q.dbg_scores && pt >= 0) q.dbg_scores[(size_t)pt * ncols + c] = sf;
+                        const bool lt = sf < m1;
+                        m2 = lt ? m1 : fminf(m2, sf);
+                        bi = lt ? c : bi;
+                        m1 = lt ? sf : m1;
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[ab]);
+            }
+            const int xb = ti & 1;
+            timed_wait(&xn_full[xb], xb ? xph1 : xph0, w1, prof);
+            if (xb) xph1 ^= 1u; else xph0 ^= 1u;
+            const float xn2c = s_xn[xb][0][row] + s_xn[xb][1][row];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&xn_empty[xb]);
+            if (pt >= 0) {
+                p.label_out[pt] = w.coff + bi;
+                if (p.local_out) p.local_out[pt] = bi;
+                const float cmc = sqrtf(q.cmaxf[3 * w.bin]) * 1.000001f;       // centred max ||c'||
+                const float cmr = sqrtf(q.cmaxf[3 * w.bin + 1]) * 1.000001f;   // raw max ||c||
+                const float xnc = sqrtf(xn2c) * 1.000001f;
+                const float xnr = xnc + q.cmaxf[3 * w.bin + 2];                  // ||x|| <= ||x'|| + ||mean||
+                const float err = q.err_coef * cmc * (2.0f * xnc + cmc);           // tensor-core evaluation error
+                const float tol = (float)p.tie_scale * cmr * (2.0f * xnr + cmr);   // fp64 tie band
+                if (!(m2 - m1 > 2.0f * err + 2.0f * tol)) p.recheck_list[atomicAdd(p.recheck_count, 1)] = pt;
+            }
+            w.next_tile(tt, my_tiles);
+        }
+    } else if (warp >= TC_CONV_WARP0) {
+        // =========================== staging + conversion warps ===========================
+        // (a) every warp issues the cp.async copies of 16 point rows of the chunk n_raw-1 steps ahead (fire and forget,
+        //     completion lands on raw_full); (b) converts ITS rows of the current chunk: thread = one point row (the
+        //     TMEM lane it may write), 16 consecutive elements of the 32-element chunk.
+        const int cwp = warp - TC_CONV_WARP0;              // 0..7
+        const int quarter = warp & 3;                      // TMEM lane quarter this warp can access
+        const int khalf = cwp >> 2;                        // which 16 elements of the chunk
+        const int row = quarter * 32 + lane;
+        constexpr int CR = TC_TP / TC_CONV_WARPS;          // rows each warp copies (16)
+        constexpr int SEGS = TC_KC / VEC;
+        constexpr int RPI = 32 / SEGS;
+        constexpr int XQ = CR / RPI;
+        const int seg = lane % SEGS, crs = lane / SEGS;
+        const int kcol0 = seg * VEC;
+        TileWalk<TC_TP> cw{0, 0, 0, 0, 0, 0, 0, 0};       // step being converted
+        cw.load(tt, my_tiles);
+        TileWalk<TC_TP> iw = cw;                           // step whose copies are being issued
+        TileWalk<TC_TP> nw = cw;                           // tile whose point indices are being prefetched
+        const double* xsrc[XQ];
+        int32_t pidx_next[XQ];
+        auto fetch = [&](const TileWalk<TC_TP>& t) {
+#pragma unroll
+            for (int k = 0; k < XQ; ++k) {
+                const int r = cwp * CR + k * RPI + crs;
+                pidx_next[k] = (r < t.pcount) ? p.perm[t.pstart + r] : -1;
+            }
+        };
+        auto set_xsrc = [&]() {
+#pragma unroll
+            for (int k = 0; k < XQ; ++k)
+                xsrc[k] = (pidx_next[k] >= 0) ? p.X + (int64_t)pidx_next[k] * p.ldx + kcol0 : nullptr;
+        };
+        fetch(iw);
+        set_xsrc();
+        nw.next_tile(tt, my_tiles);
+        fetch(nw);
+        const int64_t total_steps = (int64_t)my_tiles * ncb * nch;
+        int is = 0;
+        uint32_t iphase = 0;
+        int64_t issued = 0;
+        auto issue_one = [&]() {
+            timed_wait(&raw_empty[is], iphase ^ 1u, w2, prof);
+            double* st = reinterpret_cast<double*>(raw_base + (size_t)is * TC_RAW_BYTES);
+            const int k0 = iw.kc * TC_KC;
+            int vbytes = (p.D - k0 - kcol0) * 8;
+            vbytes = vbytes < 0 ? 0 : (vbytes > VEC * 8 ? VEC * 8 : vbytes);
+            double* dst = st + (cwp * CR + crs) * TC_RAW_LD + kcol0;
+#pragma unroll
+            for (int k = 0; k < XQ; ++k)   // (a zero-size copy still gets an in-range source address)
+                if (xsrc[k]) cp_async_zfill<VEC>(dst + k * RPI * TC_RAW_LD, vbytes ? xsrc[k] + k0 : p.X, vbytes);
+            if (cwp == 0 && lane < 16)   // the bin-mean chunk rides along (zero padded past D: always 16 x 16 B)
+                cp_async_zfill<2>(st + TC_TP * TC_RAW_LD + 2 * lane, q.mean + (size_t)iw.bin * q.d_pad + k0 + 2 * lane, 16);
+            cp_async_arrive_noinc(&raw_full[is]);
+            if (++is == n_raw) { is = 0; iphase ^= 1u; }
+            ++issued;
+            if (iw.advance(tt, ncb, nch, my_tiles)) {
+                set_xsrc();
+                nw.next_tile(tt, my_tiles);
+                fetch(nw);
+            }
+        };
+        while (issued < total_steps && issued < n_raw - 1) issue_one();
+
+        int rs = 0, as = 0;
+        uint32_t rphase = 0, aphase = 0, xph0 = 0, xph1 = 0;
+        const uint32_t a_lane = (uint32_t)(quarter * 32) << 16;
+        float xc = 0.f;
+        for (int64_t step = 0; step < total_steps; ++step) {
+            if (issued < total_steps) issue_one();
+            timed_wait(&raw_full[rs], rphase, w0, prof);
+            const double* st = reinterpret_cast<const double*>(raw_base + (size_t)rs * TC_RAW_BYTES);
+            const double* src = st + row * TC_RAW_LD + 16 * khalf;
+            const double* mup = st + TC_TP * TC_RAW_LD + 16 * khalf;
+            float hi[16], lo[16];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const double2 xv = *reinterpret_cast<const double2*>(src + 2 * e);
+                const double2 mv = *reinterpret_cast<const double2*>(mup + 2 * e);
+                const float x0 = (float)(xv.x - mv.x), x1 = (float)(xv.y - mv.y);
+                hi[2 * e] = tf32_rna(x0);
+                hi[2 * e + 1] = tf32_rna(x1);
+                lo[2 * e] = x0 - hi[2 * e];
+                lo[2 * e + 1] = x1 - hi[2 * e + 1];
+                if (cw.cb == 0) xc = fmaf(x0, x0, fmaf(x1, x1, xc));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&raw_empty[rs]);        // the staged fp64 chunk is in registers
+            timed_wait(&a_empty[as], aphase ^ 1u, w1, prof);   // the MMAs that read this TMEM stage have completed
+            tc_fence_after();
+            const uint32_t ta = tmem_base + a_lane + qq.a_col0 + (uint32_t)(as * TC2_A_STAGE_COLS + 16 * khalf);
+            tmem_st16(ta, hi);
+            tmem_st16(ta + TC_KC, lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[as]);
+            if (++rs == n_raw) { rs = 0; rphase ^= 1u; }
+            if (++as == n_a) { as = 0; aphase ^= 1u; }
+            if (cw.kc == nch - 1 && cw.cb == ncb - 1) {
+                // partial centred ||x'||^2 of this thread's row -> epilogue (fp32 sums of fp32 roundings, inflated a little)
+                const int xbuf = cw.ti & 1;
+                mbar_wait(&xn_empty[xbuf], (xbuf ? xph1 : xph0) ^ 1u);
+                if (xbuf) xph1 ^= 1u; else xph0 ^= 1u;
+                s_xn[xbuf][khalf][row] = xc * 1.0001f;
+                xc = 0.f;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&xn_full[xbuf]);
+            }
+            cw.advance(tt, ncb, nch, my_tiles);
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+
+    if (prof && lane == 0 && (warp == TC_MMA_WARP || warp == TC_CENTRE_WARP || warp == TC_EPI_WARP0 || warp == TC_CONV_WARP0)) {
+        const int role = warp == TC_MMA_WARP ? 0 : warp == TC_CENTRE_WARP ? 1 : warp == TC_EPI_WARP0 ? 2 : 4;
+        atomicAdd(q.dbg_prof + role * 4 + 0, (unsigned long long)(clock64() - t_begin));
+        atomicAdd(q.dbg_prof + role * 4 + 1, (unsigned long long)w0);
+        atomicAdd(q.dbg_prof + role * 4 + 2, (unsigned long long)w1);
+        atomicAdd(q.dbg_prof + role * 4 + 3, (unsigned long long)w2);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(q.tmem_cols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
 
@@ -630,8 +991,70 @@ int launch_assign_tc(const AssignParams& p_in, int32_t max_k, int64_t N, void* p
     q.err_coef = (float)(1.0 / 1048576.0 + (3.0 * ((p_in.D + 7) / 8) + 10.0) / 4194304.0);
     q.dbg_scores = g_dbg_scores;
     q.dbg_prof = g_dbg_prof;
-    const size_t tf_bytes = 2 * (size_t)TC_A_BYTES + (size_t)2 * (L.n_pad / 8) * TC_SBO;
     const size_t table_bytes = (p_in.nbins <= AS_TABLE_BINS) ? (size_t)(p_in.nbins + 2) * 16 + 16 : 0;
+    const bool vec2 = (p_in.D % 2 == 0) && (p_in.ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(p_in.X) & 15) == 0);
+    const int64_t max_tiles = (N + TC_TP - 1) / TC_TP + p_in.nbins;
+    int64_t grid = sm_count();
+    if (grid > max_tiles) grid = max_tiles;
+    if (grid < 1) grid = 1;
+    cudaEvent_t ev0, ev1;
+    timing_events(&ev0, &ev1);
+
+    // generation 2 (A operand in tensor memory) whenever two accumulators and >= 2 A stages fit the 512 TMEM columns
+    int gen = (2 * L.n_pad + 2 * TC2_A_STAGE_COLS <= 512) ? 2 : 1;
+    if (const char* e = getenv("MWE_TC_KERNEL")) gen = (atoi(e) == 1 || gen == 1) ? 1 : 2;
+    if (gen == 2) {
+        Tc2Params q2;
+        const size_t b_bytes = (size_t)2 * (L.n_pad / 8) * TC_SBO;
+        int n_a = (512 - 2 * L.n_pad) / TC2_A_STAGE_COLS;
+        if (n_a > TC2_MAX_A_STAGES) n_a = TC2_MAX_A_STAGES;
+        int n_b = 2;
+        if (const char* e = getenv("MWE_TC_B_STAGES")) n_b = atoi(e);
+        if (n_b < 1) n_b = 1;
+        if (n_b > TC2_MAX_B_STAGES) n_b = TC2_MAX_B_STAGES;
+        while (n_b > 1 && (size_t)n_b * b_bytes + 2 * (size_t)TC_RAW_BYTES + table_bytes > TC_SMEM_BUDGET) --n_b;
+        if ((size_t)n_b * b_bytes + 2 * (size_t)TC_RAW_BYTES + table_bytes > TC_SMEM_BUDGET) {
+            set_last_error("assign(tc): pipeline stages do not fit in shared memory");
+            return MWE_E_UNSUPPORTED;
+        }
+        int n_raw = (int)((TC_SMEM_BUDGET - table_bytes - (size_t)n_b * b_bytes) / TC_RAW_BYTES);
+        if (n_raw > TC_MAX_STAGES) n_raw = TC_MAX_STAGES;
+        if (const char* e = getenv("MWE_TC_RAW_STAGES")) n_raw = atoi(e) < n_raw ? (atoi(e) < 2 ? 2 : atoi(e)) : n_raw;
+        q.nstages = n_b;
+        q.nstages_raw = n_raw;
+        uint32_t cols2 = 32;
+        while (cols2 < (uint32_t)(2 * L.n_pad + n_a * TC2_A_STAGE_COLS)) cols2 <<= 1;
+        q.tmem_cols = cols2;
+        q2.t = q;
+        q2.n_a = n_a;
+        q2.n_b = n_b;
+        q2.a_col0 = (uint32_t)(2 * L.n_pad);
+        const size_t smem = b_bytes * n_b + (size_t)TC_RAW_BYTES * n_raw + table_bytes;
+        if (vec2) {
+            static size_t configured_dev[MWE_MAX_DEVICES] = {};   // the attribute is per device, not per process
+            size_t& configured = configured_dev[device_slot()];
+            if (configured < smem) {
+                MWE_CHECK_CUDA(cudaFuncSetAttribute(assign_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured = smem;
+            }
+            if (ev0) MWE_CHECK_CUDA(cudaEventRecord(ev0, stream));
+            assign_tc2_kernel<2><<<(unsigned)grid, TC_THREADS, smem, stream>>>(q2);
+        } else {
+            static size_t configured_dev[MWE_MAX_DEVICES] = {};
+            size_t& configured = configured_dev[device_slot()];
+            if (configured < smem) {
+                MWE_CHECK_CUDA(cudaFuncSetAttribute(assign_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured = smem;
+            }
+            if (ev0) MWE_CHECK_CUDA(cudaEventRecord(ev0, stream));
+            assign_tc2_kernel<1><<<(unsigned)grid, TC_THREADS, smem, stream>>>(q2);
+        }
+        MWE_CHECK_LAUNCH();
+        if (ev1) MWE_CHECK_CUDA(cudaEventRecord(ev1, stream));
+        return MWE_OK;
+    }
+
+    const size_t tf_bytes = 2 * (size_t)TC_A_BYTES + (size_t)2 * (L.n_pad / 8) * TC_SBO;
     // two TF32 stages when they fit next to two fp64 stages, the rest of the budget goes to the fp64 ring
     // (that ring is what keeps HBM requests in flight)
     int n_tf = (2 * tf_bytes + 2 * (size_t)TC_RAW_BYTES + table_bytes <= TC_SMEM_BUDGET) ? 2 : 1;
@@ -645,13 +1068,6 @@ int launch_assign_tc(const AssignParams& p_in, int32_t max_k, int64_t N, void* p
     q.nstages = n_tf;
     q.nstages_raw = n_raw;
     const size_t smem = tf_bytes * n_tf + (size_t)TC_RAW_BYTES * n_raw + table_bytes;
-    const bool vec2 = (p_in.D % 2 == 0) && (p_in.ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(p_in.X) & 15) == 0);
-    const int64_t max_tiles = (N + TC_TP - 1) / TC_TP + p_in.nbins;
-    int64_t grid = sm_count();
-    if (grid > max_tiles) grid = max_tiles;
-    if (grid < 1) grid = 1;
-    cudaEvent_t ev0, ev1;
-    timing_events(&ev0, &ev1);
     if (vec2) {
         static size_t configured_dev[MWE_MAX_DEVICES] = {};   // the attribute is per device, not per process
         size_t& configured = configured_dev[device_slot()];
