@@ -152,6 +152,13 @@ MWE_API int mwe_lloyd_finalize_f64(const double* sum_wx, const double* sum_w, in
 MWE_API int mwe_minibatch_finalize_f64(const double* sum_wx, const double* sum_w, int64_t sumK, int D, double* centers,
                                double* counts, void* stream);
 
+/* ||x_i - centre[label_i]||^2 (fp64) of the n listed points (list [n] int32 indices into X / label).  Used by the
+ * empty-cluster relocation of the Lloyd M step (sklearn/cluster/_k_means_common.pyx _relocate_empty_clusters_dense,
+ * reached through KMeans.fit from msm_we/_hamsm/_clustering.py:289,491): only the points of the WE bins that own an
+ * empty cluster are listed, and only the handful of farthest ones ever leave the device. */
+MWE_API int mwe_point_center_dist2_f64(const double* X, int64_t ldx, int D, const int32_t* list, int64_t n,
+                                       const int64_t* label, const double* centers, double* out, void* stream);
+
 /* ---- group-by-label + per-label statistics ----------------------------
  * Replaces the O(n_clusters x iterations) np.where loops of ClusteringMixin.get_cluster_centers
  * (msm_we/_hamsm/_clustering.py:1528-1599: nanmean / nanmin / nanmax of the end pcoord of every cluster's

@@ -52,6 +52,7 @@ SIGNATURES = {
     "mwe_minibatch_update_f64": (_int, [_p, _i64, _int, _i64, _p, _p, _i64, _p, _p, _p, _sz, _p]),
     "mwe_lloyd_finalize_f64": (_int, [_p, _p, _i64, _int, _p, _p]),
     "mwe_minibatch_finalize_f64": (_int, [_p, _p, _i64, _int, _p, _p, _p]),
+    "mwe_point_center_dist2_f64": (_int, [_p, _i64, _int, _p, _i64, _p, _p, _p, _p]),
     "mwe_group_by_label": (_int, [_p, _i64, _i64, _p, _p, _p, _sz, _p]),
     "mwe_label_stats_f64": (_int, [_p, _i64, _p, _p, _i64, _p, _p, _p, _p, _p]),
     "mwe_flux_workspace_bytes": (_sz, [_i64]),

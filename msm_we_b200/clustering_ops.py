@@ -97,43 +97,59 @@ def lloyd_fit(X_dev, w_dev, bins_dev, centers_dev, bin_offset_dev, max_k, n_iter
             dist.all_reduce(sum_wx, group=group)
             dist.all_reduce(sum_w, group=group)
         if relocate_empty:
-            _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bin_offset_dev, sum_wx, sum_w, group)
+            _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bins_dev, flags_dev, bin_offset_dev, sum_wx, sum_w, group)
         ops.lloyd_finalize(sum_wx, sum_w, centers_dev)
     return labels
 
 
-def _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bin_offset_dev, sum_wx, sum_w, group):
+def _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bins_dev, flags_dev, bin_offset_dev, sum_wx, sum_w, group):
     """sklearn's ``_relocate_empty_clusters_dense`` per WE-bin model, applied to the (all-reduced) partial sums before
-    the mean.  Empty clusters are rare (they need duplicate or far-off initial centres), so the decision is taken on
-    the host: one [sumK] read per Lloyd iteration to find them, and only for an affected bin the distances of its
-    points to their own centres (numpy, the formula sklearn uses)."""
+    the mean: a cluster that received no weight takes the point farthest from its own centre, which leaves its old
+    cluster.  The decision needs one [sumK] read per Lloyd iteration; when a bin does own an empty cluster, the distances
+    of THAT bin's points to their centres are formed on the device (``point_center_dist2``), only distances + indices
+    come to the host, where the farthest points are picked with the numpy call sklearn uses, and only those few rows
+    are fetched."""
     sw = sum_w.cpu().numpy()
     if (sw != 0).all():
-        return
+        return False
     offs = bin_offset_dev.cpu().numpy()
-    world, rank = 1, 0
+    nbins = len(offs) - 1
+    affected = []
+    for b in range(nbins):
+        lo, hi = int(offs[b]), int(offs[b + 1])
+        if hi > lo and (sw[lo:hi] == 0).any() and sw[lo:hi].sum() != 0:   # a model without any point is not being fitted
+            affected.append(b)
+    world = 1
     if group is not None:
         import torch.distributed as dist
 
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        world = dist.get_world_size(group)
+    if not affected:
+        return False
+    dev = X_dev.device
+    mask = torch.zeros(nbins, dtype=torch.bool, device=dev)
+    mask[torch.tensor(affected, device=dev)] = True
+    sel = mask[bins_dev.long()]
+    if flags_dev is not None:
+        sel &= flags_dev == 0
+    idx = torch.nonzero(sel).squeeze(1).to(torch.int32)
+    d2 = ops.point_center_dist2(X_dev, idx, labels, centers_dev).cpu().numpy()
+    idx_h = idx.cpu().numpy()
+    bin_h = bins_dev[idx.long()].cpu().numpy()
     changed = False
-    for b in range(len(offs) - 1):
+    for b in affected:
         lo, hi = int(offs[b]), int(offs[b + 1])
-        if hi == lo:
-            continue
         empty = lo + np.flatnonzero(sw[lo:hi] == 0)
-        if empty.size == 0 or sw[lo:hi].sum() == 0:       # a model without any point is not being fitted at all
-            continue
-        sel = torch.nonzero((labels >= lo) & (labels < hi)).squeeze(1)
-        Xb = X_dev[sel].cpu().numpy()
-        lb = labels[sel].cpu().numpy()
-        wb = np.ones(len(lb)) if w_dev is None else w_dev[sel].cpu().numpy()
-        cb = centers_dev[lo:hi].cpu().numpy()
-        dist2 = ((Xb - cb[lb - lo]) ** 2).sum(axis=1)
+        rows = np.flatnonzero(bin_h == b)                 # ascending point index = the row order sklearn sees
+        dist2 = d2[rows]
         n_empty = int(empty.size)
         take = min(n_empty, len(dist2))
         far = np.argpartition(dist2, -take)[:-take - 1:-1] if take else np.zeros(0, dtype=np.int64)
-        cand = [(float(dist2[i]), Xb[i].copy(), float(wb[i]), int(lb[i])) for i in far]
+        pts = torch.from_numpy(idx_h[rows[far]].astype(np.int64)).to(dev)
+        xs = X_dev[pts].cpu().numpy() if take else np.zeros((0, X_dev.shape[1]))
+        ws = np.ones(take) if w_dev is None else w_dev[pts].cpu().numpy()
+        ls = labels[pts].cpu().numpy() if take else np.zeros(0, dtype=np.int64)
+        cand = [(float(dist2[f]), xs[i], float(ws[i]), int(ls[i])) for i, f in enumerate(far)]
         if world > 1:
             import torch.distributed as dist
 
@@ -141,8 +157,9 @@ def _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bin_offset_dev, 
             dist.all_gather_object(gathered, cand, group=group)
             cand = sorted((c for part in gathered for c in part), key=lambda c: -c[0])[:n_empty]
         for new_id, (_, x, wt, old_id) in zip(empty, cand):
-            sum_wx[old_id] -= torch.from_numpy(x * wt).to(sum_wx.device)
-            sum_wx[new_id] = torch.from_numpy(x * wt).to(sum_wx.device)
+            delta = torch.from_numpy(x * wt).to(dev)
+            sum_wx[old_id] -= delta
+            sum_wx[new_id] = delta
             sum_w[new_id] = wt
             sum_w[old_id] -= wt
             changed = True

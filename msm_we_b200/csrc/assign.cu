@@ -458,8 +458,8 @@ __global__ void __launch_bounds__(CW * 32, (CW == 4 ? (NT <= 4 ? 4 : 2) : 1)) as
     asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
-// Near-tie re-check.  One warp per flagged point: scores of ALL centres of the point's bin from a
-// sequential fp64 FMA chain over k (the order DMMA itself uses), then
+// Near-tie re-check.  One warp per flagged point: fp64 scores of ALL centres of the point's bin (32 interleaved FMA
+// chains over k, combined by a fixed butterfly: a deterministic order; any fp64 order is well inside the tie band), then
 //     label = lowest j with score_j <= min_j score_j + tol,
 //     tol   = TIE_C (D+8) 2^-53 cmax (2 ||x|| + cmax),  cmax = max_j ||c_j||,
 // i.e. scores that differ by less than the rounding noise of their own evaluation count as tied and the
@@ -473,52 +473,60 @@ __global__ void __launch_bounds__(128)
                           int32_t* __restrict__ local_out) {
     pdl_wait();
     pdl_launch_dependents();
+    // One warp per listed point.  A centre's score is formed by the whole warp: lanes stride the D dimension (coalesced
+    // reads of the centre row; the point row stays in L1), partial fp64 FMA chains are combined by a fixed butterfly, so
+    // every lane holds the same s_j and the result does not depend on scheduling.  Lane j % 32 keeps s_j of round j / 32
+    // in a register, so the tolerance pass needs no second evaluation for K_b <= 32 * RC_ROUNDS.
+    constexpr int RC_ROUNDS = 8;
     const int n = *count;
     const int lane = threadIdx.x & 31;
     const int warps_total = gridDim.x * (blockDim.x >> 5);
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
     for (int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps_total) {
         const int32_t pt = list[e];
         const int32_t b = bin[pt];
         const int64_t coff = bin_offset[b];
         const int kb = (int)(bin_offset[b + 1] - coff);
         const double* x = X + (int64_t)pt * ldx;
-        double xx = 0.0;
-        for (int k = 0; k < D; ++k) xx = fma(x[k], x[k], xx);
-        const double inf = __longlong_as_double(0x7ff0000000000000ll);
-        double smin = inf, cm = 0.0;
-        for (int j0 = 0; j0 < kb; j0 += 32) {
-            const int j = j0 + lane;
-            if (j < kb) {
-                const double* c = centers + (coff + j) * D;
-                double acc = 0.0;
-                for (int k = 0; k < D; ++k) acc = fma(x[k], c[k], acc);
-                const double cs = csq[coff + j];
-                const double s = fma(-2.0, acc, cs);
-                if (s < smin) smin = s;
-                cm = fmax(cm, cs);
+        auto score = [&](int j, double& xx_part) {
+            const double* c = centers + (coff + j) * D;
+            double acc = 0.0;
+            for (int k = lane; k < D; k += 32) {
+                const double xv = x[k];
+                acc = fma(xv, c[k], acc);
+                if (j == 0) xx_part = fma(xv, xv, xx_part);
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            return fma(-2.0, acc, csq[coff + j]);
+        };
+        double sc[RC_ROUNDS];
+#pragma unroll
+        for (int r = 0; r < RC_ROUNDS; ++r) sc[r] = inf;
+        double smin = inf, cm = 0.0, xx = 0.0;
+        for (int j = 0; j < kb; ++j) {
+            const double s = score(j, xx);
+            if (s < smin) smin = s;
+            cm = fmax(cm, csq[coff + j]);
+            const int r = j >> 5;
+#pragma unroll
+            for (int rr = 0; rr < RC_ROUNDS; ++rr)
+                if (rr == r && (j & 31) == lane) sc[rr] = s;
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            smin = fmin(smin, __shfl_xor_sync(0xffffffffu, smin, o));
-            cm = fmax(cm, __shfl_xor_sync(0xffffffffu, cm, o));
-        }
+        for (int o = 16; o > 0; o >>= 1) xx += __shfl_xor_sync(0xffffffffu, xx, o);
         const double cmax = sqrt(cm);
         const double tol = tie_scale * cmax * (2.0 * sqrt(xx) + cmax);
         int best = 0x7fffffff;
-        for (int j0 = 0; j0 < kb && best == 0x7fffffff; j0 += 32) {
-            const int j = j0 + lane;
-            int cand = 0x7fffffff;
-            if (j < kb) {
-                const double* c = centers + (coff + j) * D;
-                double acc = 0.0;
-                for (int k = 0; k < D; ++k) acc = fma(x[k], c[k], acc);
-                const double s = fma(-2.0, acc, csq[coff + j]);
-                if (s <= smin + tol) cand = j;
-            }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
-            best = cand;
+        for (int r = 0; r < RC_ROUNDS; ++r) {
+            if (best != 0x7fffffff || r * 32 >= kb) break;
+            const unsigned m = __ballot_sync(0xffffffffu, sc[r] <= smin + tol);      // (+inf on lanes past K_b: never set)
+            if (m) best = r * 32 + (__ffs(m) - 1);
+        }
+        for (int j = 32 * RC_ROUNDS; j < kb && best == 0x7fffffff; ++j) {              // very wide bins: evaluate again
+            double dummy = 0.0;
+            if (score(j, dummy) <= smin + tol) best = j;
         }
         if (best == 0x7fffffff) best = 0;  // all scores NaN: the reference's scan keeps index 0
         if (lane == 0) {
@@ -726,7 +734,7 @@ extern "C" int mwe_assign_stratified_f64(const double* X, int64_t N, int D, int6
         rc = vec2 ? dispatch_nt<2>(nt, p, max_tiles, s) : dispatch_nt<1>(nt, p, max_tiles, s);
     }
     if (rc != MWE_OK) return rc;
-    MWE_CHECK_CUDA(launch_pdl(assign_recheck_kernel, dim3(sm_count()), dim3(128), 0, s, X, ldx, D, bin, centers, csq, bin_offset,
+    MWE_CHECK_CUDA(launch_pdl(assign_recheck_kernel, dim3(sm_count() * 8), dim3(128), 0, s, X, ldx, D, bin, centers, csq, bin_offset,
                               ws.recheck_list, ws.recheck_count, p.tie_scale, label_out, local_out));
     return MWE_OK;
 }

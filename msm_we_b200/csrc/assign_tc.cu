@@ -568,6 +568,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
 static constexpr int TC2_A_STAGE_COLS = 64;
 static constexpr int TC2_MAX_A_STAGES = 4;
 static constexpr int TC2_MAX_B_STAGES = 4;
+static constexpr int TC2_CONV_WARPS = 16;                  // 4 per TMEM lane quarter: each converts 8 of the chunk's 32 elements
+static constexpr int TC2_KSUB = TC_KC / (TC2_CONV_WARPS / 4);   // elements per thread and chunk
+static constexpr int TC2_THREADS = (TC_CONV_WARP0 + TC2_CONV_WARPS) * 32;
 
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -575,6 +578,12 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
         "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
     asm volatile(
@@ -594,7 +603,7 @@ struct Tc2Params {
 };
 
 template <int VEC>
-__global__ void __launch_bounds__(TC_THREADS, 1) assign_tc2_kernel(const Tc2Params qq) {
+__global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Params qq) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const TcParams& q = qq.t;
     const AssignParams& p = q.a;
@@ -603,7 +612,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc2_kernel(const Tc2Para
     __shared__ uint64_t b_full[TC2_MAX_B_STAGES], b_empty[TC2_MAX_B_STAGES]; // centre blocks in shared memory
     __shared__ uint64_t tmem_full[2], tmem_empty[2], xn_full[2], xn_empty[2];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float s_xn[2][2][TC_TP];                  // [buffer][k-half][row]: partial centred ||x'||^2
+    __shared__ float s_xn[2][TC2_CONV_WARPS / 4][TC_TP];    // [buffer][k-slice][row]: partial centred ||x'||^2
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -615,11 +624,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc2_kernel(const Tc2Para
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < n_raw; ++s) {
-            mbar_init(&raw_full[s], TC_CONV_WARPS * 32);      // every staging thread: cp.async ... arrive.noinc
-            mbar_init(&raw_empty[s], TC_CONV_WARPS);          // one lane per converter warp
+            mbar_init(&raw_full[s], TC2_CONV_WARPS * 32);     // every staging thread: cp.async ... arrive.noinc
+            mbar_init(&raw_empty[s], TC2_CONV_WARPS);         // one lane per converter warp
         }
         for (int s = 0; s < n_a; ++s) {
-            mbar_init(&a_full[s], TC_CONV_WARPS);             // one lane per converter warp, after its tcgen05.st
+            mbar_init(&a_full[s], TC2_CONV_WARPS);            // one lane per converter warp, after its tcgen05.st
             mbar_init(&a_empty[s], 1);                        // tcgen05.commit
         }
         for (int s = 0; s < n_b; ++s) {
@@ -629,7 +638,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc2_kernel(const Tc2Para
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);    // tcgen05.commit
             mbar_init(&tmem_empty[i], 4);   // one lane per epilogue warp
-            mbar_init(&xn_full[i], TC_CONV_WARPS);
+            mbar_init(&xn_full[i], TC2_CONV_WARPS);
             mbar_init(&xn_empty[i], 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -639,7 +648,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc2_kernel(const Tc2Para
         int32_t* s_tp = reinterpret_cast<int32_t*>(raw_base + (size_t)n_raw * TC_RAW_BYTES);
         int32_t* s_bs = s_tp + (p.nbins + 1);
         int64_t* s_bo = reinterpret_cast<int64_t*>(s_bs + (p.nbins + 1));
-        for (int b = threadIdx.x; b <= p.nbins; b += TC_THREADS) {
+        for (int b = threadIdx.x; b <= p.nbins; b += TC2_THREADS) {
             s_tp[b] = p.tile_prefix[b];
             s_bs[b] = p.bin_start[b];
             s_bo[b] = p.bin_offset[b];
@@ -764,7 +773,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc2_kernel(const Tc2Para
             const int xb = ti & 1;
             timed_wait(&xn_full[xb], xb ? xph1 : xph0, w1, prof);
             if (xb) xph1 ^= 1u; else xph0 ^= 1u;
-            const float xn2c = s_xn[xb][0][row] + s_xn[xb][1][row];
+            float xn2c = 0.f;
+#pragma unroll
+            for (int h = 0; h < TC2_CONV_WARPS / 4; ++h) xn2c += s_xn[xb][h][row];
             __syncwarp();
             if (lane == 0) mbar_arrive(&xn_empty[xb]);
             if (pt >= 0) {
@@ -785,11 +796,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc2_kernel(const Tc2Para
         // (a) every warp issues the cp.async copies of 16 point rows of the chunk n_raw-1 steps ahead (fire and forget,
         //     completion lands on raw_full); (b) converts ITS rows of the current chunk: thread = one point row (the
         //     TMEM lane it may write), 16 consecutive elements of the 32-element chunk.
-        const int cwp = warp - TC_CONV_WARP0;              // 0..7
+        const int cwp = warp - TC_CONV_WARP0;              // 0..15
         const int quarter = warp & 3;                      // TMEM lane quarter this warp can access
-        const int khalf = cwp >> 2;                        // which 16 elements of the chunk
+        const int khalf = cwp >> 2;                        // which TC2_KSUB elements of the chunk
         const int row = quarter * 32 + lane;
-        constexpr int CR = TC_TP / TC_CONV_WARPS;          // rows each warp copies (16)
+        constexpr int CR = TC_TP / TC2_CONV_WARPS;         // rows each warp copies (8)
         constexpr int SEGS = TC_KC / VEC;
         constexpr int RPI = 32 / SEGS;
         constexpr int XQ = CR / RPI;
@@ -852,11 +863,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc2_kernel(const Tc2Para
             if (issued < total_steps) issue_one();
             timed_wait(&raw_full[rs], rphase, w0, prof);
             const double* st = reinterpret_cast<const double*>(raw_base + (size_t)rs * TC_RAW_BYTES);
-            const double* src = st + row * TC_RAW_LD + 16 * khalf;
-            const double* mup = st + TC_TP * TC_RAW_LD + 16 * khalf;
-            float hi[16], lo[16];
+            const double* src = st + row * TC_RAW_LD + TC2_KSUB * khalf;
+            const double* mup = st + TC_TP * TC_RAW_LD + TC2_KSUB * khalf;
+            float hi[TC2_KSUB], lo[TC2_KSUB];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
+            for (int e = 0; e < TC2_KSUB / 2; ++e) {
                 const double2 xv = *reinterpret_cast<const double2*>(src + 2 * e);
                 const double2 mv = *reinterpret_cast<const double2*>(mup + 2 * e);
                 const float x0 = (float)(xv.x - mv.x), x1 = (float)(xv.y - mv.y);
@@ -870,9 +881,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc2_kernel(const Tc2Para
             if (lane == 0) mbar_arrive(&raw_empty[rs]);        // the staged fp64 chunk is in registers
             timed_wait(&a_empty[as], aphase ^ 1u, w1, prof);   // the MMAs that read this TMEM stage have completed
             tc_fence_after();
-            const uint32_t ta = tmem_base + a_lane + qq.a_col0 + (uint32_t)(as * TC2_A_STAGE_COLS + 16 * khalf);
-            tmem_st16(ta, hi);
-            tmem_st16(ta + TC_KC, lo);
+            const uint32_t ta = tmem_base + a_lane + qq.a_col0 + (uint32_t)(as * TC2_A_STAGE_COLS + TC2_KSUB * khalf);
+            if (TC2_KSUB == 8) {
+                tmem_st8(ta, hi);
+                tmem_st8(ta + TC_KC, lo);
+            } else {
+                tmem_st16(ta, hi);
+                tmem_st16(ta + TC_KC, lo);
+            }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
@@ -1038,7 +1054,7 @@ int launch_assign_tc(const AssignParams& p_in, int32_t max_k, int64_t N, void* p
                 configured = smem;
             }
             if (ev0) MWE_CHECK_CUDA(cudaEventRecord(ev0, stream));
-            assign_tc2_kernel<2><<<(unsigned)grid, TC_THREADS, smem, stream>>>(q2);
+            assign_tc2_kernel<2><<<(unsigned)grid, TC2_THREADS, smem, stream>>>(q2);
         } else {
             static size_t configured_dev[MWE_MAX_DEVICES] = {};
             size_t& configured = configured_dev[device_slot()];
@@ -1047,7 +1063,7 @@ int launch_assign_tc(const AssignParams& p_in, int32_t max_k, int64_t N, void* p
                 configured = smem;
             }
             if (ev0) MWE_CHECK_CUDA(cudaEventRecord(ev0, stream));
-            assign_tc2_kernel<1><<<(unsigned)grid, TC_THREADS, smem, stream>>>(q2);
+            assign_tc2_kernel<1><<<(unsigned)grid, TC2_THREADS, smem, stream>>>(q2);
         }
         MWE_CHECK_LAUNCH();
         if (ev1) MWE_CHECK_CUDA(cudaEventRecord(ev1, stream));

@@ -313,6 +313,29 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Squared distance of listed points to their own centre (empty-cluster relocation of the Lloyd M step: sklearn moves an
+// empty cluster onto the point farthest from its centre, _k_means_common.pyx _relocate_empty_clusters_dense).  One warp
+// per listed point, lanes stride the features, fixed butterfly.
+__global__ void __launch_bounds__(256)
+    point_center_dist2_kernel(const double* __restrict__ X, int64_t ldx, int D, const int32_t* __restrict__ list, int64_t n,
+                              const int64_t* __restrict__ label, const double* __restrict__ centers, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t e = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); e < n; e += warps) {
+        const int64_t pt = list[e];
+        const double* x = X + pt * ldx;
+        const double* c = centers + label[pt] * D;
+        double acc = 0.0;
+        for (int k = lane; k < D; k += 32) {
+            const double d = x[k] - c[k];
+            acc = fma(d, d, acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) out[e] = acc;
+    }
+}
+
 static int group_by_label(const int64_t* label, int64_t N, int64_t n_labels, uint32_t* members_out, int32_t* seg_start_out,
                           void* workspace, size_t workspace_bytes, cudaStream_t s) {
     MWE_REQUIRE(N >= 0 && N < ((int64_t)1 << 31), "group_by_label: N must be < 2^31 per call");
@@ -409,5 +432,19 @@ extern "C" int mwe_label_stats_f64(const double* values, int64_t ldv, const uint
     if (blocks > cap) blocks = cap;
     MWE_CHECK_CUDA(launch_pdl(label_stats_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream),
                               values, ldv, members, seg_start, n_labels, count, sum, vmin, vmax));
+    return MWE_OK;
+}
+
+extern "C" int mwe_point_center_dist2_f64(const double* X, int64_t ldx, int D, const int32_t* list, int64_t n,
+                                          const int64_t* label, const double* centers, double* out, void* stream) {
+    using namespace mwe;
+    MWE_REQUIRE(n >= 0 && D >= 1 && ldx >= D, "point_center_dist2: bad shape");
+    if (n == 0) return MWE_OK;
+    MWE_REQUIRE(X && list && label && centers && out, "point_center_dist2: null pointer");
+    int64_t blocks = (n + 7) / 8;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    point_center_dist2_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(X, ldx, D, list, n, label, centers, out);
+    MWE_CHECK_LAUNCH();
     return MWE_OK;
 }

@@ -324,3 +324,16 @@ def rows_with_nan(X):
     out = torch.empty(N, dtype=torch.uint8, device=X.device)
     check(lib.mwe_rows_with_nan_f64(_ptr(X), N, D, X.stride(0) if N > 1 else D, _ptr(out), _stream()), "mwe_rows_with_nan_f64")
     return out
+
+
+def point_center_dist2(X, index_list, labels, centers):
+    """fp64 ``||x_i - centers[labels_i]||^2`` for the points in ``index_list`` (int32 CUDA tensor)."""
+    if not X.is_cuda or X.dtype != torch.float64 or X.dim() != 2 or X.stride(1) != 1:
+        raise TypeError("X: expected a CUDA float64 [N, D] tensor with unit column stride")
+    _req(index_list, torch.int32, "index_list"); _req(labels, torch.int64, "labels"); _req(centers, torch.float64, "centers")
+    n = index_list.numel()
+    out = torch.empty(n, dtype=torch.float64, device=X.device)
+    N, D = X.shape
+    check(lib.mwe_point_center_dist2_f64(_ptr(X), X.stride(0) if N > 1 else D, D, _ptr(index_list), n, _ptr(labels),
+                                         _ptr(centers), _ptr(out), _stream()), "mwe_point_center_dist2_f64")
+    return out

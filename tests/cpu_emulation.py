@@ -197,6 +197,11 @@ def emulate_kernels(monkeypatch):
     def rows_with_nan(X):
         return torch.from_numpy(np.isnan(_np(X)).any(axis=1).astype(np.uint8))
 
+    def point_center_dist2(X, index_list, labels, centers):
+        x, idx = _np(X), _np(index_list).astype(np.int64)
+        c = _np(centers)[_np(labels)[idx]]
+        return torch.from_numpy(((x[idx] - c) ** 2).sum(axis=1))
+
     def project(X, components, mean=None, out=None):
         r = O.linear_transform(_np(X), _np(components), None if mean is None else _np(mean))
         return torch.from_numpy(np.ascontiguousarray(r))
@@ -204,6 +209,6 @@ def emulate_kernels(monkeypatch):
     for name, fn in dict(centers_sqnorm=centers_sqnorm, bin_flags=bin_flags, assign_stratified=assign_stratified,
                          minibatch_update=minibatch_update, centroid_accumulate=centroid_accumulate,
                          lloyd_finalize=lloyd_finalize, flux_accumulate=flux_accumulate, divide_=divide_,
-                         group_by_label=group_by_label, label_stats=label_stats, rows_with_nan=rows_with_nan,
+                         group_by_label=group_by_label, label_stats=label_stats, rows_with_nan=rows_with_nan, point_center_dist2=point_center_dist2,
                          project=project).items():
         monkeypatch.setattr(ops, name, fn)
