@@ -50,11 +50,15 @@ __global__ void __launch_bounds__(256)
 
 enum CentroidMode { CM_ACCUMULATE = 0, CM_MINIBATCH = 1 };
 
-static constexpr int CS_THREADS = 128;
-static constexpr int CS_ROWS = 24;    // member rows per staged chunk (3 stages x 24 rows x 512 B = 36 KB: five CTAs per SM)
-static constexpr int CS_FT = 64;      // feature columns per pass: thread f < CS_FT owns column ft*CS_FT + f
 static constexpr int CS_ST = 3;       // ring depth: two chunks in flight per CTA while one is being added
 static constexpr int CS_SUPER = 8;    // chunks per metadata super-chunk
+// Two geometries.  FT = feature columns handled per pass over a cluster's member list (thread f < FT owns column
+// ft*FT + f).  Narrow rows (D <= 64... cfg2) use 64 columns x 24 staged rows; wide rows (cfg5: 256, cfg3: 3000) use 256
+// columns x 6 rows, so a cluster's member list is walked ONCE per 256 features instead of once per 64 -- with a few
+// hundred members per cluster the per-pass prologue (two dependent metadata loads + pipeline fill) is what costs.
+template <int FT> struct CsGeom;
+template <> struct CsGeom<64> { static constexpr int THREADS = 128, ROWS = 24; };
+template <> struct CsGeom<256> { static constexpr int THREADS = 288, ROWS = 6; };   // 256 owners + one warp (weight sum)
 
 // One CTA per cluster.  The add chain of a (cluster, feature) pair is sequential by definition (sample order, product
 // and sum rounded separately), so the parallelism is clusters x features; what must not be serial is the MEMORY
@@ -63,13 +67,15 @@ static constexpr int CS_SUPER = 8;    // chunks per metadata super-chunk
 // prefetched into registers, and the 64 feature threads only ever read shared memory.  One extra thread adds the
 // weights in member order while the others work (the first version made every thread walk the whole weight list
 // through two dependent global loads per member before it started: 416 us on the cfg2 shape, now HBM-bound).
-template <int MODE, int VEC>
-__global__ void __launch_bounds__(CS_THREADS)
+template <int MODE, int VEC, int CS_FT>
+__global__ void __launch_bounds__(CsGeom<CS_FT>::THREADS, CS_FT == 256 ? 4 : 5)
     centroid_sum_kernel(const double* __restrict__ X, int64_t ldx, int D, const double* __restrict__ w,
                         const uint32_t* __restrict__ members, const int32_t* __restrict__ seg_start,
                         double* __restrict__ out_wx, double* __restrict__ out_w) {
     pdl_wait();
     pdl_launch_dependents();
+    constexpr int CS_THREADS = CsGeom<CS_FT>::THREADS;
+    constexpr int CS_ROWS = CsGeom<CS_FT>::ROWS;
     constexpr int SROWS = CS_SUPER * CS_ROWS;         // members whose index + weight are staged together
     static_assert(SROWS <= 2 * CS_THREADS, "two metadata entries per thread");
     __shared__ __align__(16) double s_x[CS_ST][CS_ROWS][CS_FT];
@@ -262,8 +268,17 @@ static int centroid_run(const double* X, int64_t N, int D, int64_t ldx, const do
         MWE_CHECK_CUDA(cudaMemsetAsync(seg_start, 0, (size_t)(sumK + 2) * sizeof(int32_t), s));
     }
     const bool vec2 = (D % 2 == 0) && (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
-    if (vec2) MWE_CHECK_CUDA(launch_pdl(centroid_sum_kernel<MODE, 2>, dim3((unsigned)sumK), dim3(CS_THREADS), 0, s, X, ldx, D, w, vs, seg_start, out_wx, out_w));
-    else MWE_CHECK_CUDA(launch_pdl(centroid_sum_kernel<MODE, 1>, dim3((unsigned)sumK), dim3(CS_THREADS), 0, s, X, ldx, D, w, vs, seg_start, out_wx, out_w));
+    const bool wide = D > 96;
+    const dim3 g((unsigned)sumK);
+    if (wide) {
+        const dim3 b(CsGeom<256>::THREADS);
+        if (vec2) MWE_CHECK_CUDA(launch_pdl(centroid_sum_kernel<MODE, 2, 256>, g, b, 0, s, X, ldx, D, w, vs, seg_start, out_wx, out_w));
+        else MWE_CHECK_CUDA(launch_pdl(centroid_sum_kernel<MODE, 1, 256>, g, b, 0, s, X, ldx, D, w, vs, seg_start, out_wx, out_w));
+    } else {
+        const dim3 b(CsGeom<64>::THREADS);
+        if (vec2) MWE_CHECK_CUDA(launch_pdl(centroid_sum_kernel<MODE, 2, 64>, g, b, 0, s, X, ldx, D, w, vs, seg_start, out_wx, out_w));
+        else MWE_CHECK_CUDA(launch_pdl(centroid_sum_kernel<MODE, 1, 64>, g, b, 0, s, X, ldx, D, w, vs, seg_start, out_wx, out_w));
+    }
     return MWE_OK;
 }
 

@@ -7,8 +7,11 @@ from msm_we_b200 import ops
 from msm_we_b200.binning import RectilinearBinMapper
 from msm_we_b200.engine import DeviceClusters
 
+import dataclasses
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 cfg = synthetic.CONFIGS[name]
+if len(sys.argv) > 2:
+    cfg = dataclasses.replace(cfg, n_iters=int(sys.argv[2]))
 dev = torch.device("cuda:0")
 means, centers = synthetic.make_centers(cfg)
 basis, target = synthetic.region_bounds(cfg)
