@@ -200,6 +200,25 @@ MWE_API int mwe_flux_accumulate_f64(const int64_t* start, const int64_t* end, co
                             int64_t* nnz_out, void* workspace, size_t workspace_bytes, int32_t* err_count,
                             void* stream);
 /* buf[i] = buf[i] / divisor      (fluxMatrix / nI, _fluxmatrix.py:342) */
+/* ---- history colours along WE lineages ----------------------------------------
+ * Replaces the per-trajectory Python walk of NonMarkovModel.fit (msm_we/nmm.py:117-167) for trajectories that are the
+ * lineages of a weighted-ensemble run (traced through seg_index['parent_id'], msm_we/_hamsm/_data.py:807-932):
+ *   mwe_lineage_colour : one iteration forward.  colour_now[s] = 0 if state_class[label_now[s]] == 1 (state in A),
+ *                        1 if == 2 (state in B), else colour_prev[parent[s]] (-1 = undefined; colour_prev NULL for the
+ *                        first coloured iteration, parent < 0 = no parent);
+ *   mwe_lineage_leaves : one iteration backward.  leaves_prev[parent[s]] += leaves_now[s] (caller zeroes leaves_prev
+ *                        and seeds the last iteration with 1): how many traced trajectories pass through a segment;
+ *   mwe_lineage_records: the coloured transition records of one iteration for mwe_flux_accumulate_f64 with C = 2:
+ *                        (label_prev[parent], label_now, colour_prev[parent], colour_now, weight = leaves_now), weight 0
+ *                        where a colour is undefined or the segment has no parent. */
+MWE_API int mwe_lineage_colour(const int64_t* label_now, const int64_t* parent, int64_t S_now, const int8_t* colour_prev,
+                               int64_t S_prev, const uint8_t* state_class, int64_t n_states, int8_t* colour_now, void* stream);
+MWE_API int mwe_lineage_leaves(const int64_t* parent, const uint64_t* leaves_now, int64_t S_now, uint64_t* leaves_prev,
+                               int64_t S_prev, void* stream);
+MWE_API int mwe_lineage_records(const int64_t* label_prev, const int8_t* colour_prev, int64_t S_prev, const int64_t* label_now,
+                                const int8_t* colour_now, const int64_t* parent, const uint64_t* leaves_now, int64_t S_now,
+                                int64_t* start, int64_t* end, uint8_t* col0, uint8_t* col1, double* w, void* stream);
+
 MWE_API int mwe_divide_f64(double* buf, int64_t count, double divisor, void* stream);
 
 /* ---- one-call hot path ------------------------------------------------------------------------

@@ -57,6 +57,9 @@ SIGNATURES = {
     "mwe_label_stats_f64": (_int, [_p, _i64, _p, _p, _i64, _p, _p, _p, _p, _p]),
     "mwe_flux_workspace_bytes": (_sz, [_i64]),
     "mwe_flux_accumulate_f64": (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _int, _p, _i64, _p, _p, _p, _p, _p, _p, _sz, _p, _p]),
+    "mwe_lineage_colour": (_int, [_p, _p, _i64, _p, _i64, _p, _i64, _p, _p]),
+    "mwe_lineage_leaves": (_int, [_p, _p, _i64, _p, _i64, _p]),
+    "mwe_lineage_records": (_int, [_p, _p, _i64, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p]),
     "mwe_divide_f64": (_int, [_p, _i64, _f64, _p]),
     "mwe_hotpath_workspace_bytes": (_sz, [_i64, _i32]),
     "mwe_hotpath_workspace_bytes_ex": (_sz, [_i64, _i32, _int, _i32, _int]),

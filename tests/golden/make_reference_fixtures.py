@@ -353,7 +353,7 @@ def run_colour():
             cur = int(parents[it][cur])
         trajs.append(t[::-1])
     stateA, stateB = [0], [n_states - 1]
-    nm = NonMarkovModel(trajs, stateA, stateB, lag_time=1, clean_traj=False, sliding_window=True)
+    nm = NonMarkovModel(trajs, stateA, stateB, lag_time=1, clean_traj=True, sliding_window=True)   # (clean_traj=False renumbers states with a counter that restarts per trajectory)
     out = dict(labels=np.array(labels, dtype=np.int64), parents=np.array(parents, dtype=np.int64),
                n_states=np.int64(n_states), stateA=np.array(stateA), stateB=np.array(stateB),
                nm_cmatrix=np.asarray(nm.nm_cmatrix, dtype=np.float64))

@@ -213,3 +213,70 @@ def test_host_pinning_degrades_without_a_gpu():
     assert pins.ensure(np.ones(16)) is False
     view = a.reshape(-1)[8:24]
     assert HostPins._owner(view) is a
+
+
+def _gloo_lloyd_worker(rank, world, port, tmp):
+    os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world)})
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cpu_emulation import emulate_kernels
+    from msm_we_b200 import clustering_ops
+
+    mp_ = pytest.MonkeyPatch()
+    emulate_kernels(mp_)
+    X, bins, init, K = _lloyd_case()
+    n = len(X)
+    lo, hi = n * rank // world, n * (rank + 1) // world          # contiguous shard, as iteration ranges are
+    centers = torch.from_numpy(np.concatenate(init).copy())
+    offs = torch.from_numpy(np.arange(0, (len(init) + 1) * K, K, dtype=np.int64))
+    clustering_ops.lloyd_fit(torch.from_numpy(X[lo:hi].copy()), None, torch.from_numpy(bins[lo:hi].copy()), centers, offs, K, 4,
+                             group=dist.group.WORLD)
+    np.save(os.path.join(tmp, f"centers_{rank}.npy"), centers.numpy())
+    mp_.undo()
+    dist.destroy_process_group()
+
+
+def _lloyd_case():
+    rng = np.random.default_rng(21)
+    nbins, K, D = 3, 5, 6
+    Xs, bs, init = [], [], []
+    for b in range(nbins):
+        m = rng.normal(0, 4, size=(K, D))
+        k = rng.integers(0, K, size=300)
+        Xs.append(m[k] + rng.normal(0, 0.7, size=(300, D)))
+        bs.append(np.full(300, b, dtype=np.int32))
+        c = m + rng.normal(0, 0.3, size=(K, D))
+        if b == 1:
+            c[3] = c[0]              # a duplicate centre: empty cluster -> relocation, candidates exchanged between ranks
+        init.append(c)
+    order = rng.permutation(900)
+    return np.concatenate(Xs)[order], np.concatenate(bs)[order], init, K
+
+
+def test_sharded_lloyd_gloo_world2_matches_single_process(tmp_path, monkeypatch):
+    """Iteration-range sharded Lloyd (partial sums all-reduced, empty-cluster candidates all-gathered) equals the
+    single-process fit and the real sklearn KMeans per bin."""
+    import torch
+    import torch.multiprocessing as mp
+    from sklearn.cluster import KMeans
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    port = 29500 + ((os.getpid() + 977) % 2000)
+    mp.spawn(_gloo_lloyd_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "centers_0.npy"), np.load(tmp_path / "centers_1.npy")
+    assert np.array_equal(a, b)
+    from cpu_emulation import emulate_kernels
+    from msm_we_b200 import clustering_ops
+
+    emulate_kernels(monkeypatch)
+    X, bins, init, K = _lloyd_case()
+    centers = torch.from_numpy(np.concatenate(init).copy())
+    offs = torch.from_numpy(np.arange(0, (len(init) + 1) * K, K, dtype=np.int64))
+    clustering_ops.lloyd_fit(torch.from_numpy(X), None, torch.from_numpy(bins), centers, offs, K, 4)
+    assert np.allclose(a, centers.numpy(), rtol=1e-12, atol=1e-13)
+    for bb in range(len(init)):
+        ref = KMeans(n_clusters=K, init=init[bb], n_init=1, max_iter=4, tol=0.0, algorithm="lloyd").fit(X[bins == bb]).cluster_centers_
+        assert np.allclose(a[bb * K:(bb + 1) * K], ref, rtol=1e-11, atol=1e-12), bb

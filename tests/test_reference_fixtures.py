@@ -314,3 +314,37 @@ def test_oracle_matches_reference_run_labels_and_flux():
     ref[fx["flux_row"], fx["flux_col"]] = fx["flux_val"]
     got = O.flux_matrix(cfg.n_clusters, per, basis, target)
     assert np.array_equal(got, ref)
+
+
+@pytest.mark.gpu
+def test_lineage_colour_counts_match_reference_nonmarkov_fit():
+    """History-coloured count matrix over WE lineages: the reference's NonMarkovModel.fit over the traced trajectories
+    (fixture ref_colour_lineages.npz, made by executing msm_we/nmm.py) vs the segment-wise GPU formulation + K3 (C = 2).
+    Counts are integers: bit-exact."""
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from msm_we_b200.lineage import coloured_lineage_counts
+
+    fx = np.load(os.path.join(GOLDEN, "ref_colour_lineages.npz"))
+    got = coloured_lineage_counts(list(fx["labels"]), list(fx["parents"]), int(fx["n_states"]), fx["stateA"].tolist(),
+                                  fx["stateB"].tolist())
+    assert got.shape == fx["nm_cmatrix"].shape
+    assert np.array_equal(got, fx["nm_cmatrix"])
+
+
+def test_oracle_colour_counts_match_reference_nonmarkov_fit():
+    """Pins the oracle's colour walk to the reference-executed lineage fixture (CPU)."""
+    fx = np.load(os.path.join(GOLDEN, "ref_colour_lineages.npz"))
+    labels, parents = fx["labels"], fx["parents"]
+    n_it, S = labels.shape
+    trajs = []
+    for s in range(S):
+        t, cur = [], s
+        for it in range(n_it - 1, -1, -1):
+            t.append(int(labels[it][cur]))
+            cur = int(parents[it][cur])
+        trajs.append(t[::-1])
+    got = O.colour_counts(trajs, int(fx["n_states"]), fx["stateA"].tolist(), fx["stateB"].tolist(), lag=1)
+    assert np.array_equal(got, fx["nm_cmatrix"])
