@@ -568,7 +568,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams
 static constexpr int TC2_A_STAGE_COLS = 64;
 static constexpr int TC2_MAX_A_STAGES = 4;
 static constexpr int TC2_MAX_B_STAGES = 4;
-static constexpr int TC2_CONV_WARPS = 16;                  // 4 per TMEM lane quarter: each converts 8 of the chunk's 32 elements
+static constexpr int TC2_CONV_WARPS = 8;                   // 2 per TMEM lane quarter: each converts 16 of the chunk's 32 elements
+                                                           // (16 warps x 8 elements measured slower: 0.999 vs 0.903 ms, cfg5 slice)
 static constexpr int TC2_KSUB = TC_KC / (TC2_CONV_WARPS / 4);   // elements per thread and chunk
 static constexpr int TC2_THREADS = (TC_CONV_WARP0 + TC2_CONV_WARPS) * 32;
 
@@ -597,6 +598,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
 
 struct Tc2Params {
     TcParams t;
+    int ablate;       // tuning only: bit 0 = issue no MMAs, bit 1 = skip the fp64 -> TF32 conversion arithmetic
     int n_a;          // A stages in tensor memory
     int n_b;          // centre-block stages in shared memory
     uint32_t a_col0;  // first TMEM column of the A stages
@@ -694,6 +696,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Par
                         tc_fence_after();
                         const uint32_t a_hi = tmem_base + qq.a_col0 + (uint32_t)(as * TC2_A_STAGE_COLS), a_lo = a_hi + TC_KC;
                         const uint32_t b_hi = smem_u32(b_base + (size_t)bs * b_bytes), b_lo = b_hi + (uint32_t)(ng * TC_SBO);
+                        if (!(qq.ablate & 1))
 #pragma unroll
                         for (int j = 0; j < TC_KC / 8; ++j) {
                             const uint32_t ko = (uint32_t)(j * 2 * TC_LBO);
@@ -796,11 +799,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Par
         // (a) every warp issues the cp.async copies of 16 point rows of the chunk n_raw-1 steps ahead (fire and forget,
         //     completion lands on raw_full); (b) converts ITS rows of the current chunk: thread = one point row (the
         //     TMEM lane it may write), 16 consecutive elements of the 32-element chunk.
-        const int cwp = warp - TC_CONV_WARP0;              // 0..15
+        const int cwp = warp - TC_CONV_WARP0;              // 0..TC2_CONV_WARPS-1
         const int quarter = warp & 3;                      // TMEM lane quarter this warp can access
         const int khalf = cwp >> 2;                        // which TC2_KSUB elements of the chunk
         const int row = quarter * 32 + lane;
-        constexpr int CR = TC_TP / TC2_CONV_WARPS;         // rows each warp copies (8)
+        constexpr int CR = TC_TP / TC2_CONV_WARPS;         // rows each warp copies
         constexpr int SEGS = TC_KC / VEC;
         constexpr int RPI = 32 / SEGS;
         constexpr int XQ = CR / RPI;
@@ -866,6 +869,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Par
             const double* src = st + row * TC_RAW_LD + TC2_KSUB * khalf;
             const double* mup = st + TC_TP * TC_RAW_LD + TC2_KSUB * khalf;
             float hi[TC2_KSUB], lo[TC2_KSUB];
+            if (qq.ablate & 2) {
+#pragma unroll
+                for (int e = 0; e < TC2_KSUB; ++e) hi[e] = lo[e] = 0.f;
+            } else
 #pragma unroll
             for (int e = 0; e < TC2_KSUB / 2; ++e) {
                 const double2 xv = *reinterpret_cast<const double2*>(src + 2 * e);
@@ -1043,6 +1050,8 @@ int launch_assign_tc(const AssignParams& p_in, int32_t max_k, int64_t N, void* p
         q.tmem_cols = cols2;
         q2.t = q;
         q2.n_a = n_a;
+        q2.ablate = 0;
+        if (const char* e = getenv("MWE_TC_ABLATE")) q2.ablate = atoi(e);
         q2.n_b = n_b;
         q2.a_col0 = (uint32_t)(2 * L.n_pad);
         const size_t smem = b_bytes * n_b + (size_t)TC_RAW_BYTES * n_raw + table_bytes;

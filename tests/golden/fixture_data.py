@@ -107,3 +107,11 @@ def unpack_iterations(d):
     offs = np.concatenate([[0], np.cumsum(d["in_lens"])])
     return [dict(weights=d["in_weights"][a:b], pcoord=d["in_pcoord"][a:b], coords=d["in_coords"][a:b],
                  parent_id=d["in_parent_id"][a:b]) for a, b in zip(offs[:-1], offs[1:])]
+
+
+def flatten_featurizer(self, coords):
+    """A user featuriser as the HAMSMDriver plugin loads one (``featurization: fixture_data.flatten_featurizer``)."""
+    coords = np.asarray(coords)
+    if coords.ndim == 2:
+        return coords.reshape(1, -1)
+    return coords.reshape(coords.shape[0], -1)

@@ -348,3 +348,75 @@ def test_oracle_colour_counts_match_reference_nonmarkov_fit():
         trajs.append(t[::-1])
     got = O.colour_counts(trajs, int(fx["n_states"]), fx["stateA"].tolist(), fx["stateB"].tolist(), lag=1)
     assert np.array_equal(got, fx["nm_cmatrix"])
+
+
+class _FakeWorkManager:
+    is_master = True
+
+
+class _FakeDataManager:
+    def __init__(self, name):
+        self.we_h5filename = name
+        self.closed = False
+
+    def close_backing(self):
+        self.closed = True
+
+
+class _FakeSimManager:
+    def __init__(self, name):
+        self.work_manager = _FakeWorkManager()
+        self.data_manager = _FakeDataManager(name)
+        self.callbacks = []
+
+    def finalize_run(self):
+        pass
+
+    def register_callback(self, hook, fn, priority):
+        self.callbacks.append((hook, fn, priority))
+
+
+@pytest.mark.parametrize("gpu", BACKENDS)
+def test_hamsm_driver_plugin_builds_the_reference_model(request, monkeypatch, gpu):
+    """The WESTPA plugin boundary (msm_we/westpa_plugins/hamsm_driver.py:8-144) with a stand-in sim_manager /
+    data_manager: callback registration, featuriser loading, build_analyze_model through the whole chain (HDF5 feeder ->
+    clustering -> discretization -> flux -> cleaning -> block validation), model stored on the data manager -- and the
+    model equals the one the reference built from the same WE file (pipeline1d fixture)."""
+    from msm_we_b200 import msm_we as mw
+    from msm_we_b200.westpa_plugins.hamsm_driver import HAMSMDriver
+
+    _backend(request, monkeypatch, gpu)
+    monkeypatch.setattr(mw.modelWE, "processCoordinates", mw.modelWE.processCoordinates)     # restored after the test
+    fx = np.load(os.path.join(GOLDEN, "ref_pipeline1d.npz"))
+    fname = "plugin_pipeline1d_west.h5"
+    refshim.register_we_file(fname, FD.unpack_iterations(fx))
+    sim = _FakeSimManager(fname)
+    cfg = {"model_name": "plugin", "n_clusters": int(fx["K"]), "tau": 1.0, "basis_pcoord_bounds": fx["basis"],
+           "target_pcoord_bounds": fx["target"], "dimreduce_method": "none", "featurization": "fixture_data.flatten_featurizer",
+           "ref_pdb_file": {"coords": None, "nAtoms": int(fx["n_atoms"]), "coord_ndim": int(fx["coord_ndim"])},
+           "user_bin_mapper": _mapper(fx), "cross_validation_groups": 2,
+           "cluster_args": {"random_state": int(fx["cluster_kwarg_random_state"]),
+                            "iters_to_use": fx["cluster_call_iters_to_use"].tolist()}}
+    driver = HAMSMDriver(sim, cfg)
+    assert len(sim.callbacks) == 1 and sim.callbacks[0][0] == sim.finalize_run and sim.callbacks[0][2] == 2
+    # cluster_stratified logs "conflicting parameters" when both first_cluster_iter and iters_to_use arrive and goes on
+    # with iters_to_use, exactly as the reference does (_clustering.py:646-650)
+    model = sim.callbacks[0][1]()
+    assert sim.data_manager.closed and sim.data_manager.hamsm_model is model and driver.data_manager is sim.data_manager
+    _check_clusters(model, fx, "o_")
+    _close(model.fluxMatrix, fx["o_fluxMatrix"], "plugin-built cleaned fluxMatrix")
+    assert len(model.validation_models) == 2
+    for g, vm in enumerate(model.validation_models):
+        _close(vm.fluxMatrix, fx[f"v{g}_fluxMatrix"], f"plugin validation group {g}")
+
+
+def test_dimreduce_refuses_methods_it_cannot_fit():
+    from msm_we_b200.msm_we import LinearCoordinates, modelWE
+
+    m = modelWE()
+    m.dimReduceMethod = "pca"
+    with pytest.raises(NotImplementedError):
+        m.dimReduce(use_weights=True, variance_cutoff=0.9)
+    m.coordinates = LinearCoordinates(np.eye(3)[:2], np.zeros(3))
+    m.dimReduce()
+    assert m.ndim == 2
