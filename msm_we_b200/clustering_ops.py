@@ -105,62 +105,95 @@ def lloyd_fit(X_dev, w_dev, bins_dev, centers_dev, bin_offset_dev, max_k, n_iter
 def _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bins_dev, flags_dev, bin_offset_dev, sum_wx, sum_w, group):
     """sklearn's ``_relocate_empty_clusters_dense`` per WE-bin model, applied to the (all-reduced) partial sums before
     the mean: a cluster that received no weight takes the point farthest from its own centre, which leaves its old
-    cluster.  The decision needs one [sumK] read per Lloyd iteration; when a bin does own an empty cluster, the distances
-    of THAT bin's points to their centres are formed on the device (``point_center_dist2``), only distances + indices
-    come to the host, where the farthest points are picked with the numpy call sklearn uses, and only those few rows
-    are fetched."""
-    sw = sum_w.cpu().numpy()
+    cluster.
+
+    Host round trips are what this costs, so there are few: (1) the [sumK] weight sums (every Lloyd iteration; nothing
+    else happens when no fitted bin owns an empty cluster); when one does: (2) the indices of the affected bins' points,
+    whose distances to their centres are formed on the device (``point_center_dist2``); (3) those distances, from which
+    the host picks each bin's farthest points with the numpy call sklearn uses; (4) the winners' old labels.  The rows
+    themselves never leave the device: they are gathered, (with a process group: all-gathered as one small tensor, the
+    global winners picked from every rank's candidates,) and subtracted / assigned by indexed device updates."""
+    sw = sum_w.cpu().numpy()                                                     # (1)
     if (sw != 0).all():
         return False
     offs = bin_offset_dev.cpu().numpy()
     nbins = len(offs) - 1
-    affected = []
-    for b in range(nbins):
-        lo, hi = int(offs[b]), int(offs[b + 1])
-        if hi > lo and (sw[lo:hi] == 0).any() and sw[lo:hi].sum() != 0:   # a model without any point is not being fitted
-            affected.append(b)
-    world = 1
+    affected = [b for b in range(nbins)
+                if offs[b + 1] > offs[b] and (sw[offs[b]:offs[b + 1]] == 0).any() and sw[offs[b]:offs[b + 1]].sum() != 0]
+    if not affected:          # (a model without any point is not being fitted at all)
+        return False
+    world, rank = 1, 0
     if group is not None:
         import torch.distributed as dist
 
-        world = dist.get_world_size(group)
-    if not affected:
-        return False
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = X_dev.device
+    D = X_dev.shape[1]
     mask = torch.zeros(nbins, dtype=torch.bool, device=dev)
     mask[torch.tensor(affected, device=dev)] = True
     sel = mask[bins_dev.long()]
     if flags_dev is not None:
         sel &= flags_dev == 0
-    idx = torch.nonzero(sel).squeeze(1).to(torch.int32)
-    d2 = ops.point_center_dist2(X_dev, idx, labels, centers_dev).cpu().numpy()
-    idx_h = idx.cpu().numpy()
-    bin_h = bins_dev[idx.long()].cpu().numpy()
-    changed = False
+    idx = torch.nonzero(sel).squeeze(1).to(torch.int32)                          # (2)
+    d2_dev = ops.point_center_dist2(X_dev, idx, labels, centers_dev)
+    packed = torch.stack([d2_dev, bins_dev[idx.long()].to(torch.float64)]).cpu().numpy()   # (3)
+    d2, bin_h = packed[0], packed[1].astype(np.int64)
+    # slots: one per empty cluster, grouped by bin; every rank sees the same sums, hence the same slots
+    slot_bin, slot_new, local_pos, local_d2 = [], [], [], []
     for b in affected:
         lo, hi = int(offs[b]), int(offs[b + 1])
         empty = lo + np.flatnonzero(sw[lo:hi] == 0)
         rows = np.flatnonzero(bin_h == b)                 # ascending point index = the row order sklearn sees
         dist2 = d2[rows]
-        n_empty = int(empty.size)
-        take = min(n_empty, len(dist2))
+        take = min(len(empty), len(dist2))
         far = np.argpartition(dist2, -take)[:-take - 1:-1] if take else np.zeros(0, dtype=np.int64)
-        pts = torch.from_numpy(idx_h[rows[far]].astype(np.int64)).to(dev)
-        xs = X_dev[pts].cpu().numpy() if take else np.zeros((0, X_dev.shape[1]))
-        ws = np.ones(take) if w_dev is None else w_dev[pts].cpu().numpy()
-        ls = labels[pts].cpu().numpy() if take else np.zeros(0, dtype=np.int64)
-        cand = [(float(dist2[f]), xs[i], float(ws[i]), int(ls[i])) for i, f in enumerate(far)]
-        if world > 1:
-            import torch.distributed as dist
+        for k, new_id in enumerate(empty):
+            slot_bin.append(b)
+            slot_new.append(int(new_id))
+            local_pos.append(int(rows[far[k]]) if k < take else -1)
+            local_d2.append(float(dist2[far[k]]) if k < take else -np.inf)
+    E = len(slot_new)
+    pos_t = torch.tensor([max(p, 0) for p in local_pos], dtype=torch.int64, device=dev)
+    pts = idx.long()[pos_t] if idx.numel() else torch.zeros(E, dtype=torch.int64, device=dev)
+    cand = torch.empty((E, D + 3), dtype=torch.float64, device=dev)             # row | weight | old label | distance
+    cand[:, :D] = X_dev[pts]
+    cand[:, D] = 1.0 if w_dev is None else w_dev[pts]
+    cand[:, D + 1] = labels[pts].to(torch.float64)
+    cand[:, D + 2] = torch.tensor(local_d2, dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
 
-            gathered = [None] * world
-            dist.all_gather_object(gathered, cand, group=group)
-            cand = sorted((c for part in gathered for c in part), key=lambda c: -c[0])[:n_empty]
-        for new_id, (_, x, wt, old_id) in zip(empty, cand):
-            delta = torch.from_numpy(x * wt).to(dev)
-            sum_wx[old_id] -= delta
-            sum_wx[new_id] = delta
-            sum_w[new_id] = wt
-            sum_w[old_id] -= wt
-            changed = True
-    return changed
+        parts = [torch.empty((E, D + 3), dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(parts, cand.contiguous(), group=group)
+        cand = torch.cat(parts, dim=0)
+    meta = cand[:, D:].cpu().numpy()                                             # (4)  [world*E, 3]
+    # winners per bin: the n_empty largest distances among all ranks' candidates of that bin (rank order breaks ties)
+    slot_bin = np.asarray(slot_bin)
+    win_rows, win_new = [], []
+    for b in affected:
+        slots = np.flatnonzero(slot_bin == b)
+        rows_b = np.concatenate([r * E + slots for r in range(world)])
+        d_b = meta[rows_b, 2]
+        order = np.argsort(-d_b, kind="stable")[: len(slots)]
+        for k, o in enumerate(order):
+            if np.isfinite(d_b[o]):
+                win_rows.append(int(rows_b[o]))
+                win_new.append(slot_new[slots[k]])
+    if not win_rows:
+        return False
+    wr = torch.tensor(win_rows, dtype=torch.int64, device=dev)
+    new_ids = torch.tensor(win_new, dtype=torch.int64, device=dev)
+    wts = cand[wr, D]
+    delta = cand[wr, :D] * wts[:, None]
+    old_h = meta[win_rows, 1].astype(np.int64)
+    old_ids = torch.from_numpy(old_h).to(dev)
+    if len(set(old_h.tolist())) == len(old_h):
+        sum_wx.index_add_(0, old_ids, -delta)
+        sum_w.index_add_(0, old_ids, -wts)
+    else:                       # one old cluster loses several points: subtract in sklearn's order
+        for k in range(len(old_h)):
+            sum_wx[old_ids[k]] -= delta[k]
+            sum_w[old_ids[k]] -= wts[k]
+    sum_wx[new_ids] = delta
+    sum_w[new_ids] = wts
+    return True
