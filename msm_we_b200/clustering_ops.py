@@ -134,24 +134,42 @@ def _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bins_dev, flags_
     sel = mask[bins_dev.long()]
     if flags_dev is not None:
         sel &= flags_dev == 0
-    idx = torch.nonzero(sel).squeeze(1).to(torch.int32)                          # (2)
+    idx = torch.nonzero(sel).squeeze(1).to(torch.int32)                          # (2)  ascending point index
     d2_dev = ops.point_center_dist2(X_dev, idx, labels, centers_dev)
-    packed = torch.stack([d2_dev, bins_dev[idx.long()].to(torch.float64)]).cpu().numpy()   # (3)
-    d2, bin_h = packed[0], packed[1].astype(np.int64)
-    # slots: one per empty cluster, grouped by bin; every rank sees the same sums, hence the same slots
+    bins_aff = bins_dev[idx.long()].to(torch.int64)
+    # group the listed points by WE bin (stable: ascending point index inside a bin, the row order sklearn sees) and take
+    # every bin's largest distance on the device; only bins that lost SEVERAL clusters need their whole distance list
+    members, seg_start = ops.group_by_label(bins_aff, nbins)
+    _, _, _, vmax = ops.label_stats(d2_dev, members, seg_start, nbins)
+    at_max = torch.nonzero(d2_dev == vmax[bins_aff]).squeeze(1)                  # (3)  ~ one position per affected bin
+    at_max_h = at_max.cpu().numpy()
+    at_max_bin = bins_aff[at_max].cpu().numpy()
+    seg_h = seg_start.cpu().numpy()
+    d2_at_max = d2_dev[at_max].cpu().numpy()
     slot_bin, slot_new, local_pos, local_d2 = [], [], [], []
     for b in affected:
         lo, hi = int(offs[b]), int(offs[b + 1])
         empty = lo + np.flatnonzero(sw[lo:hi] == 0)
-        rows = np.flatnonzero(bin_h == b)                 # ascending point index = the row order sklearn sees
-        dist2 = d2[rows]
-        take = min(len(empty), len(dist2))
-        far = np.argpartition(dist2, -take)[:-take - 1:-1] if take else np.zeros(0, dtype=np.int64)
+        n_here = int(seg_h[b + 1] - seg_h[b])
+        if len(empty) == 1 or n_here == 0:
+            hit = np.flatnonzero(at_max_bin == b)
+            far_pos = [int(at_max_h[hit[0]])] if len(hit) and n_here else []
+            far_d2 = [float(d2_at_max[hit[0]])] if far_pos else []
+        else:
+            # several empty clusters in one model: which far point goes to which cluster follows numpy's argpartition
+            # order in sklearn, so the same call runs on this bin's full distance list (rare; one small transfer)
+            rows_t = members[int(seg_h[b]):int(seg_h[b + 1])].long()
+            dist2 = d2_dev[rows_t].cpu().numpy()
+            rows = rows_t.cpu().numpy()
+            take = min(len(empty), len(dist2))
+            far = np.argpartition(dist2, -take)[:-take - 1:-1]
+            far_pos = [int(rows[f]) for f in far]
+            far_d2 = [float(dist2[f]) for f in far]
         for k, new_id in enumerate(empty):
             slot_bin.append(b)
             slot_new.append(int(new_id))
-            local_pos.append(int(rows[far[k]]) if k < take else -1)
-            local_d2.append(float(dist2[far[k]]) if k < take else -np.inf)
+            local_pos.append(far_pos[k] if k < len(far_pos) else -1)
+            local_d2.append(far_d2[k] if k < len(far_pos) else -np.inf)
     E = len(slot_new)
     pos_t = torch.tensor([max(p, 0) for p in local_pos], dtype=torch.int64, device=dev)
     pts = idx.long()[pos_t] if idx.numel() else torch.zeros(E, dtype=torch.int64, device=dev)

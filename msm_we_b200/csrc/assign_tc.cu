@@ -571,10 +571,7 @@ static constexpr int TC2_MAX_B_STAGES = 4;
 static constexpr int TC2_CONV_WARPS = 8;                   // 2 per TMEM lane quarter: each converts 16 of the chunk's 32 elements
                                                            // (16 warps x 8 elements measured slower: 0.999 vs 0.903 ms, cfg5 slice)
 static constexpr int TC2_KSUB = TC_KC / (TC2_CONV_WARPS / 4);   // elements per thread and chunk
-static constexpr int TC2_PROD_WARP0 = 6;                   // 4 staging warps (cp.async gathers only)
-static constexpr int TC2_PROD_WARPS = 4;
-static constexpr int TC2_CONV_WARP0 = TC2_PROD_WARP0 + TC2_PROD_WARPS;   // 10: (warp & 3) = TMEM lane quarter
-static constexpr int TC2_THREADS = (TC2_CONV_WARP0 + TC2_CONV_WARPS) * 32;
+static constexpr int TC2_THREADS = (TC_CONV_WARP0 + TC2_CONV_WARPS) * 32;
 
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -601,7 +598,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
 
 struct Tc2Params {
     TcParams t;
-    int ablate;       // tuning only: bit 0 = issue no MMAs, bit 1 = skip the fp64 -> TF32 conversion arithmetic
+    int ablate;       // tuning only: bit 0 = issue no MMAs, bit 1 = skip the fp64 -> TF32 conversion arithmetic, bit 2 = no centre-block loads
     int n_a;          // A stages in tensor memory
     int n_b;          // centre-block stages in shared memory
     uint32_t a_col0;  // first TMEM column of the A stages
@@ -629,7 +626,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Par
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < n_raw; ++s) {
-            mbar_init(&raw_full[s], TC2_PROD_WARPS * 32);     // every staging thread: cp.async ... arrive.noinc
+            mbar_init(&raw_full[s], TC2_CONV_WARPS * 32);     // every staging thread: cp.async ... arrive.noinc
             mbar_init(&raw_empty[s], TC2_CONV_WARPS);         // one lane per converter warp
         }
         for (int s = 0; s < n_a; ++s) {
@@ -729,8 +726,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Par
                         timed_wait(&b_empty[bs], bph ^ 1u, w0, prof);
                         unsigned char* dst = b_base + (size_t)bs * b_bytes;
                         const unsigned char* src = q.bprep + ((size_t)(w.bin * ncb + cb) * nch + kc) * b_bytes;
-                        mbar_expect_tx(&b_full[bs], b_bytes);
-                        bulk_copy_g2s(dst, src, b_bytes, &b_full[bs]);
+                        if (qq.ablate & 4) {
+                            mbar_arrive(&b_full[bs]);          // measurement only: no centre-block traffic
+                        } else {
+                            mbar_expect_tx(&b_full[bs], b_bytes);
+                            bulk_copy_g2s(dst, src, b_bytes, &b_full[bs]);
+                        }
                         if (++bs == n_b) { bs = 0; bph ^= 1u; }
                     }
                 w.next_tile(tt, my_tiles);
@@ -797,79 +798,76 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Par
             }
             w.next_tile(tt, my_tiles);
         }
-    } else if (warp >= TC2_PROD_WARP0 && warp < TC2_PROD_WARP0 + TC2_PROD_WARPS) {
-        // =========================== staging producers ===========================
-        // Only copies: the cp.async (LDGSTS, zero-filling) gathers of the chunk's 128 row pieces into the fp64 ring, as far
-        // ahead as the ring allows.  Kept apart from the converters so that a converter waiting for a TMEM stage never
-        // delays the next HBM requests (with the copies issued from the converter loop the bare data path -- no MMAs, no
-        // conversion arithmetic -- topped out at 70 % of the HBM rate a pure gather ring reaches).
-        const int pw = warp - TC2_PROD_WARP0;              // 0..TC2_PROD_WARPS-1
-        constexpr int CR = TC_TP / TC2_PROD_WARPS;         // rows each producer warp copies (32)
+    } else if (warp >= TC_CONV_WARP0) {
+        // =========================== staging + conversion warps ===========================
+        // (a) every warp issues the cp.async copies of 16 point rows of the chunk n_raw-1 steps ahead (fire and forget,
+        //     completion lands on raw_full); (b) converts ITS rows of the current chunk: thread = one point row (the
+        //     TMEM lane it may write), 16 consecutive elements of the 32-element chunk.
+        const int cwp = warp - TC_CONV_WARP0;              // 0..TC2_CONV_WARPS-1
+        const int quarter = warp & 3;                      // TMEM lane quarter this warp can access
+        const int khalf = cwp >> 2;                        // which TC2_KSUB elements of the chunk
+        const int row = quarter * 32 + lane;
+        constexpr int CR = TC_TP / TC2_CONV_WARPS;         // rows each warp copies
         constexpr int SEGS = TC_KC / VEC;
         constexpr int RPI = 32 / SEGS;
         constexpr int XQ = CR / RPI;
         const int seg = lane % SEGS, crs = lane / SEGS;
         const int kcol0 = seg * VEC;
-        TileWalk<TC_TP> iw{0, 0, 0, 0, 0, 0, 0, 0};       // step whose copies are being issued
-        iw.load(tt, my_tiles);
-        TileWalk<TC_TP> nw = iw;                           // tile whose point indices are being prefetched
-        int64_t xoff[XQ];                                  // row offsets (elements) of this thread's rows, -1 = past the tile
+        TileWalk<TC_TP> cw{0, 0, 0, 0, 0, 0, 0, 0};       // step being converted
+        cw.load(tt, my_tiles);
+        TileWalk<TC_TP> iw = cw;                           // step whose copies are being issued
+        TileWalk<TC_TP> nw = cw;                           // tile whose point indices are being prefetched
+        const double* xsrc[XQ];
         int32_t pidx_next[XQ];
         auto fetch = [&](const TileWalk<TC_TP>& t) {
 #pragma unroll
             for (int k = 0; k < XQ; ++k) {
-                const int r = pw * CR + k * RPI + crs;
+                const int r = cwp * CR + k * RPI + crs;
                 pidx_next[k] = (r < t.pcount) ? p.perm[t.pstart + r] : -1;
             }
         };
-        auto set_xoff = [&]() {
+        auto set_xsrc = [&]() {
 #pragma unroll
-            for (int k = 0; k < XQ; ++k) xoff[k] = (pidx_next[k] >= 0) ? (int64_t)pidx_next[k] * p.ldx + kcol0 : -1;
+            for (int k = 0; k < XQ; ++k)
+                xsrc[k] = (pidx_next[k] >= 0) ? p.X + (int64_t)pidx_next[k] * p.ldx + kcol0 : nullptr;
         };
         fetch(iw);
-        set_xoff();
+        set_xsrc();
         nw.next_tile(tt, my_tiles);
         fetch(nw);
         const int64_t total_steps = (int64_t)my_tiles * ncb * nch;
         int is = 0;
         uint32_t iphase = 0;
-        for (int64_t step = 0; step < total_steps; ++step) {
-            timed_wait(&raw_empty[is], iphase ^ 1u, w0, prof);
+        int64_t issued = 0;
+        auto issue_one = [&]() {
+            timed_wait(&raw_empty[is], iphase ^ 1u, w2, prof);
             double* st = reinterpret_cast<double*>(raw_base + (size_t)is * TC_RAW_BYTES);
             const int k0 = iw.kc * TC_KC;
             int vbytes = (p.D - k0 - kcol0) * 8;
             vbytes = vbytes < 0 ? 0 : (vbytes > VEC * 8 ? VEC * 8 : vbytes);
-            double* dst = st + (pw * CR + crs) * TC_RAW_LD + kcol0;
+            double* dst = st + (cwp * CR + crs) * TC_RAW_LD + kcol0;
 #pragma unroll
             for (int k = 0; k < XQ; ++k)   // (a zero-size copy still gets an in-range source address)
-                if (xoff[k] >= 0) cp_async_zfill<VEC>(dst + k * RPI * TC_RAW_LD, vbytes ? p.X + xoff[k] + k0 : p.X, vbytes);
-            if (pw == 0 && lane < 16)   // the bin-mean chunk rides along (zero padded past D: always 16 x 16 B)
+                if (xsrc[k]) cp_async_zfill<VEC>(dst + k * RPI * TC_RAW_LD, vbytes ? xsrc[k] + k0 : p.X, vbytes);
+            if (cwp == 0 && lane < 16)   // the bin-mean chunk rides along (zero padded past D: always 16 x 16 B)
                 cp_async_zfill<2>(st + TC_TP * TC_RAW_LD + 2 * lane, q.mean + (size_t)iw.bin * q.d_pad + k0 + 2 * lane, 16);
             cp_async_arrive_noinc(&raw_full[is]);
             if (++is == n_raw) { is = 0; iphase ^= 1u; }
+            ++issued;
             if (iw.advance(tt, ncb, nch, my_tiles)) {
-                set_xoff();
+                set_xsrc();
                 nw.next_tile(tt, my_tiles);
                 fetch(nw);
             }
-        }
-        asm volatile("cp.async.wait_all;" ::: "memory");
-    } else if (warp >= TC2_CONV_WARP0) {
-        // =========================== conversion warps ===========================
-        // thread = one point row (the TMEM lane it may write), TC2_KSUB consecutive elements of the 32-element chunk:
-        // fp64 staging ring -> centred TF32 hi / lo -> tensor memory.
-        const int cwp = warp - TC2_CONV_WARP0;             // 0..TC2_CONV_WARPS-1
-        const int quarter = warp & 3;                      // TMEM lane quarter this warp can access
-        const int khalf = cwp >> 2;                        // which TC2_KSUB elements of the chunk
-        const int row = quarter * 32 + lane;
-        TileWalk<TC_TP> cw{0, 0, 0, 0, 0, 0, 0, 0};       // step being converted
-        cw.load(tt, my_tiles);
-        const int64_t total_steps = (int64_t)my_tiles * ncb * nch;
+        };
+        while (issued < total_steps && issued < n_raw - 1) issue_one();
+
         int rs = 0, as = 0;
         uint32_t rphase = 0, aphase = 0, xph0 = 0, xph1 = 0;
         const uint32_t a_lane = (uint32_t)(quarter * 32) << 16;
         float xc = 0.f;
         for (int64_t step = 0; step < total_steps; ++step) {
+            if (issued < total_steps) issue_one();
             timed_wait(&raw_full[rs], rphase, w0, prof);
             const double* st = reinterpret_cast<const double*>(raw_base + (size_t)rs * TC_RAW_BYTES);
             const double* src = st + row * TC_RAW_LD + TC2_KSUB * khalf;
@@ -878,20 +876,17 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Par
             if (qq.ablate & 2) {
 #pragma unroll
                 for (int e = 0; e < TC2_KSUB; ++e) hi[e] = lo[e] = 0.f;
-            } else {
-                double2 xv[TC2_KSUB / 2];
+            } else
 #pragma unroll
-                for (int e = 0; e < TC2_KSUB / 2; ++e) xv[e] = *reinterpret_cast<const double2*>(src + 2 * e);
-#pragma unroll
-                for (int e = 0; e < TC2_KSUB / 2; ++e) {
-                    const double2 mv = *reinterpret_cast<const double2*>(mup + 2 * e);
-                    const float x0 = (float)(xv[e].x - mv.x), x1 = (float)(xv[e].y - mv.y);
-                    hi[2 * e] = tf32_rna(x0);
-                    hi[2 * e + 1] = tf32_rna(x1);
-                    lo[2 * e] = x0 - hi[2 * e];
-                    lo[2 * e + 1] = x1 - hi[2 * e + 1];
-                    if (cw.cb == 0) xc = fmaf(x0, x0, fmaf(x1, x1, xc));
-                }
+            for (int e = 0; e < TC2_KSUB / 2; ++e) {
+                const double2 xv = *reinterpret_cast<const double2*>(src + 2 * e);
+                const double2 mv = *reinterpret_cast<const double2*>(mup + 2 * e);
+                const float x0 = (float)(xv.x - mv.x), x1 = (float)(xv.y - mv.y);
+                hi[2 * e] = tf32_rna(x0);
+                hi[2 * e + 1] = tf32_rna(x1);
+                lo[2 * e] = x0 - hi[2 * e];
+                lo[2 * e + 1] = x1 - hi[2 * e + 1];
+                if (cw.cb == 0) xc = fmaf(x0, x0, fmaf(x1, x1, xc));
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&raw_empty[rs]);        // the staged fp64 chunk is in registers
@@ -923,10 +918,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Par
             }
             cw.advance(tt, ncb, nch, my_tiles);
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
     }
 
-    if (prof && lane == 0 && (warp == TC_MMA_WARP || warp == TC_CENTRE_WARP || warp == TC_EPI_WARP0 || warp == TC2_PROD_WARP0 || warp == TC2_CONV_WARP0)) {
-        const int role = warp == TC_MMA_WARP ? 0 : warp == TC_CENTRE_WARP ? 1 : warp == TC_EPI_WARP0 ? 2 : warp == TC2_PROD_WARP0 ? 3 : 4;
+    if (prof && lane == 0 && (warp == TC_MMA_WARP || warp == TC_CENTRE_WARP || warp == TC_EPI_WARP0 || warp == TC_CONV_WARP0)) {
+        const int role = warp == TC_MMA_WARP ? 0 : warp == TC_CENTRE_WARP ? 1 : warp == TC_EPI_WARP0 ? 2 : 4;
         atomicAdd(q.dbg_prof + role * 4 + 0, (unsigned long long)(clock64() - t_begin));
         atomicAdd(q.dbg_prof + role * 4 + 1, (unsigned long long)w0);
         atomicAdd(q.dbg_prof + role * 4 + 2, (unsigned long long)w1);
