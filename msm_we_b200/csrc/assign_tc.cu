@@ -604,7 +604,8 @@ struct Tc2Params {
     uint32_t a_col0;  // first TMEM column of the A stages
 };
 
-template <int VEC>
+// FULLK: D is a multiple of the k-chunk, so no copy needs a zero-filled tail; PROF: per-role wait-cycle counters.
+template <int VEC, bool FULLK, bool PROF>
 __global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Params qq) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const TcParams& q = qq.t;
@@ -671,7 +672,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Par
     const int32_t n_tiles = tt.tile_prefix[p.nbins];
     const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int ncb = p.ncb, nch = p.nch;
-    const bool prof = q.dbg_prof != nullptr;
+    constexpr bool prof = PROF;
     long long w0 = 0, w1 = 0, w2 = 0;
     const long long t_begin = clock64();
 
@@ -800,9 +801,14 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Par
         }
     } else if (warp >= TC_CONV_WARP0) {
         // =========================== staging + conversion warps ===========================
-        // (a) every warp issues the cp.async copies of 16 point rows of the chunk n_raw-1 steps ahead (fire and forget,
-        //     completion lands on raw_full); (b) converts ITS rows of the current chunk: thread = one point row (the
-        //     TMEM lane it may write), 16 consecutive elements of the 32-element chunk.
+        // Each of the 8 warps (a) issues the cp.async (LDGSTS) copies of 16 point rows of the chunk n_raw-1 steps ahead
+        // into the fp64 staging ring -- fire and forget, completion lands on raw_full -- and (b) converts ITS rows of
+        // the current chunk: thread = one point row (the TMEM lane it may write), 16 consecutive elements.
+        // These warps are ISSUE-bound (ncu: nothing else on the SM is above 45 %; the first version of this loop spent
+        // ~550 instructions per step and warp, 170 of them on predicates / selects / 64-bit address pairs around the 8
+        // copies), so the loop is kept lean: row pointers are formed once per tile, rows past the end of a tile read row
+        // 0 instead of being predicated off (their products are never looked at), full chunks use the plain copy, and
+        // the walk over (tile, centre block, k-chunk) is three counters.
         const int cwp = warp - TC_CONV_WARP0;              // 0..TC2_CONV_WARPS-1
         const int quarter = warp & 3;                      // TMEM lane quarter this warp can access
         const int khalf = cwp >> 2;                        // which TC2_KSUB elements of the chunk
@@ -813,86 +819,108 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Par
         constexpr int XQ = CR / RPI;
         const int seg = lane % SEGS, crs = lane / SEGS;
         const int kcol0 = seg * VEC;
-        TileWalk<TC_TP> cw{0, 0, 0, 0, 0, 0, 0, 0};       // step being converted
-        cw.load(tt, my_tiles);
-        TileWalk<TC_TP> iw = cw;                           // step whose copies are being issued
-        TileWalk<TC_TP> nw = cw;                           // tile whose point indices are being prefetched
-        const double* xsrc[XQ];
+        TileWalk<TC_TP> iw{0, 0, 0, 0, 0, 0, 0, 0};       // tile whose copies are being issued
+        iw.load(tt, my_tiles);
+        TileWalk<TC_TP> nw = iw;                           // tile whose point indices are being prefetched
+        const double* xrow[XQ];                            // k-chunk 0 of this thread's rows of the tile being issued
         int32_t pidx_next[XQ];
         auto fetch = [&](const TileWalk<TC_TP>& t) {
 #pragma unroll
             for (int k = 0; k < XQ; ++k) {
                 const int r = cwp * CR + k * RPI + crs;
-                pidx_next[k] = (r < t.pcount) ? p.perm[t.pstart + r] : -1;
+                pidx_next[k] = (r < t.pcount) ? p.perm[t.pstart + r] : 0;
             }
         };
-        auto set_xsrc = [&]() {
+        auto set_rows = [&]() {
 #pragma unroll
-            for (int k = 0; k < XQ; ++k)
-                xsrc[k] = (pidx_next[k] >= 0) ? p.X + (int64_t)pidx_next[k] * p.ldx + kcol0 : nullptr;
+            for (int k = 0; k < XQ; ++k) xrow[k] = p.X + (int64_t)pidx_next[k] * p.ldx + kcol0;
         };
         fetch(iw);
-        set_xsrc();
+        set_rows();
         nw.next_tile(tt, my_tiles);
         fetch(nw);
         const int64_t total_steps = (int64_t)my_tiles * ncb * nch;
-        int is = 0;
+        const uint32_t raw32 = smem_u32(raw_base) + (uint32_t)(((cwp * CR + crs) * TC_RAW_LD + kcol0) * 8);
+        const uint32_t mean32 = smem_u32(raw_base) + (uint32_t)((TC_TP * TC_RAW_LD + 2 * lane) * 8);
+        const double* mean_src = q.mean + (size_t)iw.bin * q.d_pad + 2 * lane;
+        int is = 0, ikc = 0, icb = 0;
         uint32_t iphase = 0;
         int64_t issued = 0;
         auto issue_one = [&]() {
             timed_wait(&raw_empty[is], iphase ^ 1u, w2, prof);
-            double* st = reinterpret_cast<double*>(raw_base + (size_t)is * TC_RAW_BYTES);
-            const int k0 = iw.kc * TC_KC;
-            int vbytes = (p.D - k0 - kcol0) * 8;
-            vbytes = vbytes < 0 ? 0 : (vbytes > VEC * 8 ? VEC * 8 : vbytes);
-            double* dst = st + (cwp * CR + crs) * TC_RAW_LD + kcol0;
+            const uint32_t dst = raw32 + (uint32_t)is * (uint32_t)TC_RAW_BYTES;
+            const int k0 = ikc * TC_KC;
+            if (FULLK) {
 #pragma unroll
-            for (int k = 0; k < XQ; ++k)   // (a zero-size copy still gets an in-range source address)
-                if (xsrc[k]) cp_async_zfill<VEC>(dst + k * RPI * TC_RAW_LD, vbytes ? xsrc[k] + k0 : p.X, vbytes);
+                for (int k = 0; k < XQ; ++k) {
+                    if (VEC == 2) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(k * RPI * TC_RAW_LD * 8)), "l"(xrow[k] + k0) : "memory");
+                    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (uint32_t)(k * RPI * TC_RAW_LD * 8)), "l"(xrow[k] + k0) : "memory");
+                }
+            } else {
+                int vbytes = (p.D - k0 - kcol0) * 8;
+                vbytes = vbytes < 0 ? 0 : (vbytes > VEC * 8 ? VEC * 8 : vbytes);
+                const int koff = vbytes ? k0 : 0;          // (a zero-size copy still gets an in-range source address)
+#pragma unroll
+                for (int k = 0; k < XQ; ++k) {
+                    if (VEC == 2) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)(k * RPI * TC_RAW_LD * 8)), "l"(xrow[k] + koff), "r"(vbytes) : "memory");
+                    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + (uint32_t)(k * RPI * TC_RAW_LD * 8)), "l"(xrow[k] + koff), "r"(vbytes) : "memory");
+                }
+            }
             if (cwp == 0 && lane < 16)   // the bin-mean chunk rides along (zero padded past D: always 16 x 16 B)
-                cp_async_zfill<2>(st + TC_TP * TC_RAW_LD + 2 * lane, q.mean + (size_t)iw.bin * q.d_pad + k0 + 2 * lane, 16);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(mean32 + (uint32_t)is * (uint32_t)TC_RAW_BYTES), "l"(mean_src + k0) : "memory");
             cp_async_arrive_noinc(&raw_full[is]);
             if (++is == n_raw) { is = 0; iphase ^= 1u; }
             ++issued;
-            if (iw.advance(tt, ncb, nch, my_tiles)) {
-                set_xsrc();
-                nw.next_tile(tt, my_tiles);
-                fetch(nw);
+            if (++ikc == nch) {
+                ikc = 0;
+                if (++icb == ncb) {                        // next tile: its indices were prefetched a tile ago
+                    icb = 0;
+                    iw.next_tile(tt, my_tiles);
+                    set_rows();
+                    mean_src = q.mean + (size_t)iw.bin * q.d_pad + 2 * lane;
+                    nw.next_tile(tt, my_tiles);
+                    fetch(nw);
+                }
             }
         };
         while (issued < total_steps && issued < n_raw - 1) issue_one();
 
-        int rs = 0, as = 0;
+        int rs = 0, as = 0, ckc = 0, ccb = 0, cti = 0;
         uint32_t rphase = 0, aphase = 0, xph0 = 0, xph1 = 0;
-        const uint32_t a_lane = (uint32_t)(quarter * 32) << 16;
+        const uint32_t ta0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + qq.a_col0 + (uint32_t)(TC2_KSUB * khalf);
+        const uint32_t src32 = smem_u32(raw_base) + (uint32_t)((row * TC_RAW_LD + TC2_KSUB * khalf) * 8);
+        const uint32_t mu32 = smem_u32(raw_base) + (uint32_t)((TC_TP * TC_RAW_LD + TC2_KSUB * khalf) * 8);
         float xc = 0.f;
         for (int64_t step = 0; step < total_steps; ++step) {
             if (issued < total_steps) issue_one();
             timed_wait(&raw_full[rs], rphase, w0, prof);
-            const double* st = reinterpret_cast<const double*>(raw_base + (size_t)rs * TC_RAW_BYTES);
-            const double* src = st + row * TC_RAW_LD + TC2_KSUB * khalf;
-            const double* mup = st + TC_TP * TC_RAW_LD + TC2_KSUB * khalf;
+            const uint32_t so = (uint32_t)rs * (uint32_t)TC_RAW_BYTES;
             float hi[TC2_KSUB], lo[TC2_KSUB];
             if (qq.ablate & 2) {
 #pragma unroll
                 for (int e = 0; e < TC2_KSUB; ++e) hi[e] = lo[e] = 0.f;
-            } else
+            } else {
+                double2 xv[TC2_KSUB / 2];
 #pragma unroll
-            for (int e = 0; e < TC2_KSUB / 2; ++e) {
-                const double2 xv = *reinterpret_cast<const double2*>(src + 2 * e);
-                const double2 mv = *reinterpret_cast<const double2*>(mup + 2 * e);
-                const float x0 = (float)(xv.x - mv.x), x1 = (float)(xv.y - mv.y);
-                hi[2 * e] = tf32_rna(x0);
-                hi[2 * e + 1] = tf32_rna(x1);
-                lo[2 * e] = x0 - hi[2 * e];
-                lo[2 * e + 1] = x1 - hi[2 * e + 1];
-                if (cw.cb == 0) xc = fmaf(x0, x0, fmaf(x1, x1, xc));
+                for (int e = 0; e < TC2_KSUB / 2; ++e)
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xv[e].x), "=d"(xv[e].y) : "r"(src32 + so + 16u * e));
+#pragma unroll
+                for (int e = 0; e < TC2_KSUB / 2; ++e) {
+                    double2 mv;
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(mv.x), "=d"(mv.y) : "r"(mu32 + so + 16u * e));
+                    const float x0 = (float)(xv[e].x - mv.x), x1 = (float)(xv[e].y - mv.y);
+                    hi[2 * e] = tf32_rna(x0);
+                    hi[2 * e + 1] = tf32_rna(x1);
+                    lo[2 * e] = x0 - hi[2 * e];
+                    lo[2 * e + 1] = x1 - hi[2 * e + 1];
+                    if (ccb == 0) xc = fmaf(x0, x0, fmaf(x1, x1, xc));
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&raw_empty[rs]);        // the staged fp64 chunk is in registers
             timed_wait(&a_empty[as], aphase ^ 1u, w1, prof);   // the MMAs that read this TMEM stage have completed
             tc_fence_after();
-            const uint32_t ta = tmem_base + a_lane + qq.a_col0 + (uint32_t)(as * TC2_A_STAGE_COLS + TC2_KSUB * khalf);
+            const uint32_t ta = ta0 + (uint32_t)(as * TC2_A_STAGE_COLS);
             if (TC2_KSUB == 8) {
                 tmem_st8(ta, hi);
                 tmem_st8(ta + TC_KC, lo);
@@ -906,17 +934,21 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Par
             if (lane == 0) mbar_arrive(&a_full[as]);
             if (++rs == n_raw) { rs = 0; rphase ^= 1u; }
             if (++as == n_a) { as = 0; aphase ^= 1u; }
-            if (cw.kc == nch - 1 && cw.cb == ncb - 1) {
-                // partial centred ||x'||^2 of this thread's row -> epilogue (fp32 sums of fp32 roundings, inflated a little)
-                const int xbuf = cw.ti & 1;
-                mbar_wait(&xn_empty[xbuf], (xbuf ? xph1 : xph0) ^ 1u);
-                if (xbuf) xph1 ^= 1u; else xph0 ^= 1u;
-                s_xn[xbuf][khalf][row] = xc * 1.0001f;
-                xc = 0.f;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&xn_full[xbuf]);
+            if (++ckc == nch) {
+                ckc = 0;
+                if (++ccb == ncb) {
+                    // partial centred ||x'||^2 of this thread's row -> epilogue (fp32 sums of fp32 roundings, inflated a little)
+                    ccb = 0;
+                    const int xbuf = cti & 1;
+                    mbar_wait(&xn_empty[xbuf], (xbuf ? xph1 : xph0) ^ 1u);
+                    if (xbuf) xph1 ^= 1u; else xph0 ^= 1u;
+                    s_xn[xbuf][khalf][row] = xc * 1.0001f;
+                    xc = 0.f;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&xn_full[xbuf]);
+                    ++cti;
+                }
             }
-            cw.advance(tt, ncb, nch, my_tiles);
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
     }
@@ -1059,25 +1091,28 @@ int launch_assign_tc(const AssignParams& p_in, int32_t max_k, int64_t N, void* p
         q2.n_b = n_b;
         q2.a_col0 = (uint32_t)(2 * L.n_pad);
         const size_t smem = b_bytes * n_b + (size_t)TC_RAW_BYTES * n_raw + table_bytes;
-        if (vec2) {
-            static size_t configured_dev[MWE_MAX_DEVICES] = {};   // the attribute is per device, not per process
-            size_t& configured = configured_dev[device_slot()];
-            if (configured < smem) {
-                MWE_CHECK_CUDA(cudaFuncSetAttribute(assign_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                configured = smem;
-            }
-            if (ev0) MWE_CHECK_CUDA(cudaEventRecord(ev0, stream));
-            assign_tc2_kernel<2><<<(unsigned)grid, TC2_THREADS, smem, stream>>>(q2);
-        } else {
-            static size_t configured_dev[MWE_MAX_DEVICES] = {};
-            size_t& configured = configured_dev[device_slot()];
-            if (configured < smem) {
-                MWE_CHECK_CUDA(cudaFuncSetAttribute(assign_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                configured = smem;
-            }
-            if (ev0) MWE_CHECK_CUDA(cudaEventRecord(ev0, stream));
-            assign_tc2_kernel<1><<<(unsigned)grid, TC2_THREADS, smem, stream>>>(q2);
+        const bool fullk = (p_in.D % TC_KC) == 0;
+        const bool profiled = q.dbg_prof != nullptr;
+        void (*kern)(const Tc2Params) = nullptr;
+        const int variant = (vec2 ? 4 : 0) | (fullk ? 2 : 0) | (profiled ? 1 : 0);
+        switch (variant) {
+            case 7: kern = assign_tc2_kernel<2, true, true>; break;
+            case 6: kern = assign_tc2_kernel<2, true, false>; break;
+            case 5: kern = assign_tc2_kernel<2, false, true>; break;
+            case 4: kern = assign_tc2_kernel<2, false, false>; break;
+            case 3: kern = assign_tc2_kernel<1, true, true>; break;
+            case 2: kern = assign_tc2_kernel<1, true, false>; break;
+            case 1: kern = assign_tc2_kernel<1, false, true>; break;
+            default: kern = assign_tc2_kernel<1, false, false>; break;
         }
+        static size_t configured_dev[MWE_MAX_DEVICES][8] = {};   // the attribute is per device (and per instantiation)
+        size_t& configured = configured_dev[device_slot()][variant];
+        if (configured < smem) {
+            MWE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        if (ev0) MWE_CHECK_CUDA(cudaEventRecord(ev0, stream));
+        kern<<<(unsigned)grid, TC2_THREADS, smem, stream>>>(q2);
         MWE_CHECK_LAUNCH();
         if (ev1) MWE_CHECK_CUDA(cudaEventRecord(ev1, stream));
         return MWE_OK;
