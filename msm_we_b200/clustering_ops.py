@@ -113,6 +113,16 @@ def _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bins_dev, flags_
     the host picks each bin's farthest points with the numpy call sklearn uses; (4) the winners' old labels.  The rows
     themselves never leave the device: they are gathered, (with a process group: all-gathered as one small tensor, the
     global winners picked from every rank's candidates,) and subtracted / assigned by indexed device updates."""
+    import os, time
+    dbg = os.environ.get("MWE_RELOC_DEBUG")
+    marks = []
+
+    def mark(tag):
+        if dbg:
+            torch.cuda.synchronize() if X_dev.is_cuda else None
+            marks.append((tag, time.perf_counter()))
+
+    mark("start")
     sw = sum_w.cpu().numpy()                                                     # (1)
     if (sw != 0).all():
         return False
@@ -134,42 +144,58 @@ def _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bins_dev, flags_
     sel = mask[bins_dev.long()]
     if flags_dev is not None:
         sel &= flags_dev == 0
+    mark("host-affected")
     idx = torch.nonzero(sel).squeeze(1).to(torch.int32)                          # (2)  ascending point index
+    mark("nonzero")
     d2_dev = ops.point_center_dist2(X_dev, idx, labels, centers_dev)
+    mark("dist2")
     bins_aff = bins_dev[idx.long()].to(torch.int64)
     # group the listed points by WE bin (stable: ascending point index inside a bin, the row order sklearn sees) and take
     # every bin's largest distance on the device; only bins that lost SEVERAL clusters need their whole distance list
     members, seg_start = ops.group_by_label(bins_aff, nbins)
     _, _, _, vmax = ops.label_stats(d2_dev, members, seg_start, nbins)
+    mark("group+stats")
     at_max = torch.nonzero(d2_dev == vmax[bins_aff]).squeeze(1)                  # (3)  ~ one position per affected bin
     at_max_h = at_max.cpu().numpy()
     at_max_bin = bins_aff[at_max].cpu().numpy()
     seg_h = seg_start.cpu().numpy()
     d2_at_max = d2_dev[at_max].cpu().numpy()
+    mark("argmax-d2h")
     slot_bin, slot_new, local_pos, local_d2 = [], [], [], []
+    # bins that lost SEVERAL clusters: which far point goes to which cluster follows numpy's argpartition order in
+    # sklearn, so the same call runs on each such bin's full distance list -- fetched for all of them in one transfer
+    empties = {b: int(offs[b]) + np.flatnonzero(sw[int(offs[b]):int(offs[b + 1])] == 0) for b in affected}
+    multi = [b for b in affected if len(empties[b]) > 1 and seg_h[b + 1] > seg_h[b]]
+    multi_rows, multi_d2, multi_off = None, None, {}
+    if multi:
+        pieces, pos = [], 0
+        for b in multi:
+            pieces.append(members[int(seg_h[b]):int(seg_h[b + 1])])
+            multi_off[b] = (pos, pos + int(seg_h[b + 1] - seg_h[b]))
+            pos += int(seg_h[b + 1] - seg_h[b])
+        rows_all = torch.cat(pieces).long()
+        packed = torch.stack([d2_dev[rows_all], rows_all.to(torch.float64)]).cpu().numpy()
+        multi_d2, multi_rows = packed[0], packed[1].astype(np.int64)
     for b in affected:
-        lo, hi = int(offs[b]), int(offs[b + 1])
-        empty = lo + np.flatnonzero(sw[lo:hi] == 0)
+        empty = empties[b]
         n_here = int(seg_h[b + 1] - seg_h[b])
-        if len(empty) == 1 or n_here == 0:
-            hit = np.flatnonzero(at_max_bin == b)
-            far_pos = [int(at_max_h[hit[0]])] if len(hit) and n_here else []
-            far_d2 = [float(d2_at_max[hit[0]])] if far_pos else []
-        else:
-            # several empty clusters in one model: which far point goes to which cluster follows numpy's argpartition
-            # order in sklearn, so the same call runs on this bin's full distance list (rare; one small transfer)
-            rows_t = members[int(seg_h[b]):int(seg_h[b + 1])].long()
-            dist2 = d2_dev[rows_t].cpu().numpy()
-            rows = rows_t.cpu().numpy()
+        if b in multi_off:
+            a, z = multi_off[b]
+            dist2, rows = multi_d2[a:z], multi_rows[a:z]
             take = min(len(empty), len(dist2))
             far = np.argpartition(dist2, -take)[:-take - 1:-1]
             far_pos = [int(rows[f]) for f in far]
             far_d2 = [float(dist2[f]) for f in far]
+        else:
+            hit = np.flatnonzero(at_max_bin == b)
+            far_pos = [int(at_max_h[hit[0]])] if len(hit) and n_here else []
+            far_d2 = [float(d2_at_max[hit[0]])] if far_pos else []
         for k, new_id in enumerate(empty):
             slot_bin.append(b)
             slot_new.append(int(new_id))
             local_pos.append(far_pos[k] if k < len(far_pos) else -1)
             local_d2.append(far_d2[k] if k < len(far_pos) else -np.inf)
+    mark(f"host-pick({len(affected)} bins, {idx.numel()} pts)")
     E = len(slot_new)
     pos_t = torch.tensor([max(p, 0) for p in local_pos], dtype=torch.int64, device=dev)
     pts = idx.long()[pos_t] if idx.numel() else torch.zeros(E, dtype=torch.int64, device=dev)
@@ -205,13 +231,20 @@ def _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bins_dev, flags_
     delta = cand[wr, :D] * wts[:, None]
     old_h = meta[win_rows, 1].astype(np.int64)
     old_ids = torch.from_numpy(old_h).to(dev)
-    if len(set(old_h.tolist())) == len(old_h):
-        sum_wx.index_add_(0, old_ids, -delta)
-        sum_w.index_add_(0, old_ids, -wts)
-    else:                       # one old cluster loses several points: subtract in sklearn's order
-        for k in range(len(old_h)):
-            sum_wx[old_ids[k]] -= delta[k]
-            sum_w[old_ids[k]] -= wts[k]
+    # one old cluster may lose several points: subtract them in rounds (the r-th loss of every cluster in round r), so
+    # each round's indexed update touches distinct rows and the order of the subtractions is fixed
+    order = np.argsort(old_h, kind="stable")
+    rank = np.empty(len(old_h), dtype=np.int64)
+    sorted_old = old_h[order]
+    first = np.r_[0, np.flatnonzero(np.diff(sorted_old)) + 1]
+    rank[order] = np.arange(len(old_h)) - np.repeat(first, np.diff(np.r_[first, len(old_h)]))
+    for r in range(int(rank.max()) + 1):
+        sel_r = torch.from_numpy(np.flatnonzero(rank == r)).to(dev)
+        sum_wx.index_add_(0, old_ids[sel_r], -delta[sel_r])
+        sum_w.index_add_(0, old_ids[sel_r], -wts[sel_r])
     sum_wx[new_ids] = delta
     sum_w[new_ids] = wts
+    mark("apply")
+    if dbg:
+        print("relocate: " + "  ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f}ms" for a, b in zip(marks[:-1], marks[1:])), flush=True)
     return True

@@ -29,7 +29,9 @@ def sync():
     return time.perf_counter()
 
 
-for it in range(6):
+for it in range(12):
+    if it == 6:
+        c.copy_(eng.centers)           # second round from the initial centres: steady-state cost of the relocation path
     t0 = sync()
     csq = ops.centers_sqnorm(c)
     labels = ops.assign_stratified(Xc, bins, flags, c, csq, eng.bin_offset, eng.max_k, path=_lib.ASSIGN_AUTO, errors=eng.errors)
