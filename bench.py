@@ -475,15 +475,29 @@ def run_b200(cfg, name, iters_total, lloyd, precision_path, steps, warmup, rank,
     if world > 1 and M * M * 8 <= (64 << 20):
         from msm_we_b200.distributed import PeerFluxAllreduce
         reducer = PeerFluxAllreduce.create((M, M), dev)
-    dense = reducer.partial if reducer is not None else torch.zeros((M, M), dtype=torch.float64, device=dev)
+    # N > 1 with a large matrix: the NCCL all-reduce (+ / nI) of step k runs on a side stream while step k+1 starts its
+    # Lloyd iterations (the reduced matrix is only needed at the end of the pass); two matrices alternate
+    overlap = world > 1 and reducer is None
+    n_dense = 2 if overlap else 1
+    denses = [reducer.partial] if reducer is not None else [torch.zeros((M, M), dtype=torch.float64, device=dev)
+                                                            for _ in range(n_dense)]
+    side = torch.cuda.Stream(device=dev) if overlap else None
+    flux_group = dist.new_group() if overlap else None      # its own communicator: runs beside the Lloyd all-reduces
+    side_done = [None] * n_dense
     labels = torch.empty(2 * N, dtype=torch.int64, device=dev)
     l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     path = {"auto": _lib.ASSIGN_AUTO, "tf32x3": _lib.ASSIGN_TF32X3, "fp64": _lib.ASSIGN_FP64}[precision_path]
     if path == _lib.ASSIGN_AUTO:   # same rule as the library (csrc/assign.cu, resolve_assign_path)
         path = _lib.ASSIGN_TF32X3 if cfg.k_per_bin * cfg.dim >= 2048 else _lib.ASSIGN_FP64
     Xc, pc0 = X[N:], pc[:N]
+    step_no = [0]
 
     def step(ev=None):
+        k = step_no[0] % n_dense
+        step_no[0] += 1
+        dense = denses[k]
+        if side_done[k] is not None:
+            torch.cuda.current_stream().wait_event(side_done[k])      # the exchange that last used this matrix has finished
         dense.zero_()
         if lloyd:
             engine.centers.copy_(centers0)
@@ -501,8 +515,21 @@ def run_b200(cfg, name, iters_total, lloyd, precision_path, steps, warmup, rank,
         if reducer is not None:
             reducer.reduce(float(iters_total))
         elif world > 1:
-            dist.all_reduce(dense)
-            ops.divide_(dense, float(iters_total))
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                dist.all_reduce(dense, group=flux_group)
+                ops.divide_(dense, float(iters_total))
+                done = torch.cuda.Event()
+                done.record()
+            side_done[k] = done
+
+    def join():
+        """Everything the steps put on the side stream is complete when the main stream passes this point."""
+        for d in side_done:
+            if d is not None:
+                torch.cuda.current_stream().wait_event(d)
 
     clocks = ClockSampler(local_rank)
     if not quiet_clocks:
@@ -510,6 +537,7 @@ def run_b200(cfg, name, iters_total, lloyd, precision_path, steps, warmup, rank,
     for _ in range(warmup):
         l2_flush.zero_()
         step()
+    join()
     torch.cuda.synchronize()
     engine.check_errors()
     if rank == 0:
@@ -522,9 +550,11 @@ def run_b200(cfg, name, iters_total, lloyd, precision_path, steps, warmup, rank,
     torch.cuda.synchronize()
     clocks.mark_timed(True)
     for k in range(steps):
-        l2_flush.zero_()                       # flush L2 between timed steps (outside the events)
+        l2_flush.zero_()                       # flush L2 between timed steps (outside the events unless steps overlap)
         evs[k][0].record()
         step(kevs[k])
+        if k == steps - 1:
+            join()                             # the last step's exchange is inside the timed region
         evs[k][1].record()
     torch.cuda.synchronize()
     clocks.mark_timed(False)
@@ -532,7 +562,9 @@ def run_b200(cfg, name, iters_total, lloyd, precision_path, steps, warmup, rank,
         clocks.__exit__()
     if world > 1:
         dist.barrier()
-    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    # steps overlap when the exchange runs on the side stream: then the time is first start -> last end (which includes
+    # the L2 flushes between steps); otherwise the sum of the per-step intervals
+    total_ms = evs[0][0].elapsed_time(evs[-1][1]) if overlap else sum(a.elapsed_time(b) for a, b in evs)
     kernel_ms = sum(a.elapsed_time(b) for a, b in kevs) / steps
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -583,7 +615,9 @@ def run_b200(cfg, name, iters_total, lloyd, precision_path, steps, warmup, rank,
                    "exchange": ("none (1 GPU)" if world == 1 else
                                 ("Lloyd partial sums: NCCL all-reduce per Lloyd iteration; " if lloyd else "") +
                                 ("flux: one peer-memory kernel per rank (rank-order sum + / nI over NVLink)" if reducer is not None
-                                 else "flux: NCCL all-reduce of the dense matrix + divide")),
+                                 else "flux: NCCL all-reduce of the dense matrix + divide on a side stream, overlapping the next "
+                                      "step's Lloyd iterations (two matrices alternate; the last step's exchange is inside the "
+                                      "timed region)")),
                    "precision_path": ("tcgen05 split-TF32 candidate pass + fp64 re-check of near-ties (labels identical "
                                       "to the fp64 path)") if tc else "fp64 DMMA"},
         "roofline": roofline, "clocks": None if quiet_clocks else clocks.summary(),
@@ -592,7 +626,7 @@ def run_b200(cfg, name, iters_total, lloyd, precision_path, steps, warmup, rank,
     if reducer is not None:
         dist.barrier()
         reducer.close()
-    del data, X, pc, w, labels, dense, l2_flush
+    del data, X, pc, w, labels, denses, l2_flush
     torch.cuda.empty_cache()
     return line
 

@@ -86,16 +86,16 @@ def lloyd_fit(X_dev, w_dev, bins_dev, centers_dev, bin_offset_dev, max_k, n_iter
     if path is None:
         path = _lib.ASSIGN_AUTO
     labels = None
-    sumK = centers_dev.shape[0]
+    sumK, D = centers_dev.shape
+    sums = torch.empty(sumK * (D + 1), dtype=torch.float64, device=centers_dev.device)   # sum_wx | sum_w: one exchange
     for _ in range(n_iter):
         labels = ops.assign_stratified(X_dev, bins_dev, flags_dev, centers_dev, ops.centers_sqnorm(centers_dev),
                                        bin_offset_dev, max_k, path=path, errors=errors)
-        sum_wx, sum_w = ops.centroid_accumulate(X_dev, w_dev, labels, sumK)
+        sum_wx, sum_w = ops.centroid_accumulate(X_dev, w_dev, labels, sumK, out=sums)
         if group is not None:
             import torch.distributed as dist
 
-            dist.all_reduce(sum_wx, group=group)
-            dist.all_reduce(sum_w, group=group)
+            dist.all_reduce(sums, group=group)
         if relocate_empty:
             _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bins_dev, flags_dev, bin_offset_dev, sum_wx, sum_w, group)
         ops.lloyd_finalize(sum_wx, sum_w, centers_dev)
@@ -156,10 +156,9 @@ def _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bins_dev, flags_
     _, _, _, vmax = ops.label_stats(d2_dev, members, seg_start, nbins)
     mark("group+stats")
     at_max = torch.nonzero(d2_dev == vmax[bins_aff]).squeeze(1)                  # (3)  ~ one position per affected bin
-    at_max_h = at_max.cpu().numpy()
-    at_max_bin = bins_aff[at_max].cpu().numpy()
+    packed = torch.stack([at_max.to(torch.float64), bins_aff[at_max].to(torch.float64), d2_dev[at_max]]).cpu().numpy()
+    at_max_h, at_max_bin, d2_at_max = packed[0].astype(np.int64), packed[1].astype(np.int64), packed[2]
     seg_h = seg_start.cpu().numpy()
-    d2_at_max = d2_dev[at_max].cpu().numpy()
     mark("argmax-d2h")
     slot_bin, slot_new, local_pos, local_d2 = [], [], [], []
     # bins that lost SEVERAL clusters: which far point goes to which cluster follows numpy's argpartition order in

@@ -203,11 +203,17 @@ def _centroid_common(fn, name, X, w, label, sumK, a, b):
     check(fn(_ptr(X), N, D, ldx, _ptr(w), _ptr(label), sumK, _ptr(a), _ptr(b), _ptr(ws), ws.numel(), _stream()), name)
 
 
-def centroid_accumulate(X, w, label, sumK):
-    """K2 partial sums: (sum_wx [sumK,D], sum_w [sumK])."""
+def centroid_accumulate(X, w, label, sumK, out=None):
+    """K2 partial sums: (sum_wx [sumK,D], sum_w [sumK]).  ``out``: optional flat float64 buffer of sumK*(D+1) elements that
+    receives both (sum_wx first), so a multi-GPU caller exchanges them with ONE all-reduce."""
     D = X.shape[1]
-    sum_wx = torch.empty(sumK, D, dtype=torch.float64, device=X.device)
-    sum_w = torch.empty(sumK, dtype=torch.float64, device=X.device)
+    if out is None:
+        out = torch.empty(sumK * (D + 1), dtype=torch.float64, device=X.device)
+    _req(out, torch.float64, "out")
+    if out.numel() != sumK * (D + 1):
+        raise ValueError("out must hold sumK * (D + 1) float64 values")
+    sum_wx = out[: sumK * D].view(sumK, D)
+    sum_w = out[sumK * D:]
     _centroid_common(lib.mwe_centroid_accumulate_f64, "mwe_centroid_accumulate_f64", X, w, label, sumK, sum_wx, sum_w)
     return sum_wx, sum_w
 

@@ -113,7 +113,7 @@ def emulate_kernels(monkeypatch):
     def minibatch_update(X, w, label, centers, counts):
         O.minibatch_update(_np(X), _np(w), centers.numpy(), counts.numpy(), _np(label))
 
-    def centroid_accumulate(X, w, label, sumK):
+    def centroid_accumulate(X, w, label, sumK, out=None):
         x, lab = _np(X), _np(label)
         ww = np.ones(len(lab)) if w is None else _np(w)
         sums = np.zeros((sumK, x.shape[1]))
@@ -122,6 +122,11 @@ def emulate_kernels(monkeypatch):
         for i in np.flatnonzero(ok):                 # sample order, product and sum rounded separately
             wsum[lab[i]] += ww[i]
             sums[lab[i]] = sums[lab[i]] + x[i] * ww[i]
+        if out is not None:
+            D = x.shape[1]
+            out[: sumK * D].copy_(torch.from_numpy(sums).reshape(-1))
+            out[sumK * D:].copy_(torch.from_numpy(wsum))
+            return out[: sumK * D].view(sumK, D), out[sumK * D:]
         return torch.from_numpy(sums), torch.from_numpy(wsum)
 
     def lloyd_finalize(sum_wx, sum_w, centers):
