@@ -160,49 +160,53 @@ def _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bins_dev, flags_
     at_max_h, at_max_bin, d2_at_max = packed[0].astype(np.int64), packed[1].astype(np.int64), packed[2]
     seg_h = seg_start.cpu().numpy()
     mark("argmax-d2h")
-    slot_bin, slot_new, local_pos, local_d2 = [], [], [], []
-    # bins that lost SEVERAL clusters: which far point goes to which cluster follows numpy's argpartition order in
+    # slots: one per empty cluster of an affected bin, in ascending cluster index (= grouped by bin); every rank sees the
+    # same sums, hence the same slots.  Vectorised: a Python loop only over the bins that lost SEVERAL clusters.
+    sizes = np.diff(offs)
+    bin_of_cluster = np.repeat(np.arange(nbins), sizes)
+    aff_mask = np.zeros(nbins, dtype=bool)
+    aff_mask[affected] = True
+    slot_new = np.flatnonzero((sw == 0) & aff_mask[bin_of_cluster])
+    slot_bin = bin_of_cluster[slot_new]
+    E = len(slot_new)
+    n_empty = np.bincount(slot_bin, minlength=nbins)
+    n_here = np.diff(seg_h[: nbins + 1])
+    local_pos = np.full(E, -1, dtype=np.int64)
+    local_d2 = np.full(E, -np.inf)
+    # single-empty bins: the bin's farthest point (first position holding the bin maximum)
+    ub, first = np.unique(at_max_bin, return_index=True)
+    best_pos = np.full(nbins, -1, dtype=np.int64)
+    best_d2 = np.full(nbins, -np.inf)
+    best_pos[ub], best_d2[ub] = at_max_h[first], d2_at_max[first]
+    single = (n_empty[slot_bin] == 1) & (n_here[slot_bin] > 0)
+    local_pos[single] = best_pos[slot_bin[single]]
+    local_d2[single] = best_d2[slot_bin[single]]
+    # bins that lost several clusters: which far point goes to which cluster follows numpy's argpartition order in
     # sklearn, so the same call runs on each such bin's full distance list -- fetched for all of them in one transfer
-    empties = {b: int(offs[b]) + np.flatnonzero(sw[int(offs[b]):int(offs[b + 1])] == 0) for b in affected}
-    multi = [b for b in affected if len(empties[b]) > 1 and seg_h[b + 1] > seg_h[b]]
-    multi_rows, multi_d2, multi_off = None, None, {}
-    if multi:
-        pieces, pos = [], 0
-        for b in multi:
-            pieces.append(members[int(seg_h[b]):int(seg_h[b + 1])])
-            multi_off[b] = (pos, pos + int(seg_h[b + 1] - seg_h[b]))
-            pos += int(seg_h[b + 1] - seg_h[b])
-        rows_all = torch.cat(pieces).long()
+    multi = np.flatnonzero((n_empty > 1) & (n_here > 0))
+    if multi.size:
+        starts, ends = seg_h[multi].astype(np.int64), seg_h[multi + 1].astype(np.int64)
+        lens = ends - starts
+        gather = torch.from_numpy(np.concatenate([np.arange(a, z) for a, z in zip(starts, ends)])).to(dev)
+        rows_all = members[gather].long()
         packed = torch.stack([d2_dev[rows_all], rows_all.to(torch.float64)]).cpu().numpy()
         multi_d2, multi_rows = packed[0], packed[1].astype(np.int64)
-    for b in affected:
-        empty = empties[b]
-        n_here = int(seg_h[b + 1] - seg_h[b])
-        if b in multi_off:
-            a, z = multi_off[b]
-            dist2, rows = multi_d2[a:z], multi_rows[a:z]
-            take = min(len(empty), len(dist2))
+        cuts = np.concatenate([[0], np.cumsum(lens)])
+        slot_first = np.searchsorted(slot_bin, multi)                 # first slot of each multi-empty bin
+        for i, b in enumerate(multi):
+            dist2, rows = multi_d2[cuts[i]:cuts[i + 1]], multi_rows[cuts[i]:cuts[i + 1]]
+            take = min(int(n_empty[b]), len(dist2))
             far = np.argpartition(dist2, -take)[:-take - 1:-1]
-            far_pos = [int(rows[f]) for f in far]
-            far_d2 = [float(dist2[f]) for f in far]
-        else:
-            hit = np.flatnonzero(at_max_bin == b)
-            far_pos = [int(at_max_h[hit[0]])] if len(hit) and n_here else []
-            far_d2 = [float(d2_at_max[hit[0]])] if far_pos else []
-        for k, new_id in enumerate(empty):
-            slot_bin.append(b)
-            slot_new.append(int(new_id))
-            local_pos.append(far_pos[k] if k < len(far_pos) else -1)
-            local_d2.append(far_d2[k] if k < len(far_pos) else -np.inf)
-    mark(f"host-pick({len(affected)} bins, {idx.numel()} pts)")
-    E = len(slot_new)
-    pos_t = torch.tensor([max(p, 0) for p in local_pos], dtype=torch.int64, device=dev)
+            local_pos[slot_first[i]:slot_first[i] + take] = rows[far]
+            local_d2[slot_first[i]:slot_first[i] + take] = dist2[far]
+    mark(f"host-pick({len(affected)} bins, {E} slots, {idx.numel()} pts)")
+    pos_t = torch.from_numpy(np.maximum(local_pos, 0)).to(dev)
     pts = idx.long()[pos_t] if idx.numel() else torch.zeros(E, dtype=torch.int64, device=dev)
     cand = torch.empty((E, D + 3), dtype=torch.float64, device=dev)             # row | weight | old label | distance
     cand[:, :D] = X_dev[pts]
     cand[:, D] = 1.0 if w_dev is None else w_dev[pts]
     cand[:, D + 1] = labels[pts].to(torch.float64)
-    cand[:, D + 2] = torch.tensor(local_d2, dtype=torch.float64, device=dev)
+    cand[:, D + 2] = torch.from_numpy(local_d2).to(dev)
     if world > 1:
         import torch.distributed as dist
 
@@ -210,22 +214,24 @@ def _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bins_dev, flags_
         dist.all_gather(parts, cand.contiguous(), group=group)
         cand = torch.cat(parts, dim=0)
     meta = cand[:, D:].cpu().numpy()                                             # (4)  [world*E, 3]
-    # winners per bin: the n_empty largest distances among all ranks' candidates of that bin (rank order breaks ties)
-    slot_bin = np.asarray(slot_bin)
-    win_rows, win_new = [], []
-    for b in affected:
-        slots = np.flatnonzero(slot_bin == b)
-        rows_b = np.concatenate([r * E + slots for r in range(world)])
-        d_b = meta[rows_b, 2]
-        order = np.argsort(-d_b, kind="stable")[: len(slots)]
-        for k, o in enumerate(order):
-            if np.isfinite(d_b[o]):
-                win_rows.append(int(rows_b[o]))
-                win_new.append(slot_new[slots[k]])
-    if not win_rows:
+    # winners: per bin the n_empty largest distances among all ranks' candidates (rank order breaks ties)
+    dmat = meta[:, 2].reshape(world, E)
+    win_rank = np.argmax(dmat, axis=0)                                          # single-empty bins: the best rank's candidate
+    win_rows = win_rank * E + np.arange(E)
+    valid = np.isfinite(dmat[win_rank, np.arange(E)])
+    if world > 1:
+        for b in np.flatnonzero(n_empty > 1):                                   # several empties: global top-k of the bin
+            slots = np.flatnonzero(slot_bin == b)
+            rows_b = (np.arange(world)[:, None] * E + slots[None, :]).ravel()
+            d_b = meta[rows_b, 2]
+            order = np.argsort(-d_b, kind="stable")[: len(slots)]
+            win_rows[slots] = rows_b[order]
+            valid[slots] = np.isfinite(d_b[order])
+    win_rows, win_new = win_rows[valid], slot_new[valid]
+    if win_rows.size == 0:
         return False
-    wr = torch.tensor(win_rows, dtype=torch.int64, device=dev)
-    new_ids = torch.tensor(win_new, dtype=torch.int64, device=dev)
+    wr = torch.from_numpy(win_rows).to(dev)
+    new_ids = torch.from_numpy(win_new).to(dev)
     wts = cand[wr, D]
     delta = cand[wr, :D] * wts[:, None]
     old_h = meta[win_rows, 1].astype(np.int64)
