@@ -102,6 +102,11 @@ def lloyd_fit(X_dev, w_dev, bins_dev, centers_dev, bin_offset_dev, max_k, n_iter
     return labels
 
 
+# Above this many points in the bins that lost several clusters at once, the farthest points are ranked on the device
+# (see _relocate_empty_clusters); below it the host runs the very numpy call sklearn uses.
+EXACT_ORDER_MAX_POINTS = 1 << 16
+
+
 def _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bins_dev, flags_dev, bin_offset_dev, sum_wx, sum_w, group):
     """sklearn's ``_relocate_empty_clusters_dense`` per WE-bin model, applied to the (all-reduced) partial sums before
     the mean: a cluster that received no weight takes the point farthest from its own centre, which leaves its old
@@ -187,18 +192,36 @@ def _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bins_dev, flags_
     if multi.size:
         starts, ends = seg_h[multi].astype(np.int64), seg_h[multi + 1].astype(np.int64)
         lens = ends - starts
-        gather = torch.from_numpy(np.concatenate([np.arange(a, z) for a, z in zip(starts, ends)])).to(dev)
-        rows_all = members[gather].long()
-        packed = torch.stack([d2_dev[rows_all], rows_all.to(torch.float64)]).cpu().numpy()
-        multi_d2, multi_rows = packed[0], packed[1].astype(np.int64)
-        cuts = np.concatenate([[0], np.cumsum(lens)])
         slot_first = np.searchsorted(slot_bin, multi)                 # first slot of each multi-empty bin
-        for i, b in enumerate(multi):
-            dist2, rows = multi_d2[cuts[i]:cuts[i + 1]], multi_rows[cuts[i]:cuts[i + 1]]
-            take = min(int(n_empty[b]), len(dist2))
-            far = np.argpartition(dist2, -take)[:-take - 1:-1]
-            local_pos[slot_first[i]:slot_first[i] + take] = rows[far]
-            local_d2[slot_first[i]:slot_first[i] + take] = dist2[far]
+        if int(lens.sum()) <= EXACT_ORDER_MAX_POINTS:
+            gather = torch.from_numpy(np.concatenate([np.arange(a, z) for a, z in zip(starts, ends)])).to(dev)
+            rows_all = members[gather].long()
+            packed = torch.stack([d2_dev[rows_all], rows_all.to(torch.float64)]).cpu().numpy()
+            multi_d2, multi_rows = packed[0], packed[1].astype(np.int64)
+            cuts = np.concatenate([[0], np.cumsum(lens)])
+            for i, b in enumerate(multi):
+                dist2, rows = multi_d2[cuts[i]:cuts[i + 1]], multi_rows[cuts[i]:cuts[i + 1]]
+                take = min(int(n_empty[b]), len(dist2))
+                far = np.argpartition(dist2, -take)[:-take - 1:-1]
+                local_pos[slot_first[i]:slot_first[i] + take] = rows[far]
+                local_d2[slot_first[i]:slot_first[i] + take] = dist2[far]
+        else:
+            # large models: shipping whole distance lists to the host would dominate the Lloyd iteration.  The listed
+            # points are ordered on the device by (bin, distance descending) with two stable sorts and only each bin's
+            # first n_empty entries come back.  Same SET of relocated points as sklearn; they are handed to the bin's
+            # empty clusters in descending distance (sklearn: in the order numpy's introselect leaves them), so the
+            # relocated centres may sit at permuted cluster indices of that bin.
+            by_d = torch.argsort(d2_dev, descending=True, stable=True)
+            by_bin = torch.argsort(bins_aff[by_d], stable=True)
+            ranked = by_d[by_bin]                                          # positions grouped by bin, farthest first
+            take = np.minimum(n_empty[multi], lens)
+            want = np.concatenate([np.arange(a, a + t) for a, t in zip(starts, take)])
+            sel_pos = ranked[torch.from_numpy(want).to(dev)]
+            packed = torch.stack([sel_pos.to(torch.float64), d2_dev[sel_pos]]).cpu().numpy()
+            cuts = np.concatenate([[0], np.cumsum(take)])
+            for i in range(len(multi)):
+                local_pos[slot_first[i]:slot_first[i] + take[i]] = packed[0][cuts[i]:cuts[i + 1]].astype(np.int64)
+                local_d2[slot_first[i]:slot_first[i] + take[i]] = packed[1][cuts[i]:cuts[i + 1]]
     mark(f"host-pick({len(affected)} bins, {E} slots, {idx.numel()} pts)")
     pos_t = torch.from_numpy(np.maximum(local_pos, 0)).to(dev)
     pts = idx.long()[pos_t] if idx.numel() else torch.zeros(E, dtype=torch.int64, device=dev)

@@ -127,3 +127,27 @@ def test_model_lloyd_refine_clusters_matches_sklearn_per_bin(monkeypatch, gpu):
             continue
         ref_c, _ = _sklearn_lloyd(rows, centers[b], 3)
         assert np.allclose(clusters.cluster_models[b].cluster_centers_, ref_c, rtol=1e-11, atol=1e-12), b
+
+
+@pytest.mark.parametrize("gpu", BACKENDS)
+def test_lloyd_relocation_device_ranked_branch_relocates_the_same_points(monkeypatch, gpu):
+    """Large models rank the farthest points on the device (clustering_ops.EXACT_ORDER_MAX_POINTS): the same points are
+    relocated as by sklearn; only the cluster index that receives each of them may be permuted within the bin."""
+    import torch
+
+    dev = _backend(monkeypatch, gpu)
+    from msm_we_b200 import clustering_ops
+
+    monkeypatch.setattr(clustering_ops, "EXACT_ORDER_MAX_POINTS", 0)
+    rng = np.random.default_rng(8)
+    K, D = 7, 5
+    X = np.concatenate([rng.normal(m, 0.4, size=(80, D)) for m in (-5, 0, 5, 11)])
+    init = np.stack([X[0], X[0], X[0], X[90], X[90], X[170], X[250]])      # three empty clusters in one model
+    centers = torch.from_numpy(init.copy()).to(dev)
+    offs = torch.tensor([0, K], dtype=torch.int64, device=dev)
+    bins = torch.zeros(len(X), dtype=torch.int32, device=dev)
+    clustering_ops.lloyd_fit(torch.from_numpy(X).to(dev), None, bins, centers, offs, K, 1)
+    ref_c, _ = _sklearn_lloyd(X, init, 1)
+    got = centers.cpu().numpy()
+    key = lambda a: a[np.lexsort(a.T[::-1])]            # noqa: E731  rows in a canonical order
+    assert np.allclose(key(got), key(ref_c), rtol=1e-11, atol=1e-12)
