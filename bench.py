@@ -6,7 +6,7 @@ transition scattered).
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg5|cfg2|cfg3|cfg4|...] [--impl b200|reference]
 
 Default workload = BASELINE config 5's per-frame shape (8,000 segs x 256-dim features, 100 WE bins x 100 clusters),
-the largest configuration whose iterations can be held resident on ONE B200: 2,000 of its 5,000 iterations (65.5 GB
+the largest configuration whose iterations can be held resident on ONE B200: 4,000 of its 5,000 iterations (131 GB
 of features; the full 164 GB does not fit beside the workspaces).  One step = one "haMSM rebuild" pass over the
 resident iterations, as config 5 words it:
     10 Lloyd iterations  (K0 bins of the parent pcoords once; per iteration K1 assignment of the child frames +
@@ -47,7 +47,7 @@ METRIC = "we_frames_per_sec_assigned_and_flux_accumulated"
 UNIT = "frames/s"
 
 # iterations of each named shape held resident by ONE GPU (N > 1 splits the same iterations by range)
-RESIDENT_ITERS = {"cfg5": 2000, "cfg3": 300, "cfg2": 200, "cfg5s": 250, "cfg3s": 50, "tiny": 12}
+RESIDENT_ITERS = {"cfg5": 4000, "cfg3": 300, "cfg2": 200, "cfg5s": 250, "cfg3s": 50, "tiny": 12}
 LLOYD_ITERS = {"cfg5": 10, "cfg5s": 10}
 
 
