@@ -601,11 +601,14 @@ class ClusteringMixin:
         projection = getattr(self.coordinates, "device_projection", None)
         projection = projection(dev.device) if callable(projection) else None
         Din = int(projection[0].shape[1]) if projection is not None else dev.D
-        budget = max_device_bytes or int(0.6 * torch.cuda.mem_get_info(dev.device)[0])
-        if n * (Din + P + 4) * 8 > budget:
-            raise MemoryError(f"{n} frames x {Din} features do not fit the device budget ({budget} bytes); pass fewer "
-                              f"iterations (iters_to_use=) -- config 5 is sized for iteration-range shards over 8 GPUs")
-        X = torch.empty((n, Din), dtype=torch.float64, device=dev.device)
+        need = n * (Din + P + 4) * 8
+        if max_device_bytes is not None and need > max_device_bytes:
+            raise MemoryError(f"{n} frames x {Din} features ({need} bytes) exceed max_device_bytes={max_device_bytes}")
+        try:
+            X = torch.empty((n, Din), dtype=torch.float64, device=dev.device)
+        except torch.OutOfMemoryError as e:
+            raise MemoryError(f"{n} frames x {Din} features do not fit on the device; pass fewer iterations "
+                              f"(iters_to_use=) -- config 5 is sized for iteration-range shards over 8 GPUs") from e
         hp_t = torch.empty((n, P), dtype=torch.float64, pin_memory=True)
         hp = hp_t.numpy()
         stage_rows = max(counts)

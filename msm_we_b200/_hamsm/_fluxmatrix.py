@@ -18,6 +18,35 @@ from .._logging import log, ProgressBar
 
 DEFAULT_FLUX_CHUNK = 1 << 26  # transitions per launch sequence
 _FLUX_STAGE = {"host": None, "pending": None}   # pinned staging rows, reused across calls
+_RESULT_POOL = []                               # page-locked result matrices: (torch tensor, numpy view)
+
+
+def _to_host(dense):
+    """The dense flux matrix as a numpy array.  Small matrices: a plain copy.  Large ones (config 5: 10,002^2 fp64 =
+    800 MB) go into PAGE-LOCKED host memory, which the device fills at link speed (a pageable copy of that size runs at
+    ~2 GB/s and was 75 % of an end-to-end pass); the array handed out is a view of that buffer, and a buffer is reused
+    only once nothing outside this pool references its previous view."""
+    import sys
+
+    import torch
+
+    if dense.numel() * 8 < (64 << 20):
+        return dense.cpu().numpy()
+    shape = tuple(dense.shape)
+    slot = None
+    for t, view in _RESULT_POOL:
+        # references: the pool's tuple + this loop variable + getrefcount's argument
+        if tuple(t.shape) == shape and sys.getrefcount(view) <= 3:
+            slot = (t, view)
+            break
+    if slot is None:
+        t = torch.empty(shape, dtype=torch.float64, pin_memory=True)
+        slot = (t, t.numpy())
+        _RESULT_POOL.append(slot)
+        del _RESULT_POOL[:-4]            # at most four buffers stay page-locked
+    slot[0].copy_(dense, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return slot[1]
 
 
 class _RemoteShim:
@@ -239,7 +268,7 @@ class FluxMatrixMixin:
 
     def get_iter_fluxMatrix(self, n_iter):
         """reference: _fluxmatrix.py:21-72.  Dense ``(n_clusters+2)^2`` ndarray for one iteration."""
-        return self._flux_device([n_iter]).cpu().numpy()
+        return _to_host(self._flux_device([n_iter]))
 
     def get_fluxMatrix(self, n_lag, first_iter=1, last_iter=None, iters_to_use=None, use_ray=False,
                        result_batch_size=5, progress_bar=None):
@@ -268,4 +297,5 @@ class FluxMatrixMixin:
                 self.fluxMatrixRaw = dense.cpu().numpy() / nI
             return
         ops.divide_(dense, float(nI))
-        self.fluxMatrixRaw = dense.cpu().numpy()
+        self.fluxMatrixRaw = None            # (lets the page-locked buffer of the previous result be reused)
+        self.fluxMatrixRaw = _to_host(dense)
