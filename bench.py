@@ -584,7 +584,8 @@ def run_b200(cfg, name, iters_total, lloyd, precision_path, steps, warmup, rank,
     alg_bytes = 2 * N * (cfg.dim * 8 + 4 + 8)
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     tc = path == _lib.ASSIGN_TF32X3
-    kname = "assign_tc_kernel" if tc else ("assign_dmma_resident_kernel" if (cfg.k_per_bin <= 64 and cfg.dim % 2 == 0)
+    n_pad = (cfg.k_per_bin + 15) // 16 * 16
+    kname = ("assign_tc2_kernel" if 2 * n_pad + 128 <= 512 else "assign_tc_kernel") if tc else ("assign_dmma_resident_kernel" if (cfg.k_per_bin <= 64 and cfg.dim % 2 == 0)
                                            else "assign_dmma_kernel")
     step_bytes, step_flops = step_work(cfg, N, lloyd)        # this rank's share; ranks run concurrently
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -600,7 +601,7 @@ def run_b200(cfg, name, iters_total, lloyd, precision_path, steps, warmup, rank,
         with open(os.path.join(ROOT, "profiles", "k1_dram_traffic.json")) as f:
             entry = json.load(f).get(f"{name}/{kname}")
         if entry:
-            roofline["traffic"] = entry["bytes"] * (2 * N) / entry.get("points", 2 * N)
+            roofline["traffic"] = entry["bytes"] * (2 * N) / (entry.get("points") or 2 * N)
             roofline["traffic_source"] = entry["source"]
     except (OSError, ValueError):
         pass

@@ -473,10 +473,12 @@ __global__ void __launch_bounds__(128)
                           int32_t* __restrict__ local_out) {
     pdl_wait();
     pdl_launch_dependents();
-    // One warp per listed point.  A centre's score is formed by the whole warp: lanes stride the D dimension (coalesced
-    // reads of the centre row; the point row stays in L1), partial fp64 FMA chains are combined by a fixed butterfly, so
-    // every lane holds the same s_j and the result does not depend on scheduling.  Lane j % 32 keeps s_j of round j / 32
-    // in a register, so the tolerance pass needs no second evaluation for K_b <= 32 * RC_ROUNDS.
+    // One warp per listed point, 8 centres per pass.  Lanes stride the D dimension (coalesced reads of the centre rows;
+    // the point row stays in L1) and keep one partial fp64 FMA chain per centre of the pass; the 32 x 8 partials are
+    // folded by a transposing butterfly over lane bits 0-2 (4 + 2 + 1 exchanges) and a plain one over bits 3-4, after
+    // which lane l holds the score of centre (l & 7) of the pass: 9 exchanges per 8 centres instead of 5 per centre.
+    // Fixed order, independent of scheduling.  Four passes fill a group of 32 centres; lane j % 32 keeps s_j of group
+    // j / 32 in sc[], so the tolerance pass needs no second evaluation for K_b <= 32 * RC_ROUNDS.
     constexpr int RC_ROUNDS = 8;
     const int n = *count;
     const int lane = threadIdx.x & 31;
@@ -488,33 +490,72 @@ __global__ void __launch_bounds__(128)
         const int64_t coff = bin_offset[b];
         const int kb = (int)(bin_offset[b + 1] - coff);
         const double* x = X + (int64_t)pt * ldx;
-        auto score = [&](int j, double& xx_part) {
-            const double* c = centers + (coff + j) * D;
-            double acc = 0.0;
+        double xx = 0.0;
+        for (int k = lane; k < D; k += 32) xx = fma(x[k], x[k], xx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) xx += __shfl_xor_sync(0xffffffffu, xx, o);
+        // scores of centres [j0, j0 + 8): lane l gets centre j0 + (l & 7); +inf past K_b
+        auto pass_scores = [&](int j0) {
+            double acc[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = 0.0;
+            const double* cbase = centers + (coff + j0) * D;
+            const int nc = kb - j0;                         // >= 1; rows past K_b are not read
             for (int k = lane; k < D; k += 32) {
                 const double xv = x[k];
-                acc = fma(xv, c[k], acc);
-                if (j == 0) xx_part = fma(xv, xv, xx_part);
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (c < nc) acc[c] = fma(xv, cbase[(int64_t)c * D + k], acc[c]);
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            return fma(-2.0, acc, csq[coff + j]);
+            for (int o = 4; o > 0; o >>= 1) {               // transposing fold over lane bits 2, 1, 0
+                const bool upper = (lane & o) != 0;
+#pragma unroll
+                for (int c = 0; c < o; ++c) {
+                    const double keep = upper ? acc[c + o] : acc[c];
+                    const double give = upper ? acc[c] : acc[c + o];
+                    acc[c] = keep + __shfl_xor_sync(0xffffffffu, give, o);
+                }
+            }
+            double tot = acc[0];
+            tot += __shfl_xor_sync(0xffffffffu, tot, 8);
+            tot += __shfl_xor_sync(0xffffffffu, tot, 16);
+            const int j = j0 + (lane & 7);
+            return (j < kb) ? fma(-2.0, tot, csq[coff + j]) : inf;
+        };
+        // scores of centres [g0, g0 + 32) on lane (j - g0)
+        auto group_scores = [&](int g0) {
+            double s = inf;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (g0 + 8 * q < kb) {
+                    const double v = pass_scores(g0 + 8 * q);
+                    if ((lane >> 3) == q) s = v;
+                }
+            }
+            return s;
         };
         double sc[RC_ROUNDS];
 #pragma unroll
         for (int r = 0; r < RC_ROUNDS; ++r) sc[r] = inf;
-        double smin = inf, cm = 0.0, xx = 0.0;
-        for (int j = 0; j < kb; ++j) {
-            const double s = score(j, xx);
-            if (s < smin) smin = s;
-            cm = fmax(cm, csq[coff + j]);
-            const int r = j >> 5;
+        double smin = inf, cm = 0.0;
 #pragma unroll
-            for (int rr = 0; rr < RC_ROUNDS; ++rr)
-                if (rr == r && (j & 31) == lane) sc[rr] = s;
+        for (int r = 0; r < RC_ROUNDS; ++r) {
+            if (r * 32 < kb) {
+                sc[r] = group_scores(r * 32);
+                smin = fmin(smin, sc[r]);
+                if (r * 32 + lane < kb) cm = fmax(cm, csq[coff + r * 32 + lane]);
+            }
+        }
+        for (int g0 = 32 * RC_ROUNDS; g0 < kb; g0 += 32) {                          // very wide bins
+            smin = fmin(smin, group_scores(g0));
+            if (g0 + lane < kb) cm = fmax(cm, csq[coff + g0 + lane]);
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) xx += __shfl_xor_sync(0xffffffffu, xx, o);
+        for (int o = 16; o > 0; o >>= 1) {
+            smin = fmin(smin, __shfl_xor_sync(0xffffffffu, smin, o));
+            cm = fmax(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+        }
         const double cmax = sqrt(cm);
         const double tol = tie_scale * cmax * (2.0 * sqrt(xx) + cmax);
         int best = 0x7fffffff;
@@ -524,9 +565,9 @@ __global__ void __launch_bounds__(128)
             const unsigned m = __ballot_sync(0xffffffffu, sc[r] <= smin + tol);      // (+inf on lanes past K_b: never set)
             if (m) best = r * 32 + (__ffs(m) - 1);
         }
-        for (int j = 32 * RC_ROUNDS; j < kb && best == 0x7fffffff; ++j) {              // very wide bins: evaluate again
-            double dummy = 0.0;
-            if (score(j, dummy) <= smin + tol) best = j;
+        for (int g0 = 32 * RC_ROUNDS; g0 < kb && best == 0x7fffffff; g0 += 32) {     // very wide bins: evaluate again
+            const unsigned m = __ballot_sync(0xffffffffu, group_scores(g0) <= smin + tol);
+            if (m) best = g0 + (__ffs(m) - 1);
         }
         if (best == 0x7fffffff) best = 0;  // all scores NaN: the reference's scan keeps index 0
         if (lane == 0) {
