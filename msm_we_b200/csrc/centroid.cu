@@ -48,6 +48,43 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Launch order of the per-cluster CTAs: largest clusters first.  One CTA adds one cluster's member rows in sample order,
+// so a cluster with 10^4 members keeps its CTA busy for most of the kernel; in cluster-index order the last such
+// cluster to start IS the tail (config-5 shape, Lloyd on WE data: a few clusters per bin hold a quarter of the bin's
+// points; 2.2-2.8 ms per 4e6 points against 1.4 ms with evenly sized clusters).  Counting sort by size class (quarter
+// octaves, descending) in one CTA; the position inside a class is arbitrary, which changes the schedule, never a sum.
+static constexpr int CS_CLASSES = 128;
+static constexpr int CS_BIG = 2048, CS_SPLIT = 4;   // see centroid_sum_kernel
+__device__ __forceinline__ int cs_size_class(int n) {
+    if (n <= 0) return CS_CLASSES;
+    const int lg = 31 - __clz(n);
+    const int sub = lg >= 2 ? ((n >> (lg - 2)) & 3) : ((n << (2 - lg)) & 3);
+    return CS_CLASSES - 1 - (lg * 4 + sub);
+}
+__global__ void __launch_bounds__(1024)
+    centroid_order_kernel(const int32_t* __restrict__ seg_start, int32_t sumK, int32_t* __restrict__ order) {
+    pdl_wait();
+    pdl_launch_dependents();
+    __shared__ int hist[CS_CLASSES + 1];
+    for (int i = threadIdx.x; i <= CS_CLASSES; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int k = threadIdx.x; k < sumK; k += blockDim.x) atomicAdd(&hist[cs_size_class(seg_start[k + 1] - seg_start[k])], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i <= CS_CLASSES; ++i) {
+            const int c = hist[i];
+            hist[i] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) order[sumK] = hist[cs_size_class(CS_BIG) + 1];   // classes of >= CS_BIG members come first
+    __syncthreads();
+    for (int k = threadIdx.x; k < sumK; k += blockDim.x)
+        order[atomicAdd(&hist[cs_size_class(seg_start[k + 1] - seg_start[k])], 1)] = k;
+}
+
 enum CentroidMode { CM_ACCUMULATE = 0, CM_MINIBATCH = 1 };
 
 static constexpr int CS_ST = 3;       // ring depth: two chunks in flight per CTA while one is being added
@@ -67,46 +104,73 @@ template <> struct CsGeom<256> { static constexpr int THREADS = 288, ROWS = 6; }
 // prefetched into registers, and the 64 feature threads only ever read shared memory.  One extra thread adds the
 // weights in member order while the others work (the first version made every thread walk the whole weight list
 // through two dependent global loads per member before it started: 416 us on the cfg2 shape, now HBM-bound).
+// Clusters with at least CS_BIG members are SPLIT over CS_SPLIT CTAs by feature columns (wide geometry, accumulate
+// mode): a (cluster, feature) add chain stays sequential, but four CTAs pull the cluster's rows instead of one.  For
+// D <= 768 the four work on interleaved 64-column blocks with 24 staged rows (the same shared-memory footprint
+// reinterpreted), above that on interleaved 256-column blocks.  The order kernel puts the big clusters first and
+// leaves their number in order[sumK].
 template <int MODE, int VEC, int CS_FT>
 __global__ void __launch_bounds__(CsGeom<CS_FT>::THREADS, CS_FT == 256 ? 4 : 5)
     centroid_sum_kernel(const double* __restrict__ X, int64_t ldx, int D, const double* __restrict__ w,
                         const uint32_t* __restrict__ members, const int32_t* __restrict__ seg_start,
-                        double* __restrict__ out_wx, double* __restrict__ out_w) {
+                        const int32_t* __restrict__ order, int32_t sumK, double* __restrict__ out_wx,
+                        double* __restrict__ out_w) {
     pdl_wait();
     pdl_launch_dependents();
     constexpr int CS_THREADS = CsGeom<CS_FT>::THREADS;
     constexpr int CS_ROWS = CsGeom<CS_FT>::ROWS;
-    constexpr int SROWS = CS_SUPER * CS_ROWS;         // members whose index + weight are staged together
-    static_assert(SROWS <= 2 * CS_THREADS, "two metadata entries per thread");
-    __shared__ __align__(16) double s_x[CS_ST][CS_ROWS][CS_FT];
-    __shared__ double s_w[2][SROWS];
-    __shared__ uint32_t s_idx[2][SROWS];
+    constexpr bool CAN_SPLIT = (MODE == CM_ACCUMULATE) && CS_FT == 256;
+    constexpr int SROWS_MAX = CS_SUPER * CS_ROWS * (CAN_SPLIT ? CS_FT / 64 : 1);   // members whose index + weight are staged together
+    static_assert(SROWS_MAX <= 2 * CS_THREADS, "two metadata entries per thread");
+    __shared__ __align__(16) double s_x[CS_ST][CS_ROWS * CS_FT];
+    __shared__ double s_w[2][SROWS_MAX];
+    __shared__ uint32_t s_idx[2][SROWS_MAX];
     __shared__ double s_wsum;
-    const int64_t k = blockIdx.x;
+    // work item -> (cluster, first column block j, stride S)
+    int j = 0, S = 1;
+    int64_t k;
+    {
+        const int n_big = CAN_SPLIT ? order[sumK] : 0;
+        const int item = blockIdx.x;
+        if (item < n_big * CS_SPLIT) {
+            k = order[item / CS_SPLIT];
+            j = item % CS_SPLIT;
+            S = CS_SPLIT;
+        } else {
+            const int idx = item - n_big * (CS_SPLIT - 1);
+            if (idx >= sumK) return;
+            k = order[idx];
+        }
+    }
+    const bool narrow_blocks = CAN_SPLIT && S > 1 && D <= 3 * CS_FT;
+    const int FTe = narrow_blocks ? 64 : CS_FT;               // columns per block of this item
+    const int ROWSe = narrow_blocks ? CS_ROWS * (CS_FT / 64) : CS_ROWS;
+    const int SROWSe = CS_SUPER * ROWSe;
+    const int seg_shift = (narrow_blocks ? 6 : (CS_FT == 256 ? 8 : 6)) - (VEC == 2 ? 1 : 0);   // log2(copy segments per row)
     const int32_t s = seg_start[k], e = seg_start[k + 1];
     const int n = e - s;
-    const int nchunks = (n + CS_ROWS - 1) / CS_ROWS;
+    const int nchunks = (n + ROWSe - 1) / ROWSe;
     const int tid = threadIdx.x;
     const double count0 = (MODE == CM_MINIBATCH) ? out_w[k] : 0.0;
-    constexpr int SEGS = CS_FT / VEC;                 // copy segments per row
-    const int n_ft = (D + CS_FT - 1) / CS_FT;
+    const int n_ft = (D + FTe - 1) / FTe;
     double wsum = 0.0;                                // thread CS_THREADS-1: sum of the weights in member order
+    bool first = true;
 
-    for (int ft = 0; ft < n_ft; ++ft) {
-        const int col0 = ft * CS_FT;
-        const int ncols = min(CS_FT, D - col0);
+    for (int ft = j; ft < n_ft; ft += S) {
+        const int col0 = ft * FTe;
+        const int ncols = min(FTe, D - col0);
         // Member indices and weights (two dependent global loads per member) are fetched a whole super-chunk
         // (CS_SUPER chunks) ahead into registers and published to shared memory when the copies reach it, so that
-        // chain is paid once per 192 members, behind 8 chunks of work, instead of once per chunk.
+        // chain is paid once per super-chunk, behind 8 chunks of work, instead of once per chunk.
         uint32_t idx_r[2];
         double w_r[2];
         auto fetch_super = [&](int sc) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int m = sc * SROWS + h * CS_THREADS + tid;
+                const int m = sc * SROWSe + h * CS_THREADS + tid;
                 idx_r[h] = 0u;
                 w_r[h] = 0.0;
-                if (h * CS_THREADS + tid < SROWS && m < n) {
+                if (h * CS_THREADS + tid < SROWSe && m < n) {
                     idx_r[h] = members[s + m];
                     w_r[h] = w ? w[idx_r[h]] : 1.0;
                 }
@@ -115,21 +179,21 @@ __global__ void __launch_bounds__(CsGeom<CS_FT>::THREADS, CS_FT == 256 ? 4 : 5)
         auto publish_super = [&](int sc) {
 #pragma unroll
             for (int h = 0; h < 2; ++h)
-                if (h * CS_THREADS + tid < SROWS) {
+                if (h * CS_THREADS + tid < SROWSe) {
                     s_idx[sc & 1][h * CS_THREADS + tid] = idx_r[h];
                     s_w[sc & 1][h * CS_THREADS + tid] = w_r[h];
                 }
             __syncthreads();
         };
         auto copy_chunk = [&](int c) {
-            const int sc = c / CS_SUPER, r0 = (c % CS_SUPER) * CS_ROWS;
-            const int rows = min(CS_ROWS, n - c * CS_ROWS);
-            for (int u = tid; u < rows * SEGS; u += CS_THREADS) {
-                const int r = u / SEGS, sg = u - r * SEGS;
+            const int sc = c / CS_SUPER, r0 = (c % CS_SUPER) * ROWSe;
+            const int rows = min(ROWSe, n - c * ROWSe);
+            for (int u = tid; u < (rows << seg_shift); u += CS_THREADS) {
+                const int r = u >> seg_shift, sg = u - (r << seg_shift);
                 const int c_in = sg * VEC;
                 if (c_in < ncols) {
                     const double* src = X + (int64_t)s_idx[sc & 1][r0 + r] * ldx + col0 + c_in;
-                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_x[c % CS_ST][r][c_in]);
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_x[c % CS_ST][r * FTe + c_in]);
                     if (VEC == 2) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
                     else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
                 }
@@ -159,20 +223,21 @@ __global__ void __launch_bounds__(CsGeom<CS_FT>::THREADS, CS_FT == 256 ? 4 : 5)
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group %0;" ::"n"(CS_ST - 1) : "memory");
             __syncthreads();
-            const int st = c % CS_ST;
-            const int rows = min(CS_ROWS, n - c * CS_ROWS);
-            const double* wc = &s_w[(c / CS_SUPER) & 1][(c % CS_SUPER) * CS_ROWS];
+            const int rows = min(ROWSe, n - c * ROWSe);
+            const double* wc = &s_w[(c / CS_SUPER) & 1][(c % CS_SUPER) * ROWSe];
             if (owner) {
-                for (int r = 0; r < rows; ++r) acc = __dadd_rn(acc, __dmul_rn(s_x[st][r][tid], wc[r]));
-            } else if (tid == CS_THREADS - 1 && ft == 0) {
+                const double* xs = &s_x[c % CS_ST][tid];
+                for (int r = 0; r < rows; ++r) acc = __dadd_rn(acc, __dmul_rn(xs[r * FTe], wc[r]));
+            } else if (tid == CS_THREADS - 1 && first) {
                 for (int r = 0; r < rows; ++r) wsum = __dadd_rn(wsum, wc[r]);
             }
             __syncthreads();     // the chunk is consumed before its buffers are refilled
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (ft == 0) {
+        if (first) {
             if (tid == CS_THREADS - 1) s_wsum = wsum;
             __syncthreads();
+            first = false;
         }
         const double ws = s_wsum;
         if (MODE == CM_MINIBATCH) {
@@ -182,7 +247,7 @@ __global__ void __launch_bounds__(CsGeom<CS_FT>::THREADS, CS_FT == 256 ? 4 : 5)
             out_wx[k * D + col0 + tid] = acc;
         }
     }
-    if (tid == 0) {
+    if (tid == 0 && j == 0) {
         const double ws = s_wsum;
         if (MODE == CM_MINIBATCH) { if (ws > 0.0) out_w[k] = __dadd_rn(count0, ws); }
         else out_w[k] = ws;
@@ -249,7 +314,7 @@ static int centroid_run(const double* X, int64_t N, int D, int64_t ldx, const do
     Carver cv(workspace, workspace_bytes);
     uint64_t* keys = cv.take<uint64_t>((size_t)(N > 0 ? N : 1));
     uint32_t* vals = cv.take<uint32_t>((size_t)(N > 0 ? N : 1));
-    (void)cv.take<int32_t>((size_t)sumK + 2);   // (kept in the layout: mwe_centroid_workspace_bytes is part of the ABI)
+    int32_t* order = cv.take<int32_t>((size_t)sumK + 2);
     int32_t* seg_start = cv.take<int32_t>((size_t)sumK + 2);
     const size_t sort_bytes = sort_workspace_bytes(N);
     void* sort_ws = cv.take<char>(sort_bytes);
@@ -267,17 +332,20 @@ static int centroid_run(const double* X, int64_t N, int D, int64_t ldx, const do
     } else {
         MWE_CHECK_CUDA(cudaMemsetAsync(seg_start, 0, (size_t)(sumK + 2) * sizeof(int32_t), s));
     }
+    MWE_CHECK_CUDA(launch_pdl(centroid_order_kernel, dim3(1), dim3(1024), 0, s, seg_start, (int32_t)sumK, order));
     const bool vec2 = (D % 2 == 0) && (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
     const bool wide = D > 96;
-    const dim3 g((unsigned)sumK);
+    // wide accumulate launches carry the extra items of the split clusters (at most N / CS_BIG of them)
+    const int64_t max_big = (wide && MODE == CM_ACCUMULATE) ? std::min<int64_t>(sumK, N / CS_BIG) : 0;
+    const dim3 g((unsigned)(sumK + max_big * (CS_SPLIT - 1)));
     if (wide) {
         const dim3 b(CsGeom<256>::THREADS);
-        if (vec2) MWE_CHECK_CUDA(launch_pdl(centroid_sum_kernel<MODE, 2, 256>, g, b, 0, s, X, ldx, D, w, vs, seg_start, out_wx, out_w));
-        else MWE_CHECK_CUDA(launch_pdl(centroid_sum_kernel<MODE, 1, 256>, g, b, 0, s, X, ldx, D, w, vs, seg_start, out_wx, out_w));
+        if (vec2) MWE_CHECK_CUDA(launch_pdl(centroid_sum_kernel<MODE, 2, 256>, g, b, 0, s, X, ldx, D, w, vs, seg_start, order, (int32_t)sumK, out_wx, out_w));
+        else MWE_CHECK_CUDA(launch_pdl(centroid_sum_kernel<MODE, 1, 256>, g, b, 0, s, X, ldx, D, w, vs, seg_start, order, (int32_t)sumK, out_wx, out_w));
     } else {
         const dim3 b(CsGeom<64>::THREADS);
-        if (vec2) MWE_CHECK_CUDA(launch_pdl(centroid_sum_kernel<MODE, 2, 64>, g, b, 0, s, X, ldx, D, w, vs, seg_start, out_wx, out_w));
-        else MWE_CHECK_CUDA(launch_pdl(centroid_sum_kernel<MODE, 1, 64>, g, b, 0, s, X, ldx, D, w, vs, seg_start, out_wx, out_w));
+        if (vec2) MWE_CHECK_CUDA(launch_pdl(centroid_sum_kernel<MODE, 2, 64>, g, b, 0, s, X, ldx, D, w, vs, seg_start, order, (int32_t)sumK, out_wx, out_w));
+        else MWE_CHECK_CUDA(launch_pdl(centroid_sum_kernel<MODE, 1, 64>, g, b, 0, s, X, ldx, D, w, vs, seg_start, order, (int32_t)sumK, out_wx, out_w));
     }
     return MWE_OK;
 }

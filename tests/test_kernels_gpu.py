@@ -300,6 +300,41 @@ def test_lloyd_accumulate_and_finalize():
     assert np.array_equal(c.cpu().numpy(), new)
 
 
+@pytest.mark.parametrize("D", [256, 250, 257, 1100, 130])
+def test_accumulate_skewed_cluster_sizes_bit_exact(D):
+    """Clusters of >= 2048 members are split over several CTAs by feature columns (64-column blocks up to D = 768,
+    256-column blocks above) and scheduled first: every (cluster, feature) sum must still be the sequential
+    sample-order sum, bit for bit, next to small and empty clusters."""
+    ops = _ops()
+    rng = np.random.default_rng(1234 + D)
+    N, K = 9000, 9
+    labels = rng.choice([1, 4, 6, 7, 8], size=N, p=[0.55, 0.30, 0.1, 0.04, 0.01]).astype(np.int64)   # 0, 2, 3, 5 empty
+    X = rng.normal(size=(N, D)) * 10.0 ** rng.integers(-3, 4, size=(N, 1))
+    w = np.exp(rng.normal(0, 2, size=N))
+    sums = np.zeros((K, D)); wsum = np.zeros(K)
+    for k in range(K):
+        rows = np.flatnonzero(labels == k)
+        acc = np.zeros(D); a = 0.0
+        for i in rows:
+            acc = acc + X[i] * w[i]
+            a += w[i]
+        sums[k], wsum[k] = acc, a
+    for weights in (w, None):
+        sum_wx, sum_w = ops.centroid_accumulate(t(X), None if weights is None else t(weights), t(labels), K)
+        if weights is None:
+            ref = np.zeros((K, D))
+            for k in range(K):
+                acc = np.zeros(D)
+                for i in np.flatnonzero(labels == k):
+                    acc = acc + X[i]
+                ref[k] = acc
+            assert np.array_equal(sum_wx.cpu().numpy(), ref)
+            assert np.array_equal(sum_w.cpu().numpy(), np.bincount(labels, minlength=K).astype(float))
+        else:
+            assert np.array_equal(sum_wx.cpu().numpy(), sums)
+            assert np.array_equal(sum_w.cpu().numpy(), wsum)
+
+
 # ------------------------------------------------------------------ K3
 def _flux_case(rng, n, iters, segs):
     per = []
