@@ -143,7 +143,7 @@ def test_discretization_pinned_source_path_equals_staged_path(monkeypatch):
         for b in range(cfg.n_bins):
             clusters.cluster_models[b].cluster_centers_ = centers[b]
         clusters.cluster_args["gpu_chunk_bytes"] = 8 << 20          # several chunks
-        model.clusters = clusters; model.n_clusters = cfg.n_clusters; model.pre_discretization_model = model
+        model.clusters = clusters; model.n_clusters = cfg.n_clusters
         model.launch_ray_discretization()
         model.get_fluxMatrix(n_lag=0, first_iter=0)
         return model

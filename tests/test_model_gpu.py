@@ -334,7 +334,6 @@ def test_discretization_with_device_projection_matches_host_projection():
             clusters.cluster_models[b].cluster_centers_ = proj_centers[b]
         model.clusters = clusters
         model.n_clusters = cfg.n_clusters
-        model.pre_discretization_model = model
         model.launch_ray_discretization()
         labels.append(np.concatenate(model.pair_dtrajs))
     same = labels[0] == labels[1]

@@ -20,7 +20,7 @@ for b in range(cfg.n_bins):
     clusters.cluster_models[b].cluster_centers_ = centers[b]
 import os
 if os.environ.get('CHUNK_MB'): clusters.cluster_args['gpu_chunk_bytes'] = int(os.environ['CHUNK_MB']) << 20
-model.clusters = clusters; model.n_clusters = cfg.n_clusters; model.pre_discretization_model = model
+model.clusters = clusters; model.n_clusters = cfg.n_clusters
 
 def once():
     t0 = time.perf_counter()
