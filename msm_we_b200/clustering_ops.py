@@ -88,6 +88,7 @@ def lloyd_fit(X_dev, w_dev, bins_dev, centers_dev, bin_offset_dev, max_k, n_iter
     labels = None
     sumK, D = centers_dev.shape
     sums = torch.empty(sumK * (D + 1), dtype=torch.float64, device=centers_dev.device)   # sum_wx | sum_w: one exchange
+    offs_host = bin_offset_dev.cpu().numpy() if relocate_empty else None
     for _ in range(n_iter):
         labels = ops.assign_stratified(X_dev, bins_dev, flags_dev, centers_dev, ops.centers_sqnorm(centers_dev),
                                        bin_offset_dev, max_k, path=path, errors=errors)
@@ -97,7 +98,8 @@ def lloyd_fit(X_dev, w_dev, bins_dev, centers_dev, bin_offset_dev, max_k, n_iter
 
             dist.all_reduce(sums, group=group)
         if relocate_empty:
-            _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bins_dev, flags_dev, bin_offset_dev, sum_wx, sum_w, group)
+            _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bins_dev, flags_dev, bin_offset_dev, sum_wx, sum_w, group,
+                                     offs_host=offs_host)
         ops.lloyd_finalize(sum_wx, sum_w, centers_dev)
     return labels
 
@@ -107,7 +109,8 @@ def lloyd_fit(X_dev, w_dev, bins_dev, centers_dev, bin_offset_dev, max_k, n_iter
 EXACT_ORDER_MAX_POINTS = 1 << 16
 
 
-def _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bins_dev, flags_dev, bin_offset_dev, sum_wx, sum_w, group):
+def _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bins_dev, flags_dev, bin_offset_dev, sum_wx, sum_w, group,
+                             offs_host=None):
     """sklearn's ``_relocate_empty_clusters_dense`` per WE-bin model, applied to the (all-reduced) partial sums before
     the mean: a cluster that received no weight takes the point farthest from its own centre, which leaves its old
     cluster.
@@ -131,10 +134,17 @@ def _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bins_dev, flags_
     sw = sum_w.cpu().numpy()                                                     # (1)
     if (sw != 0).all():
         return False
-    offs = bin_offset_dev.cpu().numpy()
+    offs = bin_offset_dev.cpu().numpy() if offs_host is None else offs_host
     nbins = len(offs) - 1
-    affected = [b for b in range(nbins)
-                if offs[b + 1] > offs[b] and (sw[offs[b]:offs[b + 1]] == 0).any() and sw[offs[b]:offs[b + 1]].sum() != 0]
+    # bins with a model (>= 1 cluster) that received weight and own an empty cluster; the non-empty cluster ranges tile
+    # [0, sumK), so one reduceat per quantity covers them (weights are non-negative: the sum is 0 iff every entry is)
+    fitted = np.flatnonzero(np.diff(offs) > 0)
+    if fitted.size == 0:
+        return False
+    first = offs[fitted]
+    has_empty = np.add.reduceat((sw == 0).astype(np.int64), first) > 0
+    has_weight = np.add.reduceat(sw, first) != 0
+    affected = fitted[has_empty & has_weight].tolist()
     if not affected:          # (a model without any point is not being fitted at all)
         return False
     world, rank = 1, 0
@@ -146,7 +156,7 @@ def _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bins_dev, flags_
     D = X_dev.shape[1]
     mask = torch.zeros(nbins, dtype=torch.bool, device=dev)
     mask[torch.tensor(affected, device=dev)] = True
-    sel = mask[bins_dev.long()]
+    sel = mask[bins_dev]
     if flags_dev is not None:
         sel &= flags_dev == 0
     mark("host-affected")
