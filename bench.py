@@ -702,13 +702,15 @@ def run_e2e(cfg, lloyd, rank, world, dev, e2e_iters=0):
     finally:
         _pinning.PINS.enabled = enabled
     M = cfg.n_clusters + 2
-    h2d = frames * (2 * (cfg.dim + 1) * 8) + frames * (2 * 8 + 8 + 2 * 8) + (frames * (cfg.dim + 1) * 8 if lloyd else 0)
+    # features of parent and child frames + pcoords (the child rows cross once: lloyd_refine_clusters leaves them on the
+    # device for the discretization that follows, single use), flux inputs, the Lloyd pass's own parent pcoords
+    h2d = frames * (2 * (cfg.dim + 1) * 8) + frames * (2 * 8 + 8 + 2 * 8) + (frames * 8 if lloyd else 0)
     d2h = frames * 2 * (8 + 4 + 1) + M * M * 8 + (cfg.n_clusters * cfg.dim * 8 if lloyd else 0)
     return {"value": frames * world * 3 / steady, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "frames_per_step": frames * world,
             "first_call_value": frames * world / first, "staged_value": frames * world * 2 / staged,
             "api": ("modelWE.lloyd_refine_clusters + " if lloyd else "") + "modelWE.launch_ray_discretization + get_fluxMatrix, "
-                   "numpy in / numpy out; value = steady state (source arrays page-locked in place), first_call_value = cold "
+                   "numpy in / numpy out, each frame crosses PCIe once per pass; value = steady state (source arrays page-locked in place), first_call_value = cold "
                    "pass incl. cudaHostRegister, staged_value = every array through pinned staging rows"}
 
 

@@ -31,6 +31,40 @@ from ..stratified_clustering import StratifiedClusters
 SUPPORTED_MAPPERS = set(_NATIVE_MAPPERS)
 
 DEFAULT_CHUNK_BYTES = 64 << 20
+DEFAULT_RESIDENT_BYTES = 8 << 30      # child feature rows lloyd_refine_clusters may leave on the device for the next pass
+
+
+class _ResidentChildRows:
+    """Feature rows of end-of-segment frames that ``lloyd_refine_clusters`` already shipped to the device, kept for the
+    ``launch_ray_discretization`` that follows it (the reference's order: cluster, then discretize the same frames,
+    _clustering.py:142-226 -> :1144) so those frames cross PCIe once.  Single use: the discretization pass drops it."""
+
+    def __init__(self, model, X, rows):
+        self.X, self.rows = X, rows
+        self.key = self.key_of(model)
+
+    @staticmethod
+    def key_of(model):
+        feat = model.processCoordinates
+        return (id(model.iteration_source), id(model.coordinates), getattr(feat, "__func__", feat))
+
+    def lookup(self, model, it, s, D):
+        if self.key != self.key_of(model) or self.X.shape[1] != D:
+            return None
+        hit = self.rows.get(it)
+        return self.X[hit[0]:hit[0] + s] if hit is not None and hit[1] == s else None
+
+    # a copy or a pickle of the model does not take the device rows along
+    def __deepcopy__(self, memo):
+        return None
+
+    def __reduce__(self):
+        return (_nothing, ())
+
+
+def _nothing():
+    return None
+
 
 _STAGING_POOL = None
 
@@ -132,6 +166,7 @@ class ClusteringMixin:
     cluster_structure_weights = None
     pre_discretization_model = None
     post_cluster_model = None
+    _resident_child_rows = None
 
     do_stratified_ray_discretization = _RemoteShim(_do_stratified_ray_discretization)
 
@@ -408,6 +443,10 @@ class ClusteringMixin:
         if cur:
             chunks.append(cur)
 
+        resident = getattr(self, "_resident_child_rows", None)
+        if resident is not None and (projection is not None or resident.key != resident.key_of(self)):
+            resident = None
+
         stream = torch.cuda.current_stream()
         slots = [dict(event=None, host=None, n=0), dict(event=None, host=None, n=0)]
         inflight = []   # (chunk, n, labels_host, bins_host, flags_host, nan_host, done_event)
@@ -430,6 +469,8 @@ class ClusteringMixin:
 
             def featurise_pair(item):
                 parent_coords, child_coords = self.iter_coordinate_pair(item[0])
+                if resident is not None and resident.lookup(self, item[0], item[1], D) is not None:
+                    return np.asarray(transform(featurise(parent_coords))), None     # child rows are on the device already
                 fp, fc = featurise(parent_coords), featurise(child_coords)
                 if projection is None:
                     fp, fc = transform(fp), transform(fc)
@@ -480,7 +521,11 @@ class ClusteringMixin:
                     pos += s
                     continue
                 fp, fc = feats[k]
+                if fc is None:
+                    X[n + pos:n + pos + s].copy_(resident.lookup(self, it, s, D))
                 for off, feat in ((pos, fp), (n + pos, fc)):
+                    if feat is None:
+                        continue
                     if feat.shape != (s, Din):
                         raise ValueError(f"featurised coordinates of iteration {it} have shape {feat.shape}, expected {(s, Din)}")
                     if source_owned(feat, rec) and PINS.ensure(feat):
@@ -570,6 +615,7 @@ class ClusteringMixin:
                 collect(inflight[-1])
             dev.check_errors()
 
+        self._resident_child_rows = None       # single use: the next pass ships its own frames
         self.dtrajs = [d for d in dtrajs if d is not None]
         self.pair_dtrajs = [d for d in pair_dtrajs if d is not None]
         log.debug("Discretization complete")
@@ -614,9 +660,11 @@ class ClusteringMixin:
         stage_rows = max(counts)
         stage, stage_ev, n_staged = None, [None, None], 0
         pos = 0
+        row_of_iter = {}
         for it, s in zip(iters, counts):
             if s == 0:
                 continue
+            row_of_iter[it] = (pos, s)
             rec = self._record(it)
             feat = self.processCoordinates(self._as_structures(rec.child_coords))
             if projection is None:
@@ -652,6 +700,12 @@ class ClusteringMixin:
         for b, m in enumerate(clusters.cluster_models):
             if hasattr(m, "cluster_centers_") and offs[b + 1] > offs[b]:
                 m.cluster_centers_ = np.ascontiguousarray(centers_h[offs[b]:offs[b + 1]])
+        # the discretization that normally follows labels the same end-of-segment frames: leave them on the device
+        # for it when they are small enough (features after ``coordinates.transform``; not with a device projection,
+        # whose input rows are what the discretization ships)
+        budget = int(clusters.cluster_args.get("gpu_resident_bytes", DEFAULT_RESIDENT_BYTES))
+        self._resident_child_rows = (_ResidentChildRows(self, X, row_of_iter)
+                                     if projection is None and X.numel() * 8 <= budget else None)
         return n
 
     # ------------------------------------------------------------------------------------------

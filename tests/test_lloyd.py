@@ -130,6 +130,54 @@ def test_model_lloyd_refine_clusters_matches_sklearn_per_bin(monkeypatch, gpu):
 
 
 @pytest.mark.parametrize("gpu", BACKENDS)
+def test_discretization_after_lloyd_reuses_the_resident_child_rows(monkeypatch, gpu):
+    """lloyd_refine_clusters leaves the end-of-segment feature rows on the device for the discretization that follows
+    (single use); labels must equal a pass that ships everything itself, and a copy of the model takes no device rows."""
+    import copy, pickle
+
+    _backend(monkeypatch, gpu)
+    import test_model_gpu as T
+    from msm_we_b200.stratified_clustering import StratifiedClusters
+
+    def prepared(refine, **cluster_args):
+        cfg, model, mapper, its, centers, basis, target = T._build("tiny")
+        clusters = StratifiedClusters(mapper, model, cfg.k_per_bin, [])
+        clusters.cluster_args.update(cluster_args)
+        for b in range(cfg.n_bins):
+            clusters.cluster_models[b].cluster_centers_ = centers[b].copy()
+        model.clusters = clusters
+        model.n_clusters = cfg.n_clusters
+        if refine:
+            model.lloyd_refine_clusters(2, iters_to_use=refine)
+        return cfg, model
+
+    cfg, model = prepared(None)
+    every = list(range(1, model.maxIter))
+    some = every[1::2]                                   # only part of the iterations resident
+    results = []
+    for refine, args in ((every, {}), (some, {}), (every, {"gpu_resident_bytes": 0})):
+        cfg, m = prepared(refine, **args)
+        if args:
+            assert m._resident_child_rows is None        # over budget: nothing kept
+        else:
+            assert m._resident_child_rows is not None and set(m._resident_child_rows.rows) == set(refine)
+            assert copy.deepcopy(m._resident_child_rows) is None and pickle.loads(pickle.dumps(m._resident_child_rows)) is None
+        centres = [c.cluster_centers_.copy() for c in m.clusters.cluster_models]
+        m.launch_ray_discretization()
+        assert m._resident_child_rows is None            # consumed
+        results.append((refine, centres, [d.copy() for d in m.pair_dtrajs]))
+    # reference for each: the same refined centres, every frame shipped by the discretization itself
+    for refine, centres, pairs in results:
+        cfg, m = prepared(None)
+        for c, v in zip(m.clusters.cluster_models, centres):
+            c.cluster_centers_ = v
+        m.launch_ray_discretization()
+        assert len(pairs) == len(m.pair_dtrajs)
+        for a, b in zip(pairs, m.pair_dtrajs):
+            assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("gpu", BACKENDS)
 def test_lloyd_relocation_device_ranked_branch_relocates_the_same_points(monkeypatch, gpu):
     """Large models rank the farthest points on the device (clustering_ops.EXACT_ORDER_MAX_POINTS): the same points are
     relocated as by sklearn; only the cluster index that receives each of them may be permuted within the bin."""
