@@ -700,6 +700,7 @@ class ClusteringMixin:
         for b, m in enumerate(clusters.cluster_models):
             if hasattr(m, "cluster_centers_") and offs[b + 1] > offs[b]:
                 m.cluster_centers_ = np.ascontiguousarray(centers_h[offs[b]:offs[b + 1]])
+        clusters.adopt_device_centers(centers)       # the device snapshot follows without a second upload
         # the discretization that normally follows labels the same end-of-segment frames: leave them on the device
         # for it when they are small enough (features after ``coordinates.transform``; not with a device projection,
         # whose input rows are what the discretization ships)

@@ -194,6 +194,20 @@ class BinClusterModel:
         return f"BinClusterModel(n_clusters={self.n_clusters}, fitted={hasattr(self, 'cluster_centers_')})"
 
 
+_HASH_POOL = None
+
+
+def _hash_pool():
+    global _HASH_POOL
+    if _HASH_POOL is None:
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+
+        n = min(8, max(1, (os.cpu_count() or 2) // 2))
+        _HASH_POOL = ThreadPoolExecutor(max_workers=n, thread_name_prefix="mwe-hash") if n > 1 else False
+    return _HASH_POOL or None
+
+
 class StratifiedClusters:
     """reference: msm_we/stratified_clustering.py:6-212 (same constructor, attributes and methods)."""
 
@@ -232,15 +246,19 @@ class StratifiedClusters:
         return [getattr(m, "cluster_centers_", None) for m in self.cluster_models]
 
     def _fingerprint(self):
-        parts = []
-        for m in self.cluster_models:
+        # the centres are small (K x D per bin): hash ALL their bytes, so an in-place edit is never missed.  20 MB at
+        # config-5 size: zlib releases the GIL, so the per-bin hashes run on a few threads (6 ms -> 1 ms)
+        def one(m):
             c = getattr(m, "cluster_centers_", None)
             if c is None:
-                parts.append(None)
-            else:
-                c = np.asarray(c)
-                # the centres are small (K x D per bin): hash all of them, so an in-place edit is never missed
-                parts.append((c.shape, zlib.crc32(np.ascontiguousarray(c).view(np.uint8).reshape(-1))))
+                return None
+            c = np.asarray(c)
+            return (c.shape, zlib.crc32(np.ascontiguousarray(c).view(np.uint8).reshape(-1)))
+
+        models = self.cluster_models
+        nbytes = sum(getattr(getattr(m, "cluster_centers_", None), "nbytes", 0) for m in models)
+        pool = _hash_pool() if nbytes > (1 << 20) else None
+        parts = list(pool.map(one, models)) if pool is not None else [one(m) for m in models]
         model = self.model
         bounds = (np.asarray(model.basis_pcoord_bounds).tobytes(), np.asarray(model.target_pcoord_bounds).tobytes())
         return (tuple(parts), tuple(sorted(self.we_remap.items())), id(self.bin_mapper), bounds)
@@ -256,6 +274,18 @@ class StratifiedClusters:
                                           self.model.pcoord_ndim)
             self._device_key = key
         return self._device
+
+    def adopt_device_centers(self, centers_dev):
+        """The caller refined the centres ON the device and has already written the same values to every
+        ``cluster_centers_``: keep the device snapshot (same shapes) instead of re-uploading them on the next use."""
+        from . import ops
+
+        dev = self._device
+        if dev is None or tuple(centers_dev.shape) != tuple(dev.centers.shape):
+            return
+        dev.centers.copy_(centers_dev)
+        dev.csq = ops.centers_sqnorm(dev.centers)
+        self._device_key = self._fingerprint()
 
     def predict(self, coords):
         """Same contract as the reference's ``predict`` (stratified_clustering.py:101-212): bins come from
