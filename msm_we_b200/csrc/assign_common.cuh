@@ -33,6 +33,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (++spins > AS_SPIN_LIMIT) __trap();  // never hang the GPU on a protocol bug
     }
 }
+// the same three with a precomputed 32-bit shared-memory address: the generic -> shared conversion of a pointer costs
+// 4-5 instructions per call, which shows in loops that are bound by instruction issue (assign_tc.cu, conversion warps)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar32) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar32) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar32, uint32_t parity) {
+    uint32_t done = 0;
+    int spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar32), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (++spins > AS_SPIN_LIMIT) __trap();
+    }
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar32) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar32) : "memory");
+}
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -216,6 +216,16 @@ __device__ __forceinline__ void timed_wait(uint64_t* bar, uint32_t parity, long 
     }
 }
 
+__device__ __forceinline__ void timed_wait(uint32_t bar32, uint32_t parity, long long& acc, bool on) {
+    if (on) {
+        const long long t0 = clock64();
+        mbar_wait(bar32, parity);
+        acc += clock64() - t0;
+    } else {
+        mbar_wait(bar32, parity);
+    }
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(const TcParams q) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -620,6 +630,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Par
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int n_raw = q.nstages_raw, n_a = qq.n_a, n_b = qq.n_b;
+    const int ablate = PROF ? qq.ablate : 0;          // measurement switches exist only in the profiled instantiation
     const int ng = q.n_pad / 8;
     const uint32_t b_bytes = (uint32_t)(2 * ng * TC_SBO);
     unsigned char* b_base = smem_raw;
@@ -697,7 +708,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Par
                         tc_fence_after();
                         const uint32_t a_hi = tmem_base + qq.a_col0 + (uint32_t)(as * TC2_A_STAGE_COLS), a_lo = a_hi + TC_KC;
                         const uint32_t b_hi = smem_u32(b_base + (size_t)bs * b_bytes), b_lo = b_hi + (uint32_t)(ng * TC_SBO);
-                        if (!(qq.ablate & 1))
+                        if (!(ablate & 1))
 #pragma unroll
                         for (int j = 0; j < TC_KC / 8; ++j) {
                             const uint32_t ko = (uint32_t)(j * 2 * TC_LBO);
@@ -727,7 +738,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Par
                         timed_wait(&b_empty[bs], bph ^ 1u, w0, prof);
                         unsigned char* dst = b_base + (size_t)bs * b_bytes;
                         const unsigned char* src = q.bprep + ((size_t)(w.bin * ncb + cb) * nch + kc) * b_bytes;
-                        if (qq.ablate & 4) {
+                        if (ablate & 4) {
                             mbar_arrive(&b_full[bs]);          // measurement only: no centre-block traffic
                         } else {
                             mbar_expect_tx(&b_full[bs], b_bytes);
@@ -822,8 +833,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Par
         TileWalk<TC_TP> iw{0, 0, 0, 0, 0, 0, 0, 0};       // tile whose copies are being issued
         iw.load(tt, my_tiles);
         TileWalk<TC_TP> nw = iw;                           // tile whose point indices are being prefetched
-        const double* xrow[XQ];                            // k-chunk 0 of this thread's rows of the tile being issued
-        int32_t pidx_next[XQ];
+        uint32_t xrow[XQ];                                 // point indices of this thread's rows of the tile being issued
+        int32_t pidx_next[XQ];                             // (an index, not a pointer: one IMAD.WIDE per copy, no register-pair moves)
+        const char* const Xb = reinterpret_cast<const char*>(p.X + kcol0);
+        const uint32_t ldx8 = (uint32_t)p.ldx * 8u;
         auto fetch = [&](const TileWalk<TC_TP>& t) {
 #pragma unroll
             for (int k = 0; k < XQ; ++k) {
@@ -833,7 +846,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Par
         };
         auto set_rows = [&]() {
 #pragma unroll
-            for (int k = 0; k < XQ; ++k) xrow[k] = p.X + (int64_t)pidx_next[k] * p.ldx + kcol0;
+            for (int k = 0; k < XQ; ++k) xrow[k] = (uint32_t)pidx_next[k];
         };
         fetch(iw);
         set_rows();
@@ -843,32 +856,45 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Par
         const uint32_t raw32 = smem_u32(raw_base) + (uint32_t)(((cwp * CR + crs) * TC_RAW_LD + kcol0) * 8);
         const uint32_t mean32 = smem_u32(raw_base) + (uint32_t)((TC_TP * TC_RAW_LD + 2 * lane) * 8);
         const double* mean_src = q.mean + (size_t)iw.bin * q.d_pad + 2 * lane;
+        // one opaque base register + constant offsets (left to itself the compiler re-derives every barrier address from
+        // the shared-window base at each use: 4 instructions per wait / arrive)
+        uint32_t bar0;
+        asm volatile("mov.u32 %0, %1;" : "=r"(bar0) : "r"(smem_u32(raw_full)));
+        const uint32_t raw_full32 = bar0, raw_empty32 = bar0 + (smem_u32(raw_empty) - smem_u32(raw_full)),
+                       a_full32 = bar0 + (smem_u32(a_full) - smem_u32(raw_full)),
+                       a_empty32 = bar0 + (smem_u32(a_empty) - smem_u32(raw_full)),
+                       xn_full32 = bar0 + (smem_u32(xn_full) - smem_u32(raw_full)),
+                       xn_empty32 = bar0 + (smem_u32(xn_empty) - smem_u32(raw_full));
         int is = 0, ikc = 0, icb = 0;
         uint32_t iphase = 0;
         int64_t issued = 0;
         auto issue_one = [&]() {
-            timed_wait(&raw_empty[is], iphase ^ 1u, w2, prof);
+            timed_wait(raw_empty32 + 8u * (uint32_t)is, iphase ^ 1u, w2, prof);
             const uint32_t dst = raw32 + (uint32_t)is * (uint32_t)TC_RAW_BYTES;
             const int k0 = ikc * TC_KC;
             if (FULLK) {
+                const char* const Xk = Xb + (size_t)k0 * 8;
 #pragma unroll
                 for (int k = 0; k < XQ; ++k) {
-                    if (VEC == 2) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(k * RPI * TC_RAW_LD * 8)), "l"(xrow[k] + k0) : "memory");
-                    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (uint32_t)(k * RPI * TC_RAW_LD * 8)), "l"(xrow[k] + k0) : "memory");
+                    const char* src = Xk + (size_t)xrow[k] * ldx8;
+                    if (VEC == 2) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(k * RPI * TC_RAW_LD * 8)), "l"(src) : "memory");
+                    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (uint32_t)(k * RPI * TC_RAW_LD * 8)), "l"(src) : "memory");
                 }
             } else {
                 int vbytes = (p.D - k0 - kcol0) * 8;
                 vbytes = vbytes < 0 ? 0 : (vbytes > VEC * 8 ? VEC * 8 : vbytes);
-                const int koff = vbytes ? k0 : 0;          // (a zero-size copy still gets an in-range source address)
+                const char* const Xk = vbytes ? Xb + (size_t)k0 * 8 : reinterpret_cast<const char*>(p.X);   // (a zero-size copy still gets an in-range source address)
+                const uint32_t stride8 = vbytes ? ldx8 : 0u;
 #pragma unroll
                 for (int k = 0; k < XQ; ++k) {
-                    if (VEC == 2) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)(k * RPI * TC_RAW_LD * 8)), "l"(xrow[k] + koff), "r"(vbytes) : "memory");
-                    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + (uint32_t)(k * RPI * TC_RAW_LD * 8)), "l"(xrow[k] + koff), "r"(vbytes) : "memory");
+                    const char* src = Xk + (size_t)xrow[k] * stride8;
+                    if (VEC == 2) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)(k * RPI * TC_RAW_LD * 8)), "l"(src), "r"(vbytes) : "memory");
+                    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + (uint32_t)(k * RPI * TC_RAW_LD * 8)), "l"(src), "r"(vbytes) : "memory");
                 }
             }
             if (cwp == 0 && lane < 16)   // the bin-mean chunk rides along (zero padded past D: always 16 x 16 B)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(mean32 + (uint32_t)is * (uint32_t)TC_RAW_BYTES), "l"(mean_src + k0) : "memory");
-            cp_async_arrive_noinc(&raw_full[is]);
+            cp_async_arrive_noinc(raw_full32 + 8u * (uint32_t)is);
             if (++is == n_raw) { is = 0; iphase ^= 1u; }
             ++issued;
             if (++ikc == nch) {
@@ -893,14 +919,15 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Par
         float xc = 0.f;
         for (int64_t step = 0; step < total_steps; ++step) {
             if (issued < total_steps) issue_one();
-            timed_wait(&raw_full[rs], rphase, w0, prof);
+            timed_wait(raw_full32 + 8u * (uint32_t)rs, rphase, w0, prof);
             const uint32_t so = (uint32_t)rs * (uint32_t)TC_RAW_BYTES;
             float hi[TC2_KSUB], lo[TC2_KSUB];
-            if (qq.ablate & 2) {
+            if (ablate & 2) {
 #pragma unroll
                 for (int e = 0; e < TC2_KSUB; ++e) hi[e] = lo[e] = 0.f;
             } else {
                 double2 xv[TC2_KSUB / 2];
+                float xs = xc;
 #pragma unroll
                 for (int e = 0; e < TC2_KSUB / 2; ++e)
                     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xv[e].x), "=d"(xv[e].y) : "r"(src32 + so + 16u * e));
@@ -913,12 +940,13 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Par
                     hi[2 * e + 1] = tf32_rna(x1);
                     lo[2 * e] = x0 - hi[2 * e];
                     lo[2 * e + 1] = x1 - hi[2 * e + 1];
-                    if (ccb == 0) xc = fmaf(x0, x0, fmaf(x1, x1, xc));
+                    xs = fmaf(x0, x0, fmaf(x1, x1, xs));
                 }
+                if (ccb == 0) xc = xs;                     // (one select, not one per pair)
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&raw_empty[rs]);        // the staged fp64 chunk is in registers
-            timed_wait(&a_empty[as], aphase ^ 1u, w1, prof);   // the MMAs that read this TMEM stage have completed
+            if (lane == 0) mbar_arrive(raw_empty32 + 8u * (uint32_t)rs);   // the staged fp64 chunk is in registers
+            timed_wait(a_empty32 + 8u * (uint32_t)as, aphase ^ 1u, w1, prof);   // the MMAs that read this TMEM stage have completed
             tc_fence_after();
             const uint32_t ta = ta0 + (uint32_t)(as * TC2_A_STAGE_COLS);
             if (TC2_KSUB == 8) {
@@ -931,7 +959,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Par
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&a_full[as]);
+            if (lane == 0) mbar_arrive(a_full32 + 8u * (uint32_t)as);
             if (++rs == n_raw) { rs = 0; rphase ^= 1u; }
             if (++as == n_a) { as = 0; aphase ^= 1u; }
             if (++ckc == nch) {
@@ -940,12 +968,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) assign_tc2_kernel(const Tc2Par
                     // partial centred ||x'||^2 of this thread's row -> epilogue (fp32 sums of fp32 roundings, inflated a little)
                     ccb = 0;
                     const int xbuf = cti & 1;
-                    mbar_wait(&xn_empty[xbuf], (xbuf ? xph1 : xph0) ^ 1u);
+                    mbar_wait(xn_empty32 + 8u * (uint32_t)xbuf, (xbuf ? xph1 : xph0) ^ 1u);
                     if (xbuf) xph1 ^= 1u; else xph0 ^= 1u;
                     s_xn[xbuf][khalf][row] = xc * 1.0001f;
                     xc = 0.f;
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&xn_full[xbuf]);
+                    if (lane == 0) mbar_arrive(xn_full32 + 8u * (uint32_t)xbuf);
                     ++cti;
                 }
             }
