@@ -396,6 +396,61 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Few labels with many members each (the per-WE-bin maximum of the relocation step: 100 labels x 10^4 members): one
+// CTA per label instead of one warp.  Thread t takes members s+t, s+t+256, ...; fixed butterfly inside each warp, then
+// the eight warp partials in warp order: as deterministic as the kernel above, with a different (fixed) association.
+__global__ void __launch_bounds__(256)
+    label_stats_block_kernel(const double* __restrict__ v, int64_t ldv, const uint32_t* __restrict__ members,
+                             const int32_t* __restrict__ seg_start, int64_t n_labels, int64_t* __restrict__ count,
+                             double* __restrict__ sum, double* __restrict__ mn, double* __restrict__ mx) {
+    pdl_wait();
+    pdl_launch_dependents();
+    __shared__ double s_acc[8], s_lo[8], s_hi[8];
+    __shared__ long long s_c[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t k = blockIdx.x; k < n_labels; k += gridDim.x) {
+        const int32_t s = seg_start[k], e = seg_start[k + 1];
+        double acc = 0.0, lo = __longlong_as_double(0x7ff0000000000000LL), hi = __longlong_as_double(0xfff0000000000000LL);
+        long long c = 0;
+        for (int32_t m = s + (int32_t)threadIdx.x; m < e; m += 256) {
+            const double x = v[(int64_t)members[m] * ldv];
+            if (x == x) {
+                acc += x;
+                lo = fmin(lo, x);
+                hi = fmax(hi, x);
+                ++c;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+        }
+        if (lane == 0) {
+            s_acc[warp] = acc;
+            s_lo[warp] = lo;
+            s_hi[warp] = hi;
+            s_c[warp] = c;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) {
+                acc += s_acc[w];
+                lo = fmin(lo, s_lo[w]);
+                hi = fmax(hi, s_hi[w]);
+                c += s_c[w];
+            }
+            count[k] = c;
+            sum[k] = acc;
+            mn[k] = lo;
+            mx[k] = hi;
+        }
+        __syncthreads();
+    }
+}
+
 // Squared distance of listed points to their own centre (empty-cluster relocation of the Lloyd M step: sklearn moves an
 // empty cluster onto the point farthest from its centre, _k_means_common.pyx _relocate_empty_clusters_dense).  One warp
 // per listed point, lanes stride the features, fixed butterfly.
@@ -510,6 +565,11 @@ extern "C" int mwe_label_stats_f64(const double* values, int64_t ldv, const uint
     MWE_REQUIRE(n_labels >= 0 && ldv >= 1, "label_stats: bad shape");
     if (n_labels == 0) return MWE_OK;
     MWE_REQUIRE(values && members && seg_start && count && sum && vmin && vmax, "label_stats: null pointer");
+    if (n_labels <= 512) {   // few labels: a CTA each
+        MWE_CHECK_CUDA(launch_pdl(label_stats_block_kernel, dim3((unsigned)n_labels), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                                  values, ldv, members, seg_start, n_labels, count, sum, vmin, vmax));
+        return MWE_OK;
+    }
     int64_t blocks = (n_labels + 7) / 8;
     const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;

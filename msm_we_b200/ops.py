@@ -316,6 +316,9 @@ def label_stats(values, members, seg_start, n_labels):
     n = int(n_labels)
     count = torch.empty(n, dtype=torch.int64, device=dev)
     out = torch.empty((3, n), dtype=torch.float64, device=dev)
+    if values.numel() == 0:                      # no members anywhere: the kernel's answer for an empty label
+        count.zero_(); out[0].zero_(); out[1].fill_(float("inf")); out[2].fill_(float("-inf"))
+        return count, out[0], out[1], out[2]
     ldv = values.stride(0) if values.numel() > 1 else 1
     check(lib.mwe_label_stats_f64(_ptr(values), ldv, _ptr(members), _ptr(seg_start), n, _ptr(count), _ptr(out[0]),
                                   _ptr(out[1]), _ptr(out[2]), _stream()), "mwe_label_stats_f64")

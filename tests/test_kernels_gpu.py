@@ -335,6 +335,35 @@ def test_accumulate_skewed_cluster_sizes_bit_exact(D):
             assert np.array_equal(sum_w.cpu().numpy(), wsum)
 
 
+@pytest.mark.parametrize("n_labels,N", [(40, 60000), (2000, 60000), (7, 0)])
+def test_group_by_label_and_label_stats(n_labels, N):
+    """Stable group-by-label + NaN-skipping per-label count / sum / min / max (get_cluster_centers, relocation): both
+    launch shapes (a CTA per label for few labels, a warp per label otherwise), empty labels, NaN values, a column view."""
+    ops = _ops()
+    rng = np.random.default_rng(n_labels + N)
+    labels = rng.integers(0, n_labels, size=N).astype(np.int64)
+    labels[labels == 3] = 4                                   # label 3 stays empty
+    vals = rng.normal(size=(N, 3)) * 10.0 ** rng.integers(-2, 3, size=(N, 1))
+    vals[rng.random(N) < 0.01, 1] = np.nan
+    members, seg = ops.group_by_label(t(labels), n_labels)
+    mh, sh = members.cpu().numpy().astype(np.int64), seg.cpu().numpy()
+    assert sh[0] == 0 and sh[n_labels] == N
+    for k in range(n_labels):
+        assert np.array_equal(mh[sh[k]:sh[k + 1]], np.flatnonzero(labels == k))     # input order inside a label
+    V = t(vals)
+    count, ssum, vmin, vmax = ops.label_stats(V[:, 1], members, seg, n_labels)
+    count, ssum, vmin, vmax = (x.cpu().numpy() for x in (count, ssum, vmin, vmax))
+    for k in range(n_labels):
+        x = vals[labels == k, 1]
+        x = x[~np.isnan(x)]
+        assert count[k] == len(x)
+        if len(x):
+            assert vmin[k] == x.min() and vmax[k] == x.max()
+            assert abs(ssum[k] - x.sum()) <= 1e-12 * np.abs(x).sum()
+        else:
+            assert ssum[k] == 0.0 and vmin[k] == np.inf and vmax[k] == -np.inf
+
+
 # ------------------------------------------------------------------ K3
 def _flux_case(rng, n, iters, segs):
     per = []
