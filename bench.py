@@ -307,9 +307,9 @@ def launches_per_step(cfg, tc_path, lloyd, world):
     """Kernels of ours per step, counted from the launch sequences in csrc/ (confirmed by the ncu launch lists in
     profiles/)."""
     k1 = 2 + (3 if tc_path else 0) + 2                      # scan, scatter, [mean, split, csq], main, re-check
-    k2 = 2 + 1 + max(1, (int(np.ceil(np.log2(cfg.n_clusters + 1))) + 7) // 8) + 1      # keys, bounds, hist + passes, sum
-    per_lloyd = 1 + k1 + k2 + 1                            # csq + K1 + K2 + finalize
-    final = 1 + k1 + 1 + (1 + k3_passes(cfg.n_clusters + 2)) + 3 + 1      # K0, K1, keys, sort, mark/group/cell, divide|exchange
+    k2 = 2 + 1 + max(1, (int(np.ceil(np.log2(cfg.n_clusters + 1))) + 7) // 8) + 1 + 1  # keys, bounds, hist + passes, order, sum
+    per_lloyd = 1 + (1 + k1) + k2 + 1                      # csq + (bucket count + K1) + K2 + finalize (relocation kernels not counted)
+    final = 1 + k1 + 1 + (1 + k3_passes(cfg.n_clusters + 2)) + 3 + 1      # K0 (counts the buckets), K1, keys, sort, mark/group/cell, divide|exchange
     return (1 if lloyd else 0) + lloyd * per_lloyd + (1 if lloyd else 0) + final
 
 
