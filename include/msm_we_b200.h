@@ -173,6 +173,13 @@ MWE_API int mwe_group_by_label(const int64_t* label, int64_t N, int64_t n_labels
                                int32_t* seg_start_out, void* workspace, size_t workspace_bytes, void* stream);
 MWE_API int mwe_label_stats_f64(const double* values, int64_t ldv, const uint32_t* members, const int32_t* seg_start,
                                 int64_t n_labels, int64_t* count, double* sum, double* vmin, double* vmax, void* stream);
+/*   mwe_segment_topk_f64: for each of the n_sel listed groups (seg_ids, indices into seg_start) the k <= 8 largest
+ *     values[member] with their member indices, largest first, equal values in member order (= the head of a stable
+ *     descending sort of the group); groups with fewer than k (non-NaN) members are padded with index -1.  Picks the
+ *     farthest points of a WE-bin model that lost several clusters in one Lloyd iteration (sklearn
+ *     _relocate_empty_clusters_dense, _k_means_common.pyx; reached from msm_we/_hamsm/_clustering.py:289,491). */
+MWE_API int mwe_segment_topk_f64(const double* values, const uint32_t* members, const int32_t* seg_start,
+                                 const int32_t* seg_ids, int32_t n_sel, int k, int32_t* out_pos, double* out_val, void* stream);
 
 
 /* ---- K3: weighted transition scatter into the flux matrix -----------------------------------

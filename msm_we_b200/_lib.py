@@ -55,6 +55,7 @@ SIGNATURES = {
     "mwe_point_center_dist2_f64": (_int, [_p, _i64, _int, _p, _i64, _p, _p, _p, _p]),
     "mwe_group_by_label": (_int, [_p, _i64, _i64, _p, _p, _p, _sz, _p]),
     "mwe_label_stats_f64": (_int, [_p, _i64, _p, _p, _i64, _p, _p, _p, _p, _p]),
+    "mwe_segment_topk_f64": (_int, [_p, _p, _p, _p, _i32, _int, _p, _p, _p]),
     "mwe_flux_workspace_bytes": (_sz, [_i64]),
     "mwe_flux_accumulate_f64": (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _int, _p, _i64, _p, _p, _p, _p, _p, _p, _sz, _p, _p]),
     "mwe_lineage_colour": (_int, [_p, _p, _i64, _p, _i64, _p, _i64, _p, _p]),

@@ -216,22 +216,31 @@ def _relocate_empty_clusters(X_dev, w_dev, labels, centers_dev, bins_dev, flags_
                 local_pos[slot_first[i]:slot_first[i] + take] = rows[far]
                 local_d2[slot_first[i]:slot_first[i] + take] = dist2[far]
         else:
-            # large models: shipping whole distance lists to the host would dominate the Lloyd iteration.  The listed
-            # points are ordered on the device by (bin, distance descending) with two stable sorts and only each bin's
-            # first n_empty entries come back.  Same SET of relocated points as sklearn; they are handed to the bin's
-            # empty clusters in descending distance (sklearn: in the order numpy's introselect leaves them), so the
-            # relocated centres may sit at permuted cluster indices of that bin.
-            by_d = torch.argsort(d2_dev, descending=True, stable=True)
-            by_bin = torch.argsort(bins_aff[by_d], stable=True)
-            ranked = by_d[by_bin]                                          # positions grouped by bin, farthest first
+            # large models: shipping whole distance lists to the host would dominate the Lloyd iteration.  Each such
+            # bin's n_empty farthest points are picked on the device (largest distance first, equal distances in point
+            # order -- the head of a stable descending sort) and only they come back.  Same SET of relocated points as
+            # sklearn; they are handed to the bin's empty clusters in descending distance (sklearn: in the order
+            # numpy's introselect leaves them), so the relocated centres may sit at permuted cluster indices of that bin.
             take = np.minimum(n_empty[multi], lens)
-            want = np.concatenate([np.arange(a, a + t) for a, t in zip(starts, take)])
-            sel_pos = ranked[torch.from_numpy(want).to(dev)]
-            packed = torch.stack([sel_pos.to(torch.float64), d2_dev[sel_pos]]).cpu().numpy()
-            cuts = np.concatenate([[0], np.cumsum(take)])
-            for i in range(len(multi)):
-                local_pos[slot_first[i]:slot_first[i] + take[i]] = packed[0][cuts[i]:cuts[i + 1]].astype(np.int64)
-                local_d2[slot_first[i]:slot_first[i] + take[i]] = packed[1][cuts[i]:cuts[i + 1]]
+            kmax = int(take.max())
+            if kmax <= ops.SEGMENT_TOPK_MAX:
+                pos_d, val_d = ops.segment_topk(d2_dev, members, seg_start, torch.from_numpy(multi.astype(np.int32)).to(dev), kmax)
+                packed = torch.stack([pos_d.to(torch.float64), val_d]).cpu().numpy()          # [2, n_multi, kmax]
+                for i in range(len(multi)):
+                    local_pos[slot_first[i]:slot_first[i] + take[i]] = packed[0, i, :take[i]].astype(np.int64)
+                    local_d2[slot_first[i]:slot_first[i] + take[i]] = packed[1, i, :take[i]]
+            else:
+                # (more than 8 clusters of one bin emptied at once: rank everything with two stable sorts)
+                by_d = torch.argsort(d2_dev, descending=True, stable=True)
+                by_bin = torch.argsort(bins_aff[by_d], stable=True)
+                ranked = by_d[by_bin]                                          # positions grouped by bin, farthest first
+                want = np.concatenate([np.arange(a, a + t) for a, t in zip(starts, take)])
+                sel_pos = ranked[torch.from_numpy(want).to(dev)]
+                packed = torch.stack([sel_pos.to(torch.float64), d2_dev[sel_pos]]).cpu().numpy()
+                cuts = np.concatenate([[0], np.cumsum(take)])
+                for i in range(len(multi)):
+                    local_pos[slot_first[i]:slot_first[i] + take[i]] = packed[0][cuts[i]:cuts[i + 1]].astype(np.int64)
+                    local_d2[slot_first[i]:slot_first[i] + take[i]] = packed[1][cuts[i]:cuts[i + 1]]
     mark(f"host-pick({len(affected)} bins, {E} slots, {idx.numel()} pts)")
     pos_t = torch.from_numpy(np.maximum(local_pos, 0)).to(dev)
     pts = idx.long()[pos_t] if idx.numel() else torch.zeros(E, dtype=torch.int64, device=dev)

@@ -454,7 +454,8 @@ __global__ void __launch_bounds__(256)
 // Squared distance of listed points to their own centre (empty-cluster relocation of the Lloyd M step: sklearn moves an
 // empty cluster onto the point farthest from its centre, _k_means_common.pyx _relocate_empty_clusters_dense).  One warp
 // per listed point, lanes stride the features, fixed butterfly.
-__global__ void __launch_bounds__(256)
+template <int VEC>
+__global__ void __launch_bounds__(256, 4)
     point_center_dist2_kernel(const double* __restrict__ X, int64_t ldx, int D, const int32_t* __restrict__ list, int64_t n,
                               const int64_t* __restrict__ label, const double* __restrict__ centers, double* __restrict__ out) {
     const int lane = threadIdx.x & 31;
@@ -464,13 +465,126 @@ __global__ void __launch_bounds__(256)
         const double* x = X + pt * ldx;
         const double* c = centers + label[pt] * D;
         double acc = 0.0;
-        for (int k = lane; k < D; k += 32) {
-            const double d = x[k] - c[k];
-            acc = fma(d, d, acc);
+        if (VEC == 2) {
+            // 16-byte loads, four row pieces in flight per lane before the first add (the order of the adds is fixed)
+            double acc1 = 0.0;
+            int k = 2 * lane;
+#pragma unroll 1
+            for (; k + 192 < D; k += 256) {
+                const double2 x0 = *reinterpret_cast<const double2*>(x + k), x1 = *reinterpret_cast<const double2*>(x + k + 64),
+                              x2 = *reinterpret_cast<const double2*>(x + k + 128), x3 = *reinterpret_cast<const double2*>(x + k + 192);
+                const double2 c0 = *reinterpret_cast<const double2*>(c + k), c1 = *reinterpret_cast<const double2*>(c + k + 64),
+                              c2 = *reinterpret_cast<const double2*>(c + k + 128), c3 = *reinterpret_cast<const double2*>(c + k + 192);
+                double d;
+                d = x0.x - c0.x; acc = fma(d, d, acc);  d = x0.y - c0.y; acc1 = fma(d, d, acc1);
+                d = x1.x - c1.x; acc = fma(d, d, acc);  d = x1.y - c1.y; acc1 = fma(d, d, acc1);
+                d = x2.x - c2.x; acc = fma(d, d, acc);  d = x2.y - c2.y; acc1 = fma(d, d, acc1);
+                d = x3.x - c3.x; acc = fma(d, d, acc);  d = x3.y - c3.y; acc1 = fma(d, d, acc1);
+            }
+#pragma unroll 1
+            for (; k < D; k += 64) {
+                const double2 xv = *reinterpret_cast<const double2*>(x + k), cv = *reinterpret_cast<const double2*>(c + k);
+                double d = xv.x - cv.x;
+                acc = fma(d, d, acc);
+                d = xv.y - cv.y;
+                acc1 = fma(d, d, acc1);
+            }
+            acc += acc1;
+        } else {
+            for (int k = lane; k < D; k += 32) {
+                const double d = x[k] - c[k];
+                acc = fma(d, d, acc);
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) out[e] = acc;
+    }
+}
+
+// The k largest values of each listed segment (k <= ST_KMAX), largest first, equal values in member order -- what a
+// stable descending sort of the segment would put first (the farthest points of a WE bin that lost several clusters:
+// ranking every point of every such bin took two device-wide sorts).  One CTA per listed segment: every thread keeps
+// the best k of its strided share in registers, then k rounds of a block-wide argmax over the threads' current heads.
+static constexpr int ST_KMAX = 8;
+__device__ __forceinline__ bool st_better(double va, int pa, double vb, int pb) { return va > vb || (va == vb && pa < pb); }
+__global__ void __launch_bounds__(256)
+    segment_topk_kernel(const double* __restrict__ values, const uint32_t* __restrict__ members, const int32_t* __restrict__ seg_start,
+                        const int32_t* __restrict__ seg_ids, int k, int32_t* __restrict__ out_pos, double* __restrict__ out_val) {
+    __shared__ double s_v[256 * ST_KMAX];
+    __shared__ int s_p[256 * ST_KMAX];
+    __shared__ double s_wv[8];
+    __shared__ int s_wp[8], s_wt[8];
+    const int seg = seg_ids[blockIdx.x];
+    const int32_t s = seg_start[seg], e = seg_start[seg + 1];
+    const double ninf = __longlong_as_double(0xfff0000000000000LL);
+    double tv[ST_KMAX];
+    int tp[ST_KMAX];
+#pragma unroll
+    for (int j = 0; j < ST_KMAX; ++j) {
+        tv[j] = ninf;
+        tp[j] = 0x7fffffff;
+    }
+    for (int32_t m = s + (int32_t)threadIdx.x; m < e; m += 256) {
+        int cp = (int)members[m];
+        double cvv = values[cp];
+        if (cvv == cvv && st_better(cvv, cp, tv[ST_KMAX - 1], tp[ST_KMAX - 1])) {
+#pragma unroll
+            for (int j = 0; j < ST_KMAX; ++j)
+                if (st_better(cvv, cp, tv[j], tp[j])) {
+                    const double a = tv[j];
+                    const int b = tp[j];
+                    tv[j] = cvv;
+                    tp[j] = cp;
+                    cvv = a;
+                    cp = b;
+                }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < ST_KMAX; ++j) {
+        s_v[threadIdx.x * ST_KMAX + j] = tv[j];
+        s_p[threadIdx.x * ST_KMAX + j] = tp[j];
+    }
+    __syncthreads();
+    int cursor = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = 0; r < k; ++r) {
+        double v = cursor < ST_KMAX ? s_v[threadIdx.x * ST_KMAX + cursor] : ninf;
+        int p = cursor < ST_KMAX ? s_p[threadIdx.x * ST_KMAX + cursor] : 0x7fffffff;
+        int t = (int)threadIdx.x;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int op = __shfl_xor_sync(0xffffffffu, p, o), ot = __shfl_xor_sync(0xffffffffu, t, o);
+            if (st_better(ov, op, v, p)) {
+                v = ov;
+                p = op;
+                t = ot;
+            }
+        }
+        if (lane == 0) {
+            s_wv[warp] = v;
+            s_wp[warp] = p;
+            s_wt[warp] = t;
+        }
+        __syncthreads();
+        v = s_wv[0];
+        p = s_wp[0];
+        t = s_wt[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w)
+            if (st_better(s_wv[w], s_wp[w], v, p)) {
+                v = s_wv[w];
+                p = s_wp[w];
+                t = s_wt[w];
+            }
+        if ((int)threadIdx.x == t && p != 0x7fffffff) ++cursor;
+        if (threadIdx.x == 0) {
+            out_pos[(int64_t)blockIdx.x * k + r] = (p == 0x7fffffff) ? -1 : p;     // fewer than k members: -1
+            out_val[(int64_t)blockIdx.x * k + r] = v;
+        }
+        __syncthreads();
     }
 }
 
@@ -587,7 +701,21 @@ extern "C" int mwe_point_center_dist2_f64(const double* X, int64_t ldx, int D, c
     int64_t blocks = (n + 7) / 8;
     const int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    point_center_dist2_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(X, ldx, D, list, n, label, centers, out);
+    const bool vec2 = (D % 2 == 0) && (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(centers) & 15) == 0);
+    if (vec2) point_center_dist2_kernel<2><<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(X, ldx, D, list, n, label, centers, out);
+    else point_center_dist2_kernel<1><<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(X, ldx, D, list, n, label, centers, out);
+    MWE_CHECK_LAUNCH();
+    return MWE_OK;
+}
+
+extern "C" int mwe_segment_topk_f64(const double* values, const uint32_t* members, const int32_t* seg_start, const int32_t* seg_ids,
+                                    int32_t n_sel, int k, int32_t* out_pos, double* out_val, void* stream) {
+    using namespace mwe;
+    MWE_REQUIRE(n_sel >= 0 && k >= 1 && k <= ST_KMAX, "segment_topk: k must be in [1, 8]");
+    if (n_sel == 0) return MWE_OK;
+    MWE_REQUIRE(values && members && seg_start && seg_ids && out_pos && out_val, "segment_topk: null pointer");
+    segment_topk_kernel<<<(unsigned)n_sel, 256, 0, static_cast<cudaStream_t>(stream)>>>(values, members, seg_start, seg_ids, k, out_pos, out_val);
     MWE_CHECK_LAUNCH();
     return MWE_OK;
 }

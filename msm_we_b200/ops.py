@@ -325,6 +325,25 @@ def label_stats(values, members, seg_start, n_labels):
     return count, out[0], out[1], out[2]
 
 
+SEGMENT_TOPK_MAX = 8
+
+
+def segment_topk(values, members, seg_start, seg_ids, k):
+    """For each listed group (``seg_ids`` int32, indices into ``seg_start``) the ``k`` (<= 8) largest ``values[member]``:
+    ``(pos int32 [n_sel, k], val float64 [n_sel, k])``, largest first, equal values in member order; -1 / -inf padding
+    when a group has fewer members."""
+    if not values.is_cuda or values.dtype != torch.float64 or values.dim() != 1 or (values.numel() > 1 and values.stride(0) != 1):
+        raise TypeError("values: expected a contiguous 1-D CUDA float64 tensor")
+    _req(members, torch.int32, "members"); _req(seg_start, torch.int32, "seg_start"); _req(seg_ids, torch.int32, "seg_ids")
+    n_sel, k = seg_ids.numel(), int(k)
+    pos = torch.full((n_sel, k), -1, dtype=torch.int32, device=values.device)
+    val = torch.full((n_sel, k), float("-inf"), dtype=torch.float64, device=values.device)
+    if n_sel and values.numel():
+        check(lib.mwe_segment_topk_f64(_ptr(values), _ptr(members), _ptr(seg_start), _ptr(seg_ids), n_sel, k, _ptr(pos), _ptr(val),
+                                       _stream()), "mwe_segment_topk_f64")
+    return pos, val
+
+
 def rows_with_nan(X):
     """uint8 [N]: 1 where row of X [N, D] float64 holds a NaN."""
     if not X.is_cuda or X.dtype != torch.float64 or X.dim() != 2 or X.stride(1) != 1:

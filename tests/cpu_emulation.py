@@ -199,6 +199,18 @@ def emulate_kernels(monkeypatch):
                 out[0, k], out[1, k], out[2, k] = x.sum(), x.min(), x.max()
         return torch.from_numpy(cnt), torch.from_numpy(out[0]), torch.from_numpy(out[1]), torch.from_numpy(out[2])
 
+    def segment_topk(values, members, seg_start, seg_ids, k):
+        v, m, s, ids = _np(values), _np(members).astype(np.int64), _np(seg_start), _np(seg_ids)
+        pos = np.full((len(ids), k), -1, dtype=np.int32)
+        val = np.full((len(ids), k), -np.inf)
+        for i, g in enumerate(ids):
+            mem = m[s[g]:s[g + 1]]
+            mem = mem[~np.isnan(v[mem])]
+            order = mem[np.lexsort((mem, -v[mem]))][:k]          # value descending, equal values in member order
+            pos[i, :len(order)] = order
+            val[i, :len(order)] = v[order]
+        return torch.from_numpy(pos), torch.from_numpy(val)
+
     def rows_with_nan(X):
         return torch.from_numpy(np.isnan(_np(X)).any(axis=1).astype(np.uint8))
 
@@ -214,6 +226,6 @@ def emulate_kernels(monkeypatch):
     for name, fn in dict(centers_sqnorm=centers_sqnorm, bin_flags=bin_flags, assign_stratified=assign_stratified,
                          minibatch_update=minibatch_update, centroid_accumulate=centroid_accumulate,
                          lloyd_finalize=lloyd_finalize, flux_accumulate=flux_accumulate, divide_=divide_,
-                         group_by_label=group_by_label, label_stats=label_stats, rows_with_nan=rows_with_nan, point_center_dist2=point_center_dist2,
+                         group_by_label=group_by_label, label_stats=label_stats, segment_topk=segment_topk, rows_with_nan=rows_with_nan, point_center_dist2=point_center_dist2,
                          project=project).items():
         monkeypatch.setattr(ops, name, fn)

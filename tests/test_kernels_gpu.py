@@ -364,6 +364,29 @@ def test_group_by_label_and_label_stats(n_labels, N):
             assert ssum[k] == 0.0 and vmin[k] == np.inf and vmax[k] == -np.inf
 
 
+@pytest.mark.parametrize("k", [1, 3, 8])
+def test_segment_topk_is_the_head_of_a_stable_descending_sort(k):
+    ops = _ops()
+    rng = np.random.default_rng(77 + k)
+    n_labels, N = 12, 50000
+    labels = rng.integers(0, n_labels, size=N).astype(np.int64)
+    labels[labels == 5] = 6                                   # group 5 empty
+    labels[:2] = 11; labels[labels == 11] = 10; labels[:2] = 11   # group 11 has exactly two members
+    v = np.round(rng.normal(size=N), 2)                       # many exactly equal values: ties are resolved by member order
+    v[rng.random(N) < 0.01] = np.nan
+    members, seg = ops.group_by_label(t(labels), n_labels)
+    ids = np.array([0, 5, 11, 3, 7], dtype=np.int32)
+    pos, val = ops.segment_topk(t(v), members, seg, t(ids), k)
+    pos, val = pos.cpu().numpy(), val.cpu().numpy()
+    for i, g in enumerate(ids):
+        mem = np.flatnonzero(labels == g)
+        mem = mem[~np.isnan(v[mem])]
+        want = mem[np.lexsort((mem, -v[mem]))][:k]
+        assert np.array_equal(pos[i, :len(want)], want), g
+        assert np.array_equal(val[i, :len(want)], v[want])
+        assert (pos[i, len(want):] == -1).all()
+
+
 # ------------------------------------------------------------------ K3
 def _flux_case(rng, n, iters, segs):
     per = []

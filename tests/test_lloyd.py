@@ -177,8 +177,9 @@ def test_discretization_after_lloyd_reuses_the_resident_child_rows(monkeypatch, 
             assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("dups", [2, 9])          # 3 empty clusters: per-bin top-k kernel; 10: the two-sort fallback (k > 8)
 @pytest.mark.parametrize("gpu", BACKENDS)
-def test_lloyd_relocation_device_ranked_branch_relocates_the_same_points(monkeypatch, gpu):
+def test_lloyd_relocation_device_ranked_branch_relocates_the_same_points(monkeypatch, gpu, dups):
     """Large models rank the farthest points on the device (clustering_ops.EXACT_ORDER_MAX_POINTS): the same points are
     relocated as by sklearn; only the cluster index that receives each of them may be permuted within the bin."""
     import torch
@@ -188,9 +189,9 @@ def test_lloyd_relocation_device_ranked_branch_relocates_the_same_points(monkeyp
 
     monkeypatch.setattr(clustering_ops, "EXACT_ORDER_MAX_POINTS", 0)
     rng = np.random.default_rng(8)
-    K, D = 7, 5
+    K, D = dups + 5, 5
     X = np.concatenate([rng.normal(m, 0.4, size=(80, D)) for m in (-5, 0, 5, 11)])
-    init = np.stack([X[0], X[0], X[0], X[90], X[90], X[170], X[250]])      # three empty clusters in one model
+    init = np.stack([X[0]] * (dups + 1) + [X[90], X[90], X[170], X[250]])  # dups + 1 empty clusters in one model
     centers = torch.from_numpy(init.copy()).to(dev)
     offs = torch.tensor([0, K], dtype=torch.int64, device=dev)
     bins = torch.zeros(len(X), dtype=torch.int32, device=dev)
