@@ -57,6 +57,11 @@ extern "C" {
 #define MWE_ASSIGN_FP64 0      /* fp64 tensor (DMMA) distances, the parity path                    */
 #define MWE_ASSIGN_TF32X3 1    /* tcgen05 split-TF32 candidate pass + fp64 re-check of near-ties   */
 #define MWE_ASSIGN_AUTO 2      /* the faster of the two for the shape (labels are identical)        */
+/* OR-ed into precision_path of mwe_assign_stratified_f64: the workspace, label_out and local_out still hold what the
+ * previous call with the SAME N, bin, flag, nbins and bin_offset left there (nothing else wrote to them since), so the
+ * bucketing of the points by WE bin is not recomputed -- Lloyd iterations re-label the same points against new centres
+ * (sklearn lloyd_iter_chunked_dense called max_iter times on one X, _kmeans.py:700-760). */
+#define MWE_ASSIGN_REUSE_BUCKETS 0x100
 
 MWE_API int mwe_abi_version(void);
 MWE_API const char* mwe_last_error(void);

@@ -18,6 +18,7 @@ ERR_OUT_OF_BINSPACE, ERR_NO_CENTERS, ERR_LABEL_RANGE, ERR_INTERNAL = 0, 1, 2, 3
 FLAG_BASIS, FLAG_TARGET = 1, 2
 MAPPER_RECTILINEAR, MAPPER_VORONOI, MAPPER_PRECOMPUTED = 0, 1, 2
 ASSIGN_FP64, ASSIGN_TF32X3, ASSIGN_AUTO = 0, 1, 2
+ASSIGN_REUSE_BUCKETS = 0x100
 
 _p = C.c_void_p
 _i64 = C.c_int64

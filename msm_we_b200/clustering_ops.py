@@ -89,9 +89,14 @@ def lloyd_fit(X_dev, w_dev, bins_dev, centers_dev, bin_offset_dev, max_k, n_iter
     sumK, D = centers_dev.shape
     sums = torch.empty(sumK * (D + 1), dtype=torch.float64, device=centers_dev.device)   # sum_wx | sum_w: one exchange
     offs_host = bin_offset_dev.cpu().numpy() if relocate_empty else None
-    for _ in range(n_iter):
-        labels = ops.assign_stratified(X_dev, bins_dev, flags_dev, centers_dev, ops.centers_sqnorm(centers_dev),
-                                       bin_offset_dev, max_k, path=path, errors=errors)
+    # the points and their WE bins do not change between iterations: K1 buckets them once (private workspace + one
+    # label buffer, so nothing else writes to them in between)
+    nbins = bin_offset_dev.numel() - 1
+    k1_ws = ops.assign_workspace(X_dev, nbins, max_k, path) if n_iter > 1 else None
+    labels = torch.empty(X_dev.shape[0], dtype=torch.int64, device=X_dev.device) if n_iter > 0 else None
+    for it in range(n_iter):
+        ops.assign_stratified(X_dev, bins_dev, flags_dev, centers_dev, ops.centers_sqnorm(centers_dev), bin_offset_dev, max_k,
+                              path=path, errors=errors, label_out=labels, workspace=k1_ws, reuse_buckets=it > 0)
         sum_wx, sum_w = ops.centroid_accumulate(X_dev, w_dev, labels, sumK, out=sums)
         if group is not None:
             import torch.distributed as dist

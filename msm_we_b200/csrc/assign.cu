@@ -714,7 +714,8 @@ extern "C" int mwe_assign_stratified_f64(const double* X, int64_t N, int D, int6
     MWE_REQUIRE(D >= 1 && ldx >= D, "assign: bad D / ldx");
     MWE_REQUIRE(nbins >= 1 && max_k >= 1, "assign: bad nbins / max_k");
     MWE_REQUIRE(bin && centers && csq && bin_offset && label_out && err_count, "assign: null pointer");
-    precision_path = mwe::resolve_assign_path(precision_path, D, max_k);
+    const bool reuse_buckets = (precision_path & MWE_ASSIGN_REUSE_BUCKETS) != 0;
+    precision_path = mwe::resolve_assign_path(precision_path & ~MWE_ASSIGN_REUSE_BUCKETS, D, max_k);
     if (precision_path != MWE_ASSIGN_FP64 && precision_path != MWE_ASSIGN_TF32X3) {
         set_last_error("assign: unknown precision path %d", precision_path);
         return MWE_E_UNSUPPORTED;
@@ -744,15 +745,20 @@ extern "C" int mwe_assign_stratified_f64(const double* X, int64_t N, int D, int6
     const bool use_res = res_points > 0;
     const int tile_points = use_tc ? 128 : use_res ? res_points : tile_points_for(nt);
     const int64_t blocks = (N + 256 * AS_BK_ITEMS - 1) / (256 * AS_BK_ITEMS);
-    if (!bin_count_in) {
-        MWE_CHECK_CUDA(cudaMemsetAsync(ws.bin_count, 0, (size_t)(nbins + 1) * sizeof(int32_t), s));
-        assign_count_kernel<<<(unsigned)blocks, 256, 0, s>>>(bin, flag, N, nbins, ws.bin_count);
+    if (reuse_buckets) {
+        // perm / bin_start / tile tables and the labels of basis, target and unfitted points are still in place
+        MWE_CHECK_CUDA(cudaMemsetAsync(ws.recheck_count, 0, sizeof(int32_t), s));
+    } else {
+        if (!bin_count_in) {
+            MWE_CHECK_CUDA(cudaMemsetAsync(ws.bin_count, 0, (size_t)(nbins + 1) * sizeof(int32_t), s));
+            assign_count_kernel<<<(unsigned)blocks, 256, 0, s>>>(bin, flag, N, nbins, ws.bin_count);
+        }
+        MWE_CHECK_CUDA(launch_pdl(assign_scan_kernel, dim3(1), dim3(256), 0, s, bin_count_in ? bin_count_in : ws.bin_count, bin_offset,
+                                  nbins, ws.bin_start, ws.bin_cursor, ws.tile_prefix, err_count, tile_points, ws.recheck_count));
+        MWE_CHECK_CUDA(launch_pdl(assign_scatter_kernel, dim3((unsigned)blocks), dim3(256), 0, s, bin, flag, N, nbins, bin_offset,
+                                  ws.bin_cursor, ws.perm, label_out, local_out, ws.bin_start, ws.tile_prefix, tile_points,
+                                  use_res ? ws.tile_desc : nullptr));
     }
-    MWE_CHECK_CUDA(launch_pdl(assign_scan_kernel, dim3(1), dim3(256), 0, s, bin_count_in ? bin_count_in : ws.bin_count, bin_offset,
-                              nbins, ws.bin_start, ws.bin_cursor, ws.tile_prefix, err_count, tile_points, ws.recheck_count));
-    MWE_CHECK_CUDA(launch_pdl(assign_scatter_kernel, dim3((unsigned)blocks), dim3(256), 0, s, bin, flag, N, nbins, bin_offset,
-                              ws.bin_cursor, ws.perm, label_out, local_out, ws.bin_start, ws.tile_prefix, tile_points,
-                              use_res ? ws.tile_desc : nullptr));
 
     AssignParams p;
     p.X = X; p.ldx = ldx; p.D = D; p.centers = centers; p.csq = csq; p.bin_offset = bin_offset; p.nbins = nbins;

@@ -166,9 +166,19 @@ def centers_sqnorm(centers):
     return out
 
 
+def assign_workspace(X, nbins, max_k, path=_lib.ASSIGN_FP64):
+    """A private K1 workspace (uint8 tensor) for callers that label the same points repeatedly (``reuse_buckets``)."""
+    N, D = X.shape
+    return torch.empty(lib.mwe_assign_workspace_bytes_ex(N, int(nbins), D, int(max_k), int(path)), dtype=torch.uint8, device=X.device)
+
+
 def assign_stratified(X, bin, flag, centers, csq, bin_offset, max_k, path=_lib.ASSIGN_FP64, want_local=False,
-                      errors: DeviceErrors = None, label_out=None, bin_count=None):
-    """K1.  X [N,D] f64 (row stride may exceed D) -> labels int64 [N] (and per-bin local argmin)."""
+                      errors: DeviceErrors = None, label_out=None, bin_count=None, workspace=None, reuse_buckets=False):
+    """K1.  X [N,D] f64 (row stride may exceed D) -> labels int64 [N] (and per-bin local argmin).
+
+    ``reuse_buckets``: ``workspace`` (from ``assign_workspace``) and ``label_out`` still hold what the previous call with
+    the same X rows, ``bin``, ``flag`` and ``bin_offset`` left there, so the points are not bucketed by WE bin again --
+    Lloyd iterations only change the centres."""
     if not X.is_cuda or X.dtype != torch.float64 or X.dim() != 2 or X.stride(1) != 1:
         raise TypeError("X: expected a CUDA float64 [N, D] tensor with unit column stride")
     _req(bin, torch.int32, "bin"); _req(flag, torch.uint8, "flag")
@@ -183,9 +193,16 @@ def assign_stratified(X, bin, flag, centers, csq, bin_offset, max_k, path=_lib.A
         label_out = torch.empty(N, dtype=torch.int64, device=dev)
     local = torch.empty(N, dtype=torch.int32, device=dev) if want_local else None
     nbytes = lib.mwe_assign_workspace_bytes_ex(N, nbins, D, int(max_k), int(path))
-    ws = Workspace.get(dev, nbytes)
+    if reuse_buckets and (workspace is None or want_local):
+        raise ValueError("reuse_buckets needs the private workspace (and label_out) of the previous call")
+    if workspace is not None:
+        _req(workspace, torch.uint8, "workspace")
+        if workspace.numel() < nbytes:
+            raise ValueError("workspace too small")
+    ws = workspace if workspace is not None else Workspace.get(dev, nbytes)
     check(lib.mwe_assign_stratified_f64(_ptr(X), N, D, ldx, _ptr(bin), _ptr(flag), _ptr(centers), _ptr(csq),
-                                        _ptr(bin_offset), nbins, int(max_k), int(path), _ptr(bin_count), _ptr(label_out),
+                                        _ptr(bin_offset), nbins, int(max_k),
+                                        int(path) | (_lib.ASSIGN_REUSE_BUCKETS if reuse_buckets else 0), _ptr(bin_count), _ptr(label_out),
                                         _ptr(local),
                                         _ptr(ws), ws.numel(), _ptr(errors.counts), _stream()),
           "mwe_assign_stratified_f64")

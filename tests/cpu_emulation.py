@@ -84,8 +84,12 @@ def emulate_kernels(monkeypatch):
         flag = (O.is_we_region(pc, basis).astype(np.uint8) | (O.is_we_region(pc, target).astype(np.uint8) << 1))
         return bin_out, torch.from_numpy(flag)
 
+    def assign_workspace(X, nbins, max_k, path=0):
+        return torch.empty(16, dtype=torch.uint8)
+
     def assign_stratified(X, bin, flag, centers, csq, bin_offset, max_k, path=0, want_local=False, errors=None,
-                          label_out=None, bin_count=None):
+                          label_out=None, bin_count=None, workspace=None, reuse_buckets=False):
+        assert not reuse_buckets or (workspace is not None and label_out is not None)
         x, b, c, offs = _np(X), _np(bin).astype(np.int64), _np(centers), _np(bin_offset)
         f = np.zeros(len(b), dtype=np.uint8) if flag is None else _np(flag)
         total = int(offs[-1])
@@ -223,7 +227,7 @@ def emulate_kernels(monkeypatch):
         r = O.linear_transform(_np(X), _np(components), None if mean is None else _np(mean))
         return torch.from_numpy(np.ascontiguousarray(r))
 
-    for name, fn in dict(centers_sqnorm=centers_sqnorm, bin_flags=bin_flags, assign_stratified=assign_stratified,
+    for name, fn in dict(centers_sqnorm=centers_sqnorm, bin_flags=bin_flags, assign_stratified=assign_stratified, assign_workspace=assign_workspace,
                          minibatch_update=minibatch_update, centroid_accumulate=centroid_accumulate,
                          lloyd_finalize=lloyd_finalize, flux_accumulate=flux_accumulate, divide_=divide_,
                          group_by_label=group_by_label, label_stats=label_stats, segment_topk=segment_topk, rows_with_nan=rows_with_nan, point_center_dist2=point_center_dist2,

@@ -169,6 +169,27 @@ def test_assign_tcgen05_path_gives_identical_labels(N, D, nbins, K, ragged):
     assert np.array_equal(lab_tc.cpu().numpy()[margins > 0], ref[margins > 0])
 
 
+@pytest.mark.parametrize("path_name", ["FP64", "TF32X3"])
+@pytest.mark.parametrize("N,D,nbins,K", [(5000, 64, 30, 20), (6000, 256, 6, 100), (3000, 7, 5, 100)])
+def test_assign_reusing_the_buckets_of_the_previous_call(path_name, N, D, nbins, K):
+    """Lloyd iterations label the same points against new centres: with MWE_ASSIGN_REUSE_BUCKETS the second call skips
+    the bucketing by WE bin (private workspace + the same label buffer) and must label like a fresh call."""
+    from msm_we_b200 import _lib
+    ops = _ops()
+    path = getattr(_lib, "ASSIGN_" + path_name)
+    rng = np.random.default_rng(N + D)
+    X, bins, flags, centers, offs, ks = _strat_case(rng, N, D, nbins, K, False)
+    Xd, bd, fd, od = t(X), t(bins), t(flags), t(offs)
+    ws = ops.assign_workspace(Xd, nbins, K, path)
+    labels = torch.empty(N, dtype=torch.int64, device=Xd.device)
+    for it in range(3):
+        c = t(centers + 0.3 * it * rng.normal(size=centers.shape))
+        csq = ops.centers_sqnorm(c)
+        ops.assign_stratified(Xd, bd, fd, c, csq, od, K, path=path, label_out=labels, workspace=ws, reuse_buckets=it > 0)
+        fresh = ops.assign_stratified(Xd, bd, fd, c, csq, od, K, path=path)
+        assert np.array_equal(labels.cpu().numpy(), fresh.cpu().numpy()), it
+
+
 def test_assign_tcgen05_scores_within_error_bound():
     """The rigorous part of the fast path is its error bound: dump the scores the tensor cores produced and
     compare them with fp64 (centred by the bin mean, as the kernel does)."""
