@@ -308,9 +308,10 @@ def launches_per_step(cfg, tc_path, lloyd, world):
     profiles/)."""
     k1 = 2 + (3 if tc_path else 0) + 2                      # scan, scatter, [mean, split, csq], main, re-check
     k2 = 2 + 1 + max(1, (int(np.ceil(np.log2(cfg.n_clusters + 1))) + 7) // 8) + 1 + 1  # keys, bounds, hist + passes, order, sum
-    per_lloyd = 1 + (1 + k1) + k2 + 1                      # csq + (bucket count + K1) + K2 + finalize (relocation kernels not counted)
+    per_lloyd = 1 + (k1 - 2) + k2 + 1                      # csq + K1 without bucketing + K2 + finalize (relocation kernels not counted)
+    first_lloyd = 3                                        # count, scan, scatter: the points are bucketed by WE bin once per fit
     final = 1 + k1 + 1 + (1 + k3_passes(cfg.n_clusters + 2)) + 3 + 1      # K0 (counts the buckets), K1, keys, sort, mark/group/cell, divide|exchange
-    return (1 if lloyd else 0) + lloyd * per_lloyd + (1 if lloyd else 0) + final
+    return (1 if lloyd else 0) + lloyd * per_lloyd + (first_lloyd if lloyd else 0) + (1 if lloyd else 0) + final
 
 
 def step_work(cfg, n_frames, lloyd, P=1):
