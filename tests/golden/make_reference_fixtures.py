@@ -1,7 +1,7 @@
 """Golden fixtures produced by EXECUTING the reference's own code (/root/reference/msm_we, unmodified) in this
 container -- run here only; /root/reference does not exist on the GPU box, the .npz outputs are committed.
 
-    OMP_NUM_THREADS=1 python tests/golden/make_reference_fixtures.py [pipeline1d pipeline2d predict_cfg2 predict_ntl9 colour]
+    OMP_NUM_THREADS=1 python tests/golden/make_reference_fixtures.py [pipeline1d pipeline2d pipeline_voronoi predict_cfg2 predict_ntl9 colour]
 
 How the reference is made importable is described in tests/golden/refshim.py (stand-ins for ray / h5py / westpa /
 mdtraj / deeptime / matplotlib, none of which holds arithmetic of the path; sklearn 1.9 / scipy 1.18 / numpy 2.3 are
@@ -88,15 +88,29 @@ def snapshot_clusters(model, prefix):
     return out
 
 
+def _euclid(coord, centers):
+    """The distance function a WESTPA user hands to VoronoiBinMapper."""
+    return np.linalg.norm(np.asarray(centers, dtype=np.float64) - np.asarray(coord, dtype=np.float64), axis=1)
+
+
 def run_pipeline(name, its, bnds, basis, target, K, pcoord_ndim, n_atoms, coord_ndim, dim_reduce="none",
-                 use_weights=False, cluster_kwargs=None, user_mapper=False, cluster_call_kwargs=None, organize=True):
+                 use_weights=False, cluster_kwargs=None, user_mapper=False, cluster_call_kwargs=None, organize=True,
+                 voronoi_centers=None):
     msm_we = refshim.load_reference()
     from msm_we._hamsm import _clustering as RC
 
     refshim.ragged_numpy(RC)
     _quiet()
     fname = f"{name}_west.h5"
-    mapper = refshim.RectilinearBinMapper(bnds)
+    if voronoi_centers is not None:
+        vc = np.asarray(voronoi_centers, dtype=np.float64)
+        mapper = refshim.VoronoiBinMapper(_euclid, vc)
+        # no progress coordinate may sit on a cell boundary to within float32 resolution (WESTPA compares in float32)
+        allpc = np.concatenate([d["pcoord"].reshape(-1, pcoord_ndim) for d in its])
+        d = np.sort(np.stack([_euclid(c, vc) for c in allpc]), axis=1)
+        assert (d[:, 1] - d[:, 0]).min() > 2e-5, (d[:, 1] - d[:, 0]).min()
+    else:
+        mapper = refshim.RectilinearBinMapper(bnds)
     refshim.register_we_file(fname, its, bin_mapper=mapper)
     msm_we.modelWE.processCoordinates = processCoordinates
     model = msm_we.modelWE()
@@ -112,6 +126,8 @@ def run_pipeline(name, its, bnds, basis, target, K, pcoord_ndim, n_atoms, coord_
                n_atoms=np.int64(n_atoms), coord_ndim=np.int64(coord_ndim), pcoord_ndim=np.int64(pcoord_ndim),
                use_weights=np.bool_(use_weights), maxIter=np.int64(model.maxIter),
                numSegments=np.asarray(model.numSegments, dtype=np.float64), pcoordSet=np.asarray(model.pcoordSet))
+    if voronoi_centers is not None:
+        out["voronoi_centers"] = np.asarray(voronoi_centers, dtype=np.float64)
     if dim_reduce == "pca":
         out["pca_components"] = np.asarray(model.coordinates.components_, dtype=np.float64)
         out["pca_mean"] = np.asarray(model.coordinates.mean_, dtype=np.float64)
@@ -375,6 +391,14 @@ def main(which):
         run_pipeline("pipeline2d", its, FD.boundaries(4, 2), [[0.0, 0.6], [0.0, 0.6]], [[3.4, 1.0e6], [3.4, 1.0e6]], K=3,
                      pcoord_ndim=2, n_atoms=4, coord_ndim=3, dim_reduce="pca", use_weights=True,
                      cluster_kwargs={"random_state": 7, "init": "random"}, user_mapper=True, organize=False)
+    if "pipeline_voronoi" in which:
+        # WESTPA's other supported mapper: nearest-centre bins with a user distance function; the cell of centre 5.5 is
+        # never seen while clustering (remapped through find_nearest_bin's Voronoi branch, _clustering.py:1331-1396)
+        its = FD.we_dataset(seed=13, n_iters=20, segs0=200, seg_growth=3, n_atoms=4, coord_ndim=3, bins_per_dim=8, k_true=3,
+                            skip_bin=5, skip_until=11, regions_last=([[0.0, 0.5]], [[7.5, 1.0e6]]))
+        run_pipeline("pipeline_voronoi", its, FD.boundaries(8), [[0.0, 0.5]], [[7.5, 1.0e6]], K=4, pcoord_ndim=1, n_atoms=4,
+                     coord_ndim=3, cluster_kwargs={"random_state": 4242}, cluster_call_kwargs={"iters_to_use": list(range(1, 10))},
+                     voronoi_centers=[[0.5], [1.5], [2.4], [3.6], [4.5], [5.5], [6.5], [7.5]])
     if "predict_cfg2" in which:
         run_predict_cfg2()
     if "predict_ntl9" in which:
@@ -385,4 +409,4 @@ def main(which):
 
 if __name__ == "__main__":
     os.environ.setdefault("OMP_NUM_THREADS", "1")
-    main(sys.argv[1:] or ["pipeline1d", "pipeline2d", "predict_cfg2", "predict_ntl9", "colour"])
+    main(sys.argv[1:] or ["pipeline1d", "pipeline2d", "pipeline_voronoi", "predict_cfg2", "predict_ntl9", "colour"])

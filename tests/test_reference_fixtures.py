@@ -54,8 +54,10 @@ def _close(a, b, what):
 
 
 def _mapper(fx):
-    from msm_we_b200.binning import RectilinearBinMapper
+    from msm_we_b200.binning import RectilinearBinMapper, VoronoiBinMapper
 
+    if "voronoi_centers" in fx.files:
+        return VoronoiBinMapper(centers=fx["voronoi_centers"])     # (the default distance: Euclidean, evaluated by K0)
     bnds, p = [], 0
     for ln in fx["boundary_lens"]:
         bnds.append(fx["boundaries"][p:p + int(ln)])
@@ -127,7 +129,8 @@ def _run_pipeline(name, user_featuriser=False):
 
 
 @pytest.mark.parametrize("gpu", BACKENDS)
-@pytest.mark.parametrize("name,user_featuriser", [("pipeline1d", False), ("pipeline1d", True), ("pipeline2d", False)])
+@pytest.mark.parametrize("name,user_featuriser", [("pipeline1d", False), ("pipeline1d", True), ("pipeline2d", False),
+                                                  ("pipeline_voronoi", False)])
 def test_clustering_discretization_flux_match_reference_run(request, monkeypatch, gpu, name, user_featuriser):
     _backend(request, monkeypatch, gpu)
     fx, model = _run_pipeline(name, user_featuriser)
@@ -149,10 +152,11 @@ def test_clustering_discretization_flux_match_reference_run(request, monkeypatch
     _close(model.fluxMatrixRaw, fx["flux_subset"], "fluxMatrixRaw (iters_to_use)")
 
 
+@pytest.mark.parametrize("name", ["pipeline1d", "pipeline_voronoi"])
 @pytest.mark.parametrize("gpu", BACKENDS)
-def test_cleaning_block_validation_structures_match_reference_run(request, monkeypatch, gpu):
+def test_cleaning_block_validation_structures_match_reference_run(request, monkeypatch, gpu, name):
     _backend(request, monkeypatch, gpu)
-    fx, model = _run_pipeline("pipeline1d")
+    fx, model = _run_pipeline(name)
     model.get_fluxMatrix(0, first_iter=1, last_iter=model.maxIter, use_ray=False)
     model.organize_fluxMatrix(use_ray=False)
     _check_clusters(model, fx, "o_")
