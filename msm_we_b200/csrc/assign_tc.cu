@@ -74,8 +74,18 @@ __global__ void __launch_bounds__(128)
     if (k >= d_pad) return;
     const int64_t c0 = bin_offset[b], c1 = bin_offset[b + 1];
     double s = 0.0;
-    if (k < D)
-        for (int64_t j = c0; j < c1; ++j) s += centers[j * D + k];
+    if (k < D) {
+        // eight loads in flight, the adds stay in centre order
+        int64_t j = c0;
+        for (; j + 8 <= c1; j += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = centers[(j + u) * D + k];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
+        for (; j < c1; ++j) s += centers[j * D + k];
+    }
     mean[(size_t)b * d_pad + k] = (c1 > c0 && k < D) ? s / (double)(c1 - c0) : 0.0;
 }
 
