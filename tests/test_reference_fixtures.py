@@ -320,6 +320,41 @@ def test_oracle_matches_reference_run_labels_and_flux():
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("name", ["pipeline1d", "pipeline_voronoi"])
+def test_oracle_discretization_and_flux_match_reference_pipeline_run(name):
+    """The oracle's mapper restatements (westpa's Rectilinear / Voronoi mappers are not in the image), its ``we_remap``
+    handling and its flux accumulation against what the reference's own run produced from the same fitted centres."""
+    fx = np.load(os.path.join(GOLDEN, f"ref_{name}.npz"))
+    its = FD.unpack_iterations(fx)
+    if "voronoi_centers" in fx.files:
+        mapper = O.VoronoiBinMapperOracle(fx["voronoi_centers"])
+    else:
+        bnds, p = [], 0
+        for ln in fx["boundary_lens"]:
+            bnds.append(fx["boundaries"][p:p + int(ln)])
+            p += int(ln)
+        mapper = O.RectilinearBinMapperOracle(bnds)
+    centres, p = [], 0
+    for sz in fx["c_sizes"]:
+        centres.append(None if sz < 0 else fx["c_centers"][p:p + int(sz)])
+        p += max(int(sz), 0)
+    strat = O.StratifiedOracle(mapper, centres, fx["basis"], fx["target"],
+                               we_remap={b: int(r) for b, r in enumerate(fx["c_we_remap"])})
+    P = int(fx["pcoord_ndim"])
+    pairs, per = [], []
+    for i, d in enumerate(its[: int(fx["maxIter"]) - 1], start=1):
+        S = len(d["weights"])
+        xp, xc = d["coords"][:, 0].reshape(S, -1), d["coords"][:, 1].reshape(S, -1)
+        pc0, pc1 = d["pcoord"][:, 0, :P], d["pcoord"][:, 1, :P]
+        a, b = O.discretize_iteration(strat, xp, xc, pc0, pc1)
+        pairs.append(np.stack([a, b], axis=1))
+        if i >= 2:
+            per.append((pairs[-1], pc0, pc1, d["weights"]))
+    assert np.array_equal(np.concatenate(pairs), fx["c_pair_dtrajs"])
+    got = O.flux_matrix(int(fx["c_n_clusters"]), per, fx["basis"], fx["target"])
+    _close(got, fx["flux_raw"], "oracle flux matrix")
+
+
 @pytest.mark.gpu
 def test_lineage_colour_counts_match_reference_nonmarkov_fit():
     """History-coloured count matrix over WE lineages: the reference's NonMarkovModel.fit over the traced trajectories
