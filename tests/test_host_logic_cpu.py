@@ -215,7 +215,7 @@ def test_host_pinning_degrades_without_a_gpu():
     assert HostPins._owner(view) is a
 
 
-def _gloo_lloyd_worker(rank, world, port, tmp):
+def _gloo_lloyd_worker(rank, world, port, tmp, mode="single"):
     os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world)})
     import torch
     import torch.distributed as dist
@@ -227,7 +227,9 @@ def _gloo_lloyd_worker(rank, world, port, tmp):
 
     mp_ = pytest.MonkeyPatch()
     emulate_kernels(mp_)
-    X, bins, init, K = _lloyd_case()
+    if mode == "multi_ranked":
+        mp_.setattr(clustering_ops, "EXACT_ORDER_MAX_POINTS", 0)  # the per-bin top-k path instead of numpy's argpartition
+    X, bins, init, K = _lloyd_case(multi=mode != "single")
     n = len(X)
     lo, hi = n * rank // world, n * (rank + 1) // world          # contiguous shard, as iteration ranges are
     centers = torch.from_numpy(np.concatenate(init).copy())
@@ -239,7 +241,7 @@ def _gloo_lloyd_worker(rank, world, port, tmp):
     dist.destroy_process_group()
 
 
-def _lloyd_case():
+def _lloyd_case(multi=False):
     rng = np.random.default_rng(21)
     nbins, K, D = 3, 5, 6
     Xs, bs, init = [], [], []
@@ -251,32 +253,40 @@ def _lloyd_case():
         c = m + rng.normal(0, 0.3, size=(K, D))
         if b == 1:
             c[3] = c[0]              # a duplicate centre: empty cluster -> relocation, candidates exchanged between ranks
+            if multi:
+                c[2] = c[0]          # two empty clusters in one model: the bin's two farthest points, over both ranks
         init.append(c)
     order = rng.permutation(900)
     return np.concatenate(Xs)[order], np.concatenate(bs)[order], init, K
 
 
-def test_sharded_lloyd_gloo_world2_matches_single_process(tmp_path, monkeypatch):
+@pytest.mark.parametrize("mode", ["single", "multi", "multi_ranked"])
+def test_sharded_lloyd_gloo_world2_matches_single_process(tmp_path, monkeypatch, mode):
     """Iteration-range sharded Lloyd (partial sums all-reduced, empty-cluster candidates all-gathered) equals the
-    single-process fit and the real sklearn KMeans per bin."""
+    single-process fit and the real sklearn KMeans per bin.  With several empty clusters in one model the relocated
+    centres may land on permuted cluster indices of that bin (clustering_ops._relocate_empty_clusters): compared as
+    sets of rows."""
     import torch
     import torch.multiprocessing as mp
     from sklearn.cluster import KMeans
 
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     port = 29500 + ((os.getpid() + 977) % 2000)
-    mp.spawn(_gloo_lloyd_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_gloo_lloyd_worker, args=(2, port, str(tmp_path), mode), nprocs=2, join=True)
     a, b = np.load(tmp_path / "centers_0.npy"), np.load(tmp_path / "centers_1.npy")
     assert np.array_equal(a, b)
+    canon = (lambda m: m) if mode == "single" else (lambda m: m[np.lexsort(m.T[::-1])])
     from cpu_emulation import emulate_kernels
     from msm_we_b200 import clustering_ops
 
     emulate_kernels(monkeypatch)
-    X, bins, init, K = _lloyd_case()
+    X, bins, init, K = _lloyd_case(multi=mode != "single")
     centers = torch.from_numpy(np.concatenate(init).copy())
     offs = torch.from_numpy(np.arange(0, (len(init) + 1) * K, K, dtype=np.int64))
     clustering_ops.lloyd_fit(torch.from_numpy(X), None, torch.from_numpy(bins), centers, offs, K, 4)
-    assert np.allclose(a, centers.numpy(), rtol=1e-12, atol=1e-13)
+    single = centers.numpy()
     for bb in range(len(init)):
+        sl = slice(bb * K, (bb + 1) * K)
+        assert np.allclose(canon(a[sl]), canon(single[sl]), rtol=1e-12, atol=1e-13), bb
         ref = KMeans(n_clusters=K, init=init[bb], n_init=1, max_iter=4, tol=0.0, algorithm="lloyd").fit(X[bins == bb]).cluster_centers_
-        assert np.allclose(a[bb * K:(bb + 1) * K], ref, rtol=1e-11, atol=1e-12), bb
+        assert np.allclose(canon(a[sl]), canon(ref), rtol=1e-11, atol=1e-12), bb
