@@ -19,7 +19,8 @@ are the all-reduce of the Lloyd partial sums (20.6 MB per Lloyd iteration) and o
 value  : frames/s of the whole job, inputs resident in HBM (CUDA events per step, inputs >> L2 and L2 flushed
          between steps, max over ranks);
 e2e    : the same pass through the public API (modelWE.lloyd_refine_clusters + launch_ray_discretization +
-         get_fluxMatrix) on HOST numpy buffers: every H2D / D2H copy is inside the timed region;
+         get_fluxMatrix) on HOST numpy buffers: every H2D / D2H copy is inside the timed region (each frame crosses
+         PCIe once per pass: the refinement leaves the rows it shipped on the device for the discretization);
 roofline: the dominant kernel (K1 of the final assignment) AND the whole step, against the measured HBM copy
          bandwidth and the cuBLAS DGEMM rate measured on this box;
 cpu_baseline / --impl reference: the reference's own CPU pattern on the host cores (sklearn KMeans Lloyd per WE
