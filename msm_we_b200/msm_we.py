@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import numpy as np
 
+from ._hamsm._analysis import AnalysisMixin
 from ._hamsm._clustering import ClusteringMixin
 from ._hamsm._data import ArrayIterationSource, DataMixin, H5IterationSource
 from ._hamsm._fluxmatrix import FluxMatrixMixin
@@ -61,7 +62,7 @@ class LinearCoordinates:
         return state
 
 
-class modelWE(ClusteringMixin, DataMixin, FluxMatrixMixin):
+class modelWE(ClusteringMixin, DataMixin, FluxMatrixMixin, AnalysisMixin):
     class BlockValidationError(Exception):
         pass
 
@@ -300,13 +301,9 @@ class modelWE(ClusteringMixin, DataMixin, FluxMatrixMixin):
     HOST_ANALYSIS_STEPS = ("get_Tmatrix", "get_steady_state", "get_steady_state_target_flux")
 
     def _host_analysis(self):
-        """Transition matrix / steady state / target flux are small host-side linear algebra the north star leaves on
-        the host; they live in the reference's AnalysisMixin, which can be mixed into this class unchanged (it reads
-        ``fluxMatrix``, ``indBasis``, ``indTargets``, ``nBins``).  Runs them when present; returns whether it did."""
+        """Transition matrix, steady state and target flux of the cleaned flux matrix: small host-side linear algebra
+        (``_hamsm/_analysis.py``; the north star keeps it on the host), in the reference's order (msm_we.py:812-841)."""
         for step in self.HOST_ANALYSIS_STEPS:
-            if not hasattr(self, step):
-                log.info(f"{step} is not part of msm_we_b200 (host-side analysis); stopping after the cleaned flux matrix")
-                return False
             getattr(self, step)()
         return True
 

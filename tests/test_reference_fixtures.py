@@ -170,7 +170,13 @@ def test_cleaning_block_validation_structures_match_reference_run(request, monke
     assert np.array_equal(model.sorted_centers, fx["o_sorted_centers"])
     assert model.cluster_mapping == {x: x for x in range(model.n_clusters + 2)}
 
-    # downstream (host linear algebra, reported check): transition matrix + steady state of OUR cleaned matrix
+    # downstream host linear algebra on OUR cleaned matrix: the package's own steps, and the oracle's restatement
+    model.get_Tmatrix()
+    model.get_steady_state()
+    model.get_steady_state_target_flux()
+    assert np.allclose(model.Tmatrix, fx["d_Tmatrix"], rtol=1e-10, atol=1e-300)
+    assert np.allclose(model.pSS, fx["d_pSS"], rtol=1e-6, atol=1e-12)
+    assert np.isclose(model.JtargetSS, float(fx["d_JtargetSS"]), rtol=1e-6, atol=0)
     T = O.transition_matrix(model.fluxMatrix, model.indBasis, model.indTargets)
     assert np.allclose(T, fx["d_Tmatrix"], rtol=1e-10, atol=1e-300)
     pss = O.steady_state(T)
@@ -182,6 +188,8 @@ def test_cleaning_block_validation_structures_match_reference_run(request, monke
         _close(vm.fluxMatrixRaw, fx[f"v{g}_fluxMatrixRaw"], f"validation group {g} fluxMatrixRaw")
         _close(vm.fluxMatrix, fx[f"v{g}_fluxMatrix"], f"validation group {g} fluxMatrix")
         assert int(vm.n_clusters) == int(fx[f"v{g}_n_clusters"])
+        assert np.isclose(vm.JtargetSS, float(fx[f"v{g}_JtargetSS"]), rtol=1e-6, atol=0)
+        assert np.allclose(vm.pSS, fx[f"v{g}_pSS"], rtol=1e-6, atol=1e-12)
         assert vm.iteration_source is model.iteration_source      # copies share the data set
 
     model.update_cluster_structures(build_pcoord_cache=True)
