@@ -452,9 +452,13 @@ def test_hamsm_driver_plugin_builds_the_reference_model(request, monkeypatch, gp
     assert sim.data_manager.closed and sim.data_manager.hamsm_model is model and driver.data_manager is sim.data_manager
     _check_clusters(model, fx, "o_")
     _close(model.fluxMatrix, fx["o_fluxMatrix"], "plugin-built cleaned fluxMatrix")
+    # what later WESTPA plugins read off the stored model (restart / optimization drivers): steady state + target flux
+    assert np.allclose(model.pSS, fx["d_pSS"], rtol=1e-6, atol=1e-12)
+    assert np.isclose(model.JtargetSS, float(fx["d_JtargetSS"]), rtol=1e-6, atol=0)
     assert len(model.validation_models) == 2
     for g, vm in enumerate(model.validation_models):
         _close(vm.fluxMatrix, fx[f"v{g}_fluxMatrix"], f"plugin validation group {g}")
+        assert np.isclose(vm.JtargetSS, float(fx[f"v{g}_JtargetSS"]), rtol=1e-6, atol=0)
 
 
 def test_dimreduce_refuses_methods_it_cannot_fit():
