@@ -378,6 +378,46 @@ def run_colour():
     print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB, counts {out['nm_cmatrix'].sum():.0f}")
 
 
+def run_feeder():
+    """The reference's own loader on a run spread over TWO west.h5 files (segments of an iteration concatenated in file
+    order, _data.py:807-993), a 2-D pcoord of which only the first dimension is loaded, ragged segment counts: what
+    ``load_iter_data`` / ``get_iter_coordinates`` / ``get_transition_data_lag0`` leave on the model."""
+    msm_we = refshim.load_reference()
+    _quiet()
+    its = FD.we_dataset(seed=31, n_iters=6, segs0=37, seg_growth=5, n_atoms=3, coord_ndim=3, bins_per_dim=4, k_true=2, pcoord_ndim=2)
+    cut = [int(len(d["weights"]) * 0.6) for d in its]
+    part = lambda d, sl: {k: v[sl] for k, v in d.items()}          # noqa: E731
+    refshim.register_we_file("feeder_a_west.h5", [part(d, slice(0, c)) for d, c in zip(its, cut)])
+    refshim.register_we_file("feeder_b_west.h5", [part(d, slice(c, None)) for d, c in zip(its, cut)])
+    msm_we.modelWE.processCoordinates = processCoordinates
+    model = msm_we.modelWE()
+    model.initialize(["feeder_a_west.h5", "feeder_b_west.h5"], {"coords": None, "nAtoms": 3, "coord_ndim": 3}, "feeder",
+                     basis_pcoord_bounds=[[0.0, 0.5]], target_pcoord_bounds=[[3.5, 1.0e6]], dim_reduce_method="none",
+                     tau=1.0, pcoord_ndim=1)
+    model.get_iterations()
+    out = FD.pack_iterations(its)
+    out.update(cut=np.array(cut, dtype=np.int64), maxIter=np.int64(model.maxIter),
+               numSegments=np.asarray(model.numSegments, dtype=np.float64))
+    lens, w, p0, p1, west, segind, child, pairs = [], [], [], [], [], [], [], []
+    for n in range(1, model.maxIter):
+        model.load_iter_data(n)
+        lens.append(model.nSeg)
+        w.append(np.asarray(model.weightList, dtype=np.float64))
+        p0.append(np.asarray(model.pcoord0List, dtype=np.float64).reshape(model.nSeg, -1))
+        p1.append(np.asarray(model.pcoord1List, dtype=np.float64).reshape(model.nSeg, -1))
+        west.append(np.asarray(model.westList, dtype=np.int64))
+        segind.append(np.asarray(model.segindList, dtype=np.int64))
+        child.append(np.asarray(model.get_iter_coordinates(n), dtype=np.float64))
+        model.get_transition_data_lag0()
+        pairs.append(np.asarray(model.coordPairList, dtype=np.float64))
+    out.update(f_lens=np.array(lens, dtype=np.int64), f_weights=_cat(w), f_pcoord0=np.concatenate(p0), f_pcoord1=np.concatenate(p1),
+               f_west=_cat(west, np.int64), f_segind=_cat(segind, np.int64), f_child=np.concatenate(child),
+               f_pairs=np.concatenate(pairs))
+    path = os.path.join(HERE, "ref_feeder_twofiles.npz")
+    np.savez_compressed(path, **out)
+    print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB; maxIter {model.maxIter}, segments {lens}")
+
+
 def main(which):
     if "pipeline1d" in which:
         its = FD.we_dataset(seed=11, n_iters=22, segs0=180, seg_growth=4, n_atoms=5, coord_ndim=3, bins_per_dim=8, k_true=3,
@@ -399,6 +439,8 @@ def main(which):
         run_pipeline("pipeline_voronoi", its, FD.boundaries(8), [[0.0, 0.5]], [[7.5, 1.0e6]], K=4, pcoord_ndim=1, n_atoms=4,
                      coord_ndim=3, cluster_kwargs={"random_state": 4242}, cluster_call_kwargs={"iters_to_use": list(range(1, 10))},
                      voronoi_centers=[[0.5], [1.5], [2.4], [3.6], [4.5], [5.5], [6.5], [7.5]])
+    if "feeder" in which:
+        run_feeder()
     if "predict_cfg2" in which:
         run_predict_cfg2()
     if "predict_ntl9" in which:
@@ -409,4 +451,4 @@ def main(which):
 
 if __name__ == "__main__":
     os.environ.setdefault("OMP_NUM_THREADS", "1")
-    main(sys.argv[1:] or ["pipeline1d", "pipeline2d", "pipeline_voronoi", "predict_cfg2", "predict_ntl9", "colour"])
+    main(sys.argv[1:] or ["pipeline1d", "pipeline2d", "pipeline_voronoi", "feeder", "predict_cfg2", "predict_ntl9", "colour"])

@@ -41,7 +41,18 @@ BIN_MAPPERS = {}  # name -> bin mapper returned by westpa.analysis.Run(name).ite
 
 # ---------------------------------------------------------------------------------------------- h5py
 class _Dataset(np.ndarray):
-    """ndarray with the two h5py.Dataset idioms the reference uses (``dset[:]``, ``dset["weight"]``)."""
+    """ndarray with the h5py.Dataset idioms the reference uses (``dset[:]``, ``dset["weight"]``) and
+    ``Dataset.read_direct`` with h5py's contract: the destination must be a C-contiguous, writable array and the two
+    selections (``numpy.s_`` outputs) must have the same shape."""
+
+    def read_direct(self, dest, source_sel=None, dest_sel=None):
+        if not (isinstance(dest, np.ndarray) and dest.flags.c_contiguous and dest.flags.writeable):
+            raise TypeError("Destination array must be C-contiguous and writable")
+        src = np.asarray(self)[source_sel if source_sel is not None else np.s_[...]]
+        view = dest[dest_sel if dest_sel is not None else np.s_[...]]
+        if view.shape != src.shape:
+            raise TypeError(f"Can't broadcast {src.shape} -> {view.shape}")
+        view[...] = src
 
 
 class FakeH5File:
