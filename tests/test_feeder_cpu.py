@@ -102,3 +102,65 @@ def test_source_errors(monkeypatch):
         H5IterationSource(["p_single_west.h5"]).get(1)          # start AND end structure are needed for a transition
     with pytest.raises(KeyError):
         H5IterationSource(["p_err_west.h5"]).get(17)
+
+
+BACKENDS = [pytest.param(False, id="host-logic-cpu"), pytest.param(True, id="cuda", marks=pytest.mark.gpu)]
+
+
+@pytest.mark.parametrize("gpu", BACKENDS)
+def test_nan_frames_direct_read_path_equals_staged_path(monkeypatch, gpu):
+    """A broken (NaN) structure: the reference zeroes that segment's weight in the flux pass (_data.py:302-313).  The
+    direct-read discretization finds such rows on the device (rows_with_nan) and hands them to the flux pass; the
+    staged path finds them on the host.  Both must give the same labels for the intact frames and the same flux matrix,
+    and the broken segments must not contribute."""
+    import torch
+
+    if gpu and not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    if not gpu:
+        from cpu_emulation import emulate_kernels
+
+        emulate_kernels(monkeypatch)
+    monkeypatch.setitem(sys.modules, "h5py", refshim.fake_h5py_module())
+    from msm_we_b200.binning import RectilinearBinMapper
+    from msm_we_b200.msm_we import modelWE
+    from msm_we_b200.stratified_clustering import StratifiedClusters
+
+    its = FD.we_dataset(seed=77, n_iters=7, segs0=60, seg_growth=2, n_atoms=3, coord_ndim=3, bins_per_dim=4, k_true=2)
+    broken = {2: [5, 17], 4: [0], 5: [33]}                       # iteration -> segments with a NaN end or start structure
+    for it, segs in broken.items():
+        for s in segs:
+            its[it - 1]["coords"][s, (s % 2), 1, 2] = np.nan      # start structure for odd s, end structure for even s
+    refshim.register_we_file("p_nan_west.h5", its)
+    rng = np.random.default_rng(3)
+    centres = [rng.normal(0, 3, size=(3, 9)) for _ in range(4)]
+    results = []
+    for user_featuriser in (False, True):
+        model = modelWE()
+        if user_featuriser:                                       # a monkey-patched featuriser: the staged path
+            model.processCoordinates = lambda c: np.asarray(c).reshape(np.shape(c)[0], -1)
+        model.initialize(["p_nan_west.h5"], {"coords": None, "nAtoms": 3, "coord_ndim": 3}, "nan",
+                         basis_pcoord_bounds=[[0.0, 0.5]], target_pcoord_bounds=[[3.5, 1.0e6]], dim_reduce_method="none",
+                         tau=1.0, pcoord_ndim=1)
+        model.get_iterations()
+        model.dimReduce()
+        clusters = StratifiedClusters(RectilinearBinMapper(FD.boundaries(4)), model, 3, [])
+        for b in range(4):
+            clusters.cluster_models[b].cluster_centers_ = centres[b].copy()
+        model.clusters = clusters
+        model.n_clusters = 12
+        model.launch_ray_discretization()
+        model.get_fluxMatrix(0, first_iter=1, last_iter=model.maxIter)
+        results.append((np.concatenate(model.pair_dtrajs), model.fluxMatrixRaw.copy(), model))
+    (pa, fa, ma), (pb, fb, mb) = results
+    offs = np.concatenate([[0], np.cumsum([len(d["weights"]) for d in its])])
+    bad = np.zeros(len(pa), dtype=bool)
+    for it, segs in broken.items():
+        bad[offs[it - 1] + np.array(segs)] = True
+    assert np.array_equal(pa[~bad[: len(pa)]], pb[~bad[: len(pb)]])
+    assert np.array_equal(fa, fb)
+    # the broken segments contribute nothing: total weight in the matrix == weight of the intact segments / nI
+    used = range(2, ma.maxIter)                                   # get_fluxMatrix covers first_iter + 1 .. last_iter - 1
+    total = sum(its[n - 1]["weights"][[s for s in range(len(its[n - 1]["weights"])) if s not in broken.get(n, [])]].sum()
+                for n in used)
+    assert abs(fa.sum() - total / len(used)) <= 1e-12 * total
