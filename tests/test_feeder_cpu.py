@@ -164,3 +164,53 @@ def test_nan_frames_direct_read_path_equals_staged_path(monkeypatch, gpu):
     total = sum(its[n - 1]["weights"][[s for s in range(len(its[n - 1]["weights"])) if s not in broken.get(n, [])]].sum()
                 for n in used)
     assert abs(fa.sum() - total / len(used)) <= 1e-12 * total
+
+
+@pytest.mark.parametrize("gpu", BACKENDS)
+def test_lloyd_refinement_from_hdf5_source_equals_array_source(monkeypatch, gpu):
+    """lloyd_refine_clusters stages rows of a source that does not own arrays (HDF5) through pinned buffers; same
+    refined centres as with the in-memory source, and the discretization that follows (direct-read path) is unaffected
+    by the rows the refinement left on the device."""
+    import torch
+
+    if gpu and not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    if not gpu:
+        from cpu_emulation import emulate_kernels
+
+        emulate_kernels(monkeypatch)
+    monkeypatch.setitem(sys.modules, "h5py", refshim.fake_h5py_module())
+    from msm_we_b200._hamsm._data import ArrayIterationSource, IterationRecord
+    from msm_we_b200.binning import RectilinearBinMapper
+    from msm_we_b200.msm_we import modelWE
+    from msm_we_b200.stratified_clustering import StratifiedClusters
+
+    its = FD.we_dataset(seed=91, n_iters=8, segs0=90, seg_growth=0, n_atoms=3, coord_ndim=3, bins_per_dim=4, k_true=2)
+    refshim.register_we_file("p_lloyd_west.h5", its)
+    arr = ArrayIterationSource()
+    for i, d in enumerate(its, start=1):
+        S = len(d["weights"])
+        arr.add(i, IterationRecord(d["pcoord"][:, 0], d["pcoord"][:, 1], d["weights"], d["coords"][:, 0].reshape(S, -1),
+                                   d["coords"][:, 1].reshape(S, -1)))
+    rng = np.random.default_rng(4)
+    centres = [rng.normal(0, 3, size=(3, 9)) for _ in range(4)]
+    out = []
+    for source in (["p_lloyd_west.h5"], arr):
+        model = modelWE()
+        model.initialize(source, {"coords": None, "nAtoms": 3, "coord_ndim": 3}, "lloyd", basis_pcoord_bounds=[[0.0, 0.5]],
+                         target_pcoord_bounds=[[3.5, 1.0e6]], dim_reduce_method="none", tau=1.0, pcoord_ndim=1)
+        model.get_iterations()
+        model.dimReduce()
+        clusters = StratifiedClusters(RectilinearBinMapper(FD.boundaries(4)), model, 3, [])
+        for b in range(4):
+            clusters.cluster_models[b].cluster_centers_ = centres[b].copy()
+        model.clusters = clusters
+        model.n_clusters = 12
+        n = model.lloyd_refine_clusters(3)
+        refined = np.concatenate([m.cluster_centers_ for m in clusters.cluster_models])
+        model.launch_ray_discretization()
+        assert model._resident_child_rows is None
+        out.append((n, refined, np.concatenate(model.pair_dtrajs)))
+    assert out[0][0] == out[1][0] > 0
+    assert np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[0][2], out[1][2])
